@@ -1,0 +1,287 @@
+"""ctypes wrapper around oracle/liboracle.so  --  TEST INFRASTRUCTURE ONLY.
+
+May be imported from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never from the shipped package.
+See oracle/oracle.c for what each function restates (reference file:line) and
+for the "parity unpinned" statement about the Open3D/Embree boundary.
+
+Also holds ``brute_f64_numpy``: an independent, pure-numpy float64
+Moeller-Trumbore closest hit used to validate the C oracle on small cases.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+EPS32 = float(2.0 ** -23)
+# tie margins as multiples of eps32 * (max |coordinate|): see DESIGN.md "tie classification"
+TAU_C = 16.0
+TAU_T_C = 1024.0
+GRAZE = 0.02
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with oracle/Makefile (gcc).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "--no-print-directory"],
+                              stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        i64, f64, f32, vp = C.c_int64, C.c_double, C.c_float, C.c_void_p
+        L.orc_heatmap_to_points_f64.restype = i64
+        L.orc_heatmap_to_points_f64.argtypes = [vp, i64, i64, f64, vp, vp, vp]
+        L.orc_heatmap_to_points_f32.restype = i64
+        L.orc_heatmap_to_points_f32.argtypes = [vp, i64, i64, f32, vp, vp, vp]
+        L.orc_compute_rays.restype = None
+        L.orc_compute_rays.argtypes = [vp, vp, i64, f64, f64, f64, f64, vp]
+        L.orc_rays_object_frame.restype = None
+        L.orc_rays_object_frame.argtypes = [vp, vp, i64, vp, vp]
+        L.orc_pose_vertices.restype = None
+        L.orc_pose_vertices.argtypes = [vp, i64, vp, vp]
+        L.orc_tri_test_f32.restype = C.c_int
+        L.orc_tri_test_f32.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_cast_brute_f32.restype = None
+        L.orc_cast_brute_f32.argtypes = [vp, vp, i64, vp, i64, vp, vp]
+        L.orc_bvh_build.restype = vp
+        L.orc_bvh_build.argtypes = [vp, i64, vp, i64]
+        L.orc_bvh_free.restype = None
+        L.orc_bvh_free.argtypes = [vp]
+        L.orc_bvh_num_nodes.restype = i64
+        L.orc_bvh_num_nodes.argtypes = [vp]
+        L.orc_cast_bvh_f32.restype = None
+        L.orc_cast_bvh_f32.argtypes = [vp, vp, i64, vp, vp]
+        L.orc_cast_f64.restype = None
+        L.orc_cast_f64.argtypes = [vp, vp, i64, f64, f64, f64, C.c_int, vp, vp, vp]
+        L.orc_eval_face_f64.restype = None
+        L.orc_eval_face_f64.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp, vp]
+        L.orc_accumulate.restype = None
+        L.orc_accumulate.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+        L.orc_project_frame_f32.restype = i64
+        L.orc_project_frame_f32.argtypes = [vp, vp, i64, i64, f32, vp, vp, vp, vp, vp, vp, vp]
+        L.orc_num_threads.restype = C.c_int
+        L.orc_num_threads.argtypes = []
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+# ------------------------------------------------------------------ H1 / H2 / H3
+def heatmap_to_points(heat, thr):
+    """-> xs int64[N], ys int64[N], I (heat dtype)[N]; restates src/defect_projection.py:165-179."""
+    heat = np.ascontiguousarray(heat)
+    H, W = heat.shape
+    if heat.dtype == np.float32:
+        fn, dt = lib().orc_heatmap_to_points_f32, np.float32
+    else:
+        heat = _c(heat, np.float64)
+        fn, dt = lib().orc_heatmap_to_points_f64, np.float64
+    n = fn(_p(heat), H, W, float(thr), None, None, None)
+    xs = np.empty(n, np.int64)
+    ys = np.empty(n, np.int64)
+    I = np.empty(n, dt)
+    fn(_p(heat), H, W, float(thr), _p(xs), _p(ys), _p(I))
+    return xs, ys, I
+
+
+def compute_rays(xs, ys, K):
+    """-> float64 [N,3] unit rays in the camera frame; restates :196-223."""
+    xs = _c(xs, np.int64)
+    ys = _c(ys, np.int64)
+    K = np.asarray(K, dtype=np.float64)
+    out = np.empty((len(xs), 3), np.float64)
+    lib().orc_compute_rays(_p(xs), _p(ys), len(xs), K[0, 0], K[1, 1], K[0, 2], K[1, 2], _p(out))
+    return out
+
+
+def frame_xform(K, pose):
+    """16 doubles: fx fy cx cy | Rinv row-major | tinv  for a model->camera pose."""
+    K = np.asarray(K, np.float64)
+    pose = np.asarray(pose, np.float64)
+    Rm, t = pose[:3, :3], pose[:3, 3]
+    Rinv = Rm.T
+    tinv = -(Rinv @ t)
+    return np.concatenate([[K[0, 0], K[1, 1], K[0, 2], K[1, 2]], Rinv.reshape(-1), tinv]).astype(np.float64)
+
+
+def rays_object_frame(xs, ys, xf):
+    xs = _c(xs, np.int64)
+    ys = _c(ys, np.int64)
+    xf = _c(xf, np.float64)
+    out = np.empty((len(xs), 6), np.float32)
+    lib().orc_rays_object_frame(_p(xs), _p(ys), len(xs), _p(xf), _p(out))
+    return out
+
+
+def rays6_camera(rays_f64):
+    """The float32 [N,6] tensor the reference builds at :247-251 (origin 0)."""
+    r = np.zeros((len(rays_f64), 6), np.float32)
+    r[:, 3:] = rays_f64.astype(np.float32)
+    return r
+
+
+def pose_vertices(V, T):
+    V = _c(V, np.float64)
+    T = _c(T, np.float64)
+    out = np.empty((len(V), 3), np.float32)
+    lib().orc_pose_vertices(_p(V), len(V), _p(T), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------ H4
+class Bvh:
+    def __init__(self, V, F):
+        self.V = _c(V, np.float32)
+        self.F = _c(F, np.int32)
+        self.h = lib().orc_bvh_build(_p(self.V), len(self.V), _p(self.F), len(self.F))
+        self.scale = float(np.abs(self.V).max()) if len(self.V) else 1.0
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_bvh_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def cast_f32(self, rays6):
+        rays6 = _c(rays6, np.float32)
+        n = len(rays6)
+        t = np.empty(n, np.float32)
+        f = np.empty(n, np.int32)
+        lib().orc_cast_bvh_f32(self.h, _p(rays6), n, _p(t), _p(f))
+        return t, f
+
+    def margins(self, rays6=None):
+        s = self.scale
+        if rays6 is not None and len(rays6):
+            s = max(s, float(np.abs(np.asarray(rays6)[:, :3]).max()))
+        return TAU_C * EPS32 * s, TAU_T_C * EPS32 * s
+
+    def cast_f64(self, rays6, brute=False, tau=None, tau_t=None, graze=GRAZE):
+        rays6 = _c(rays6, np.float32)
+        n = len(rays6)
+        a, b = self.margins(rays6)
+        tau = a if tau is None else tau
+        tau_t = b if tau_t is None else tau_t
+        t = np.empty(n, np.float64)
+        f = np.empty(n, np.int32)
+        tie = np.empty(n, np.uint8)
+        lib().orc_cast_f64(self.h, _p(rays6), n, tau, tau_t, graze, int(brute), _p(t), _p(f), _p(tie))
+        return t, f, tie
+
+    def eval_face(self, rays6, face, tau=None):
+        rays6 = _c(rays6, np.float32)
+        face = _c(face, np.int32)
+        n = len(rays6)
+        tau = self.margins(rays6)[0] if tau is None else tau
+        t = np.empty(n, np.float64)
+        m = np.empty(n, np.float64)
+        c = np.empty(n, np.float64)
+        lib().orc_eval_face_f64(_p(self.V), _p(self.F), _p(rays6), _p(face), n, tau, _p(t), _p(m), _p(c))
+        return t, m, c
+
+    def project_frame(self, heat, thr, K, want_acc=True):
+        """Whole frame on the CPU (all threads): the timed CPU baseline."""
+        heat = _c(heat, np.float32)
+        H, W = heat.shape
+        K = np.asarray(K, np.float64)
+        K4 = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], np.float64)
+        t = np.empty(H * W, np.float32)
+        f = np.empty(H * W, np.int32)
+        hist = np.zeros(len(self.F), np.int32) if want_acc else None
+        fmax = np.zeros(len(self.F), np.float32) if want_acc else None
+        vmax = np.zeros(len(self.V), np.float32) if want_acc else None
+        nh = C.c_int64(0)
+        n = lib().orc_project_frame_f32(self.h, _p(heat), H, W, float(thr), _p(K4), _p(t), _p(f),
+                                        _p(hist), _p(fmax), _p(vmax), C.byref(nh))
+        return dict(n=n, t=t[:n], face=f[:n], hist=hist, fmax=fmax, vmax=vmax, nhits=nh.value)
+
+
+def cast_brute_f32(V, F, rays6):
+    V = _c(V, np.float32)
+    F = _c(F, np.int32)
+    rays6 = _c(rays6, np.float32)
+    n = len(rays6)
+    t = np.empty(n, np.float32)
+    f = np.empty(n, np.int32)
+    lib().orc_cast_brute_f32(_p(V), _p(F), len(F), _p(rays6), n, _p(t), _p(f))
+    return t, f
+
+
+def tri_test_f32(ray6, v0, v1, v2):
+    ray6 = _c(ray6, np.float32)
+    v0, v1, v2 = (_c(v, np.float32) for v in (v0, v1, v2))
+    t = C.c_float(0)
+    hit = lib().orc_tri_test_f32(_p(ray6), _p(v0), _p(v1), _p(v2), C.byref(t))
+    return bool(hit), (float(t.value) if hit else float("inf"))
+
+
+def accumulate(face, I, F, nV):
+    face = _c(face, np.int32)
+    I = _c(I, np.float32)
+    F = _c(F, np.int32)
+    hist = np.zeros(len(F), np.int32)
+    fmax = np.zeros(len(F), np.float32)
+    vmax = np.zeros(nV, np.float32)
+    lib().orc_accumulate(_p(face), _p(I), len(face), _p(F), _p(hist), _p(fmax), _p(vmax))
+    return hist, fmax, vmax
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+# ------------------------------------------------------------------ independent numpy check
+def brute_f64_numpy(V, F, rays6, chunk=256):
+    """Pure-numpy float64 Moeller-Trumbore closest hit (min t, ties -> smaller face id).
+    O(N*F) memory-chunked; for validating the C oracle on small cases only."""
+    V = np.asarray(V, np.float32).astype(np.float64)
+    F = np.asarray(F, np.int64)
+    r = np.asarray(rays6, np.float32).astype(np.float64)
+    v0, v1, v2 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    e1, e2 = v1 - v0, v2 - v0
+    n = len(r)
+    tout = np.full(n, np.inf)
+    fout = np.full(n, -1, np.int32)
+    for s in range(0, n, chunk):
+        o = r[s:s + chunk, None, :3]
+        d = r[s:s + chunk, None, 3:]
+        P = np.cross(d, e2[None])
+        det = np.einsum("fk,nfk->nf", e1, P)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            T = o - v0[None]
+            u = np.einsum("nfk,nfk->nf", T, P) * inv
+            Q = np.cross(T, e1[None])
+            v = np.einsum("nfk,nfk->nf", np.broadcast_to(d, Q.shape), Q) * inv
+            t = np.einsum("fk,nfk->nf", e2, Q) * inv
+        ok = (det != 0) & (u >= 0) & (v >= 0) & (1.0 - u - v >= 0) & (t >= 0)
+        t = np.where(ok, t, np.inf)
+        j = np.argmin(t, axis=1)          # first minimum => smaller face id on ties
+        tt = t[np.arange(len(j)), j]
+        tout[s:s + chunk] = tt
+        fout[s:s + chunk] = np.where(np.isfinite(tt), j, -1)
+    return tout, fout
