@@ -1,0 +1,675 @@
+// C ABI of libdefectproj.so (see include/defectproj.h): context, buffers, call sequencing.
+#include "../../include/defectproj.h"
+#include "dp_internal.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace dp;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= cap) return cudaSuccess;
+        size_t want = need + need / 4 + 256;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, need);   // retry without head-room
+            want = need;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+}  // namespace
+
+struct dp_ctx {
+    int device = 0;
+    std::string err;
+
+    // mesh (object frame) and its camera-frame copy
+    DevBuf V, F, Vposed, V64, Vposed64;
+    int vdtype = 0;
+    int64_t nV = 0, nF = 0;
+    bool has_mesh = false, has_bvh = false, has_cam = false;
+
+    BvhStorage obj, cam;
+    DevBuf obj_nodes, obj_tris, obj_wlo, obj_whi, cam_nodes, cam_tris, cam_wlo, cam_whi, scales, tri_face;
+    Topology topo;
+    void *build_scratch = nullptr;
+    size_t build_scratch_bytes = 0;
+
+    // accumulators
+    DevBuf hist, fmax, vmax;
+
+    // per-call scratch
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, cscratch, counts, fcounts, xf, stats;
+    long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
+    bool stats_on = false;
+    dp_stats last_stats{};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timings_valid = false;
+    float build_ms = 0.f, refit_ms = 0.f;
+};
+
+namespace {
+
+int fail(dp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof(buf), "%s", what);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call, what)                                                      \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess)                                             \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? DP_E_NOMEM : DP_E_CUDA, what, e__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+BvhView view_of(const BvhStorage &b) { return BvhView{b.nodes, b.tris, b.d_scale}; }
+
+}  // namespace
+
+extern "C" {
+
+int dp_abi_version(void) { return DP_ABI_VERSION; }
+
+void dp_frame_xform(const double *K, const double *pose, double *xf)
+{
+    static const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const double *P = pose ? pose : ident;
+    xf[0] = K[0]; xf[1] = K[4]; xf[2] = K[2]; xf[3] = K[5];
+    // Rinv = R^T
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) xf[4 + 3 * r + c] = P[4 * c + r];
+    const double t0 = P[3], t1 = P[7], t2 = P[11];
+    for (int k = 0; k < 3; ++k) {
+        volatile double a = P[0 * 4 + k] * t0;
+        volatile double b = P[1 * 4 + k] * t1;
+        volatile double c = P[2 * 4 + k] * t2;
+        volatile double s = a + b;
+        s = s + c;
+        xf[13 + k] = (s == 0.0) ? 0.0 : -s;      // no negative zero: identity pose gives origin +0
+    }
+}
+
+int dp_create(int device, dp_ctx **out)
+{
+    if (!out) return fail(nullptr, DP_E_ARG, "dp_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DP_E_CUDA, "dp_create: no CUDA device (this library has no CPU fallback)", e);
+    if (device < 0 || device >= ndev) return fail(nullptr, DP_E_ARG, "dp_create: device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, DP_E_CUDA, "dp_create", e);
+    if (prop.major < 10)
+        return fail(nullptr, DP_E_CUDA, "dp_create: device is not sm_100 class; the kernels are built for sm_100a only");
+    dp_ctx *ctx = new (std::nothrow) dp_ctx;
+    if (!ctx) return fail(nullptr, DP_E_NOMEM, "dp_create: out of host memory");
+    ctx->device = device;
+    DeviceGuard g(device);
+    for (int i = 0; i < 8; ++i)
+        if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) { delete ctx; return fail(nullptr, DP_E_CUDA, "dp_create: event", e); }
+    if ((e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_counts), 64)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, DP_E_CUDA, "dp_create: pinned alloc", e);
+    }
+    if ((e = ctx->counts.ensure(64)) != cudaSuccess || (e = ctx->stats.ensure(sizeof(TraceStats))) != cudaSuccess ||
+        (e = ctx->scales.ensure(64)) != cudaSuccess) {
+        dp_destroy(ctx);
+        return fail(nullptr, DP_E_CUDA, "dp_create: alloc", e);
+    }
+    cudaMemset(ctx->scales.p, 0, 64);
+    *out = ctx;
+    return DP_OK;
+}
+
+void dp_destroy(dp_ctx *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
+                      &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face,
+                      &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
+                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
+                      &ctx->stats};
+    for (DevBuf *b : bufs) b->release();
+    if (ctx->build_scratch) cudaFree(ctx->build_scratch);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    delete ctx;
+}
+
+const char *dp_last_error(const dp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dp_synchronize(dp_ctx *ctx, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "dp_synchronize");
+    return DP_OK;
+}
+
+int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const int32_t *F, int64_t nF, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (nV < 0 || nF < 0 || (nV > 0 && !V) || (nF > 0 && !F) || (vdtype != DP_F32 && vdtype != DP_F64))
+        return fail(ctx, DP_E_ARG, "dp_set_mesh: bad arguments");
+    if (nF > 0x7fffffffLL / 4 || nV > 0x7fffffffLL / 4) return fail(ctx, DP_E_ARG, "dp_set_mesh: mesh too large");
+    if (mem == DP_HOST) {
+        for (int64_t i = 0; i < 3 * nF; ++i)
+            if (F[i] < 0 || F[i] >= nV) return fail(ctx, DP_E_ARG, "dp_set_mesh: face index out of range");
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nv = (size_t)(nV > 0 ? nV : 1), nf = (size_t)(nF > 0 ? nF : 1);
+    CK(ctx->V.ensure(nv * 12), "dp_set_mesh: V");
+    CK(ctx->F.ensure(nf * 12), "dp_set_mesh: F");
+    CK(ctx->Vposed.ensure(nv * 12), "dp_set_mesh: Vposed");
+    if (vdtype == DP_F64) {
+        CK(ctx->V64.ensure(nv * 24), "dp_set_mesh: V64");
+        CK(ctx->Vposed64.ensure(nv * 24), "dp_set_mesh: Vposed64");
+    }
+    CK(ctx->hist.ensure(nf * 4), "dp_set_mesh: hist");
+    CK(ctx->fmax.ensure(nf * 4), "dp_set_mesh: fmax");
+    CK(ctx->vmax.ensure(nv * 4), "dp_set_mesh: vmax");
+    const cudaMemcpyKind kind = mem == DP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (nV) {
+        if (vdtype == DP_F64) {
+            CK(cudaMemcpyAsync(ctx->V64.p, V, (size_t)nV * 24, kind, s), "dp_set_mesh: copy V");
+            CK(convert_f64_to_f32(ctx->V64.as<double>(), ctx->V.as<float>(), nV * 3, s), "dp_set_mesh: convert V");
+        } else {
+            CK(cudaMemcpyAsync(ctx->V.p, V, (size_t)nV * 12, kind, s), "dp_set_mesh: copy V");
+        }
+    }
+    if (nF) CK(cudaMemcpyAsync(ctx->F.p, F, (size_t)nF * 12, kind, s), "dp_set_mesh: copy F");
+    CK(cudaMemsetAsync(ctx->hist.p, 0, nf * 4, s), "dp_set_mesh: zero");
+    CK(cudaMemsetAsync(ctx->fmax.p, 0, nf * 4, s), "dp_set_mesh: zero");
+    CK(cudaMemsetAsync(ctx->vmax.p, 0, nv * 4, s), "dp_set_mesh: zero");
+    if (mem == DP_HOST) CK(cudaStreamSynchronize(s), "dp_set_mesh: sync");
+    ctx->nV = nV;
+    ctx->nF = nF;
+    ctx->vdtype = vdtype;
+    ctx->has_mesh = true;
+    ctx->has_bvh = ctx->has_cam = false;
+    return DP_OK;
+}
+
+int dp_build_bvh(dp_ctx *ctx, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_build_bvh: no mesh (call dp_set_mesh first)");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nf = (size_t)(ctx->nF > 0 ? ctx->nF : 1);
+    // a wide node is rooted at a binary node with > LEAF_MAX triangles; <= nF/2 + 1 of them
+    // can exist in the worst case of a degenerate chain, typically ~nF/5
+    const size_t cap_nodes = nf / 2 + 64;
+    CK(ctx->obj_nodes.ensure(cap_nodes * sizeof(WideNode)), "dp_build_bvh: nodes");
+    CK(ctx->obj_tris.ensure(nf * sizeof(TriRec)), "dp_build_bvh: tris");
+    CK(ctx->obj_wlo.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
+    CK(ctx->obj_whi.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
+    CK(ctx->tri_face.ensure(nf * 4), "dp_build_bvh: tri_face");
+    ctx->obj.nodes = ctx->obj_nodes.as<WideNode>();
+    ctx->obj.tris = ctx->obj_tris.as<TriRec>();
+    ctx->obj.wlo = ctx->obj_wlo.as<float>();
+    ctx->obj.whi = ctx->obj_whi.as<float>();
+    ctx->obj.cap_nodes = (int64_t)cap_nodes;
+    ctx->obj.d_scale = ctx->scales.as<float>();
+    ctx->topo.tri_face = ctx->tri_face.as<int32_t>();
+    ctx->has_bvh = ctx->has_cam = false;
+    CK(cudaEventRecord(ctx->ev[3], s), "dp_build_bvh");
+    cudaError_t e = build_lbvh(ctx->V.as<float>(), ctx->nV, ctx->F.as<int32_t>(), ctx->nF, ctx->obj, ctx->topo,
+                               &ctx->build_scratch, &ctx->build_scratch_bytes, nullptr, s);
+    if (e == cudaErrorInvalidValue) return fail(ctx, DP_E_STATE, "dp_build_bvh: hierarchy deeper than 126 levels");
+    CK(e, "dp_build_bvh");
+    CK(cudaEventRecord(ctx->ev[4], s), "dp_build_bvh");
+    CK(cudaEventSynchronize(ctx->ev[4]), "dp_build_bvh: kernels");
+    cudaEventElapsedTime(&ctx->build_ms, ctx->ev[3], ctx->ev[4]);
+    if (ctx->topo.n_levels > MAX_WIDE_DEPTH) return fail(ctx, DP_E_STATE, "dp_build_bvh: BVH too deep for the ray stack");
+    ctx->has_bvh = true;
+    return DP_OK;
+}
+
+int dp_pose_mesh(dp_ctx *ctx, const double *T, void *stream)
+{
+    if (!ctx || !T) return fail(ctx, DP_E_ARG, "dp_pose_mesh: bad arguments");
+    if (!ctx->has_bvh) return fail(ctx, DP_E_STATE, "dp_pose_mesh: no BVH (call dp_build_bvh first)");
+    if (T[12] != 0.0 || T[13] != 0.0 || T[14] != 0.0 || T[15] != 1.0)
+        return fail(ctx, DP_E_ARG, "dp_pose_mesh: last row of the transform must be 0 0 0 1");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nf = (size_t)(ctx->nF > 0 ? ctx->nF : 1);
+    const size_t cap_nodes = (size_t)ctx->obj.cap_nodes;
+    CK(ctx->cam_nodes.ensure((size_t)(ctx->obj.n_nodes + 1) * sizeof(WideNode)), "dp_pose_mesh: nodes");
+    CK(ctx->cam_tris.ensure(nf * sizeof(TriRec)), "dp_pose_mesh: tris");
+    CK(ctx->cam_wlo.ensure((size_t)(ctx->obj.n_nodes + 1) * 12), "dp_pose_mesh: boxes");
+    CK(ctx->cam_whi.ensure((size_t)(ctx->obj.n_nodes + 1) * 12), "dp_pose_mesh: boxes");
+    (void)cap_nodes;
+    ctx->cam.nodes = ctx->cam_nodes.as<WideNode>();
+    ctx->cam.tris = ctx->cam_tris.as<TriRec>();
+    ctx->cam.wlo = ctx->cam_wlo.as<float>();
+    ctx->cam.whi = ctx->cam_whi.as<float>();
+    ctx->cam.cap_nodes = ctx->obj.n_nodes + 1;
+    ctx->cam.d_scale = ctx->scales.as<float>() + 1;
+    CK(cudaEventRecord(ctx->ev[5], s), "dp_pose_mesh");
+    CK(pose_and_refit(ctx->vdtype == DP_F64 ? ctx->V64.p : ctx->V.p, ctx->vdtype, ctx->nV, ctx->F.as<int32_t>(), ctx->nF, T,
+                      ctx->Vposed.as<float>(), ctx->vdtype == DP_F64 ? ctx->Vposed64.as<double>() : nullptr, ctx->obj,
+                      ctx->cam, ctx->topo, s),
+       "dp_pose_mesh");
+    CK(cudaEventRecord(ctx->ev[6], s), "dp_pose_mesh");
+    ctx->has_cam = true;
+    ctx->refit_ms = -1.0f;   // resolved lazily by dp_get_stats
+    return DP_OK;
+}
+
+int dp_get_posed_vertices(dp_ctx *ctx, void *V, int vdtype, int mem, void *stream)
+{
+    if (!ctx || !V || (vdtype != DP_F32 && vdtype != DP_F64)) return fail(ctx, DP_E_ARG, "dp_get_posed_vertices: bad arguments");
+    if (!ctx->has_cam) return fail(ctx, DP_E_STATE, "dp_get_posed_vertices: dp_pose_mesh has not been called");
+    if (vdtype == DP_F64 && ctx->vdtype != DP_F64)
+        return fail(ctx, DP_E_STATE, "dp_get_posed_vertices: float64 output needs a mesh set with float64 vertices");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ctx->nV)
+        CK(cudaMemcpyAsync(V, vdtype == DP_F64 ? ctx->Vposed64.p : ctx->Vposed.p, (size_t)ctx->nV * (vdtype == DP_F64 ? 24 : 12),
+                           mem == DP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s),
+           "dp_get_posed_vertices");
+    if (mem == DP_HOST) CK(cudaStreamSynchronize(s), "dp_get_posed_vertices");
+    return DP_OK;
+}
+
+int dp_compute_rays(dp_ctx *ctx, const int32_t *xs, const int32_t *ys, int64_t n, const double *K, double *rays3, int mem,
+                    void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || !K || (n > 0 && (!xs || !ys || !rays3))) return fail(ctx, DP_E_ARG, "dp_compute_rays: bad arguments");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FrameXf xf;
+    dp_frame_xform(K, nullptr, xf.v);
+    const int32_t *dx = xs, *dy = ys;
+    double *dr = rays3;
+    if (mem == DP_HOST) {
+        CK(ctx->pixel.ensure((size_t)n * 8 + 16), "dp_compute_rays: xy");
+        CK(ctx->point.ensure((size_t)n * 24 + 16), "dp_compute_rays: rays");
+        CK(cudaMemcpyAsync(ctx->pixel.p, xs, (size_t)n * 4, cudaMemcpyHostToDevice, s), "dp_compute_rays: H2D");
+        CK(cudaMemcpyAsync(ctx->pixel.as<int32_t>() + n, ys, (size_t)n * 4, cudaMemcpyHostToDevice, s), "dp_compute_rays: H2D");
+        dx = ctx->pixel.as<int32_t>();
+        dy = dx + n;
+        dr = ctx->point.as<double>();
+    }
+    CK(launch_compute_rays(dx, dy, n, xf, dr, s), "dp_compute_rays: launch");
+    if (mem == DP_HOST) {
+        CK(cudaMemcpyAsync(rays3, dr, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_compute_rays: D2H");
+        CK(cudaStreamSynchronize(s), "dp_compute_rays: kernel");
+    }
+    return DP_OK;
+}
+
+int dp_compact(dp_ctx *ctx, const void *heat, int dtype, int64_t nframes, int H, int W, double thr, uint32_t *pixel,
+               float *intensity, int64_t cap, int64_t *n, int64_t *frame_count, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (nframes < 0 || H < 0 || W < 0 || cap < 0 || !n || (dtype != DP_F32 && dtype != DP_F64))
+        return fail(ctx, DP_E_ARG, "dp_compact: bad arguments");
+    const int64_t frame_elems = (int64_t)H * W, n_elems = nframes * frame_elems;
+    if (n_elems > 0 && !heat) return fail(ctx, DP_E_ARG, "dp_compact: heat is NULL");
+    if (n_elems > 0xffffffffLL) return fail(ctx, DP_E_ARG, "dp_compact: more than 2^32 pixels in one batch");
+    if (cap > 0 && !pixel) return fail(ctx, DP_E_ARG, "dp_compact: pixel is NULL");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == DP_F64 ? 8 : 4;
+    const void *d_heat = heat;
+    uint32_t *d_pixel = pixel;
+    float *d_int = intensity;
+    if (mem == DP_HOST) {
+        CK(ctx->heat.ensure((size_t)n_elems * esz + 16), "dp_compact: heat");
+        CK(ctx->pixel.ensure((size_t)cap * 4 + 16), "dp_compact: pixel");
+        if (intensity) CK(ctx->inten.ensure((size_t)cap * 4 + 16), "dp_compact: intensity");
+        if (n_elems) CK(cudaMemcpyAsync(ctx->heat.p, heat, (size_t)n_elems * esz, cudaMemcpyHostToDevice, s), "dp_compact: H2D");
+        d_heat = ctx->heat.p;
+        d_pixel = ctx->pixel.as<uint32_t>();
+        d_int = intensity ? ctx->inten.as<float>() : nullptr;
+    }
+    CK(ctx->cscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_compact: scratch");
+    long long *d_fc = nullptr;
+    if (frame_count && nframes > 0) {
+        CK(ctx->fcounts.ensure((size_t)nframes * 8), "dp_compact: frame counts");
+        d_fc = ctx->fcounts.as<long long>();
+    }
+    CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap, ctx->cscratch.as<unsigned long long>(),
+                      ctx->counts.as<long long>(), d_fc, nframes, s),
+       "dp_compact: launch");
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, 8, cudaMemcpyDeviceToHost, s), "dp_compact: count");
+    CK(cudaStreamSynchronize(s), "dp_compact: kernel");
+    const int64_t total = ctx->h_counts[0];
+    *n = total;
+    const int64_t ncopy = total < cap ? total : cap;
+    if (mem == DP_HOST && ncopy > 0) {
+        CK(cudaMemcpyAsync(pixel, d_pixel, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, s), "dp_compact: D2H");
+        if (intensity) CK(cudaMemcpyAsync(intensity, d_int, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, s), "dp_compact: D2H");
+    }
+    if (d_fc) CK(cudaMemcpyAsync(frame_count, d_fc, (size_t)nframes * 8, cudaMemcpyDeviceToHost, s), "dp_compact: D2H");
+    CK(cudaStreamSynchronize(s), "dp_compact: D2H");
+    if (total > cap) return fail(ctx, DP_E_NOMEM, "dp_compact: capacity too small for the selected pixels");
+    return DP_OK;
+}
+
+int dp_cast_rays(dp_ctx *ctx, int frame, const float *rays6, int64_t n, float *t_hit, int32_t *face, int mem,
+                 void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || (n > 0 && (!rays6 || !t_hit))) return fail(ctx, DP_E_ARG, "dp_cast_rays: bad arguments");
+    if (frame == DP_FRAME_OBJECT ? !ctx->has_bvh : !ctx->has_cam)
+        return fail(ctx, DP_E_STATE, "dp_cast_rays: no BVH for the requested frame");
+    if (frame != DP_FRAME_OBJECT && frame != DP_FRAME_CAMERA) return fail(ctx, DP_E_ARG, "dp_cast_rays: bad frame");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float *d_rays = rays6;
+    float *d_t = t_hit;
+    int32_t *d_f = face;
+    if (mem == DP_HOST) {
+        CK(ctx->rays6.ensure((size_t)n * 24), "dp_cast_rays: rays");
+        CK(ctx->t_hit.ensure((size_t)n * 4), "dp_cast_rays: t");
+        CK(ctx->face.ensure((size_t)n * 4), "dp_cast_rays: face");
+        CK(cudaMemcpyAsync(ctx->rays6.p, rays6, (size_t)n * 24, cudaMemcpyHostToDevice, s), "dp_cast_rays: H2D");
+        d_rays = ctx->rays6.as<float>();
+        d_t = ctx->t_hit.as<float>();
+        d_f = ctx->face.as<int32_t>();
+    }
+    TraceStats *st = nullptr;
+    if (ctx->stats_on) {
+        CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TraceStats), s), "dp_cast_rays: stats");
+        st = ctx->stats.as<TraceStats>();
+    }
+    const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
+    CK(launch_trace_rays6(view_of(b), d_rays, n, d_t, d_f, st, s), "dp_cast_rays: launch");
+    if (mem == DP_HOST) {
+        CK(cudaMemcpyAsync(t_hit, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_cast_rays: D2H");
+        if (face) CK(cudaMemcpyAsync(face, d_f, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_cast_rays: D2H");
+        CK(cudaStreamSynchronize(s), "dp_cast_rays: kernel");
+    }
+    return DP_OK;
+}
+
+int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nframes, int H, int W, double thr,
+               const double *K, int64_t nK, const double *pose, int accumulate, dp_rays_out *out, int64_t *n_rays,
+               int64_t *n_hits, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (nframes < 0 || H < 0 || W < 0 || !K || (nK != 1 && nK != nframes) || (dtype != DP_F32 && dtype != DP_F64))
+        return fail(ctx, DP_E_ARG, "dp_project: bad arguments");
+    if (frame != DP_FRAME_OBJECT && frame != DP_FRAME_CAMERA) return fail(ctx, DP_E_ARG, "dp_project: bad frame");
+    if (frame == DP_FRAME_OBJECT && !pose && nframes > 0) return fail(ctx, DP_E_ARG, "dp_project: pose is NULL");
+    if (frame == DP_FRAME_OBJECT ? !ctx->has_bvh : !ctx->has_cam)
+        return fail(ctx, DP_E_STATE, "dp_project: no BVH for the requested frame (dp_build_bvh / dp_pose_mesh)");
+    const int64_t frame_elems = (int64_t)H * W, n_elems = nframes * frame_elems;
+    if (n_elems > 0 && !heat) return fail(ctx, DP_E_ARG, "dp_project: heat is NULL");
+    if (n_elems > 0xffffffffLL) return fail(ctx, DP_E_ARG, "dp_project: more than 2^32 pixels in one batch");
+    if (mem == DP_HOST && !n_rays && out && (out->pixel || out->intensity || out->t_hit || out->face || out->point || out->point64))
+        return fail(ctx, DP_E_ARG, "dp_project: host outputs need n_rays (the call must synchronise)");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    const bool want_pix = out && out->pixel, want_int = out && out->intensity, want_t = out && out->t_hit,
+               want_face = out && out->face, want_pt = out && out->point, want_p64 = out && out->point64;
+    int64_t cap = n_elems;
+    if (out && (want_pix || want_int || want_t || want_face || want_pt || want_p64)) {
+        if (out->cap < 0) return fail(ctx, DP_E_ARG, "dp_project: negative capacity");
+        if (out->cap < cap) cap = out->cap;
+    }
+
+    // per-frame constants
+    std::vector<FrameXf> hxf((size_t)(nframes > 0 ? nframes : 1));
+    for (int64_t f = 0; f < nframes; ++f)
+        dp_frame_xform(K + 9 * (nK == 1 ? 0 : f), frame == DP_FRAME_OBJECT ? pose + 16 * f : nullptr, hxf[f].v);
+    CK(ctx->xf.ensure(hxf.size() * sizeof(FrameXf)), "dp_project: xf");
+    if (nframes) CK(cudaMemcpyAsync(ctx->xf.p, hxf.data(), (size_t)nframes * sizeof(FrameXf), cudaMemcpyHostToDevice, s), "dp_project: xf");
+
+    const size_t esz = dtype == DP_F64 ? 8 : 4;
+    const void *d_heat = heat;
+    CK(cudaEventRecord(ctx->ev[0], s), "dp_project");
+    if (mem == DP_HOST) {
+        CK(ctx->heat.ensure((size_t)n_elems * esz + 16), "dp_project: heat");
+        if (n_elems) CK(cudaMemcpyAsync(ctx->heat.p, heat, (size_t)n_elems * esz, cudaMemcpyHostToDevice, s), "dp_project: H2D");
+        d_heat = ctx->heat.p;
+    }
+    // ray buffers: the caller's (device) or ours
+    uint32_t *d_pixel;
+    float *d_int, *d_t = nullptr, *d_pt = nullptr;
+    double *d_p64 = nullptr;
+    int32_t *d_face = nullptr;
+    const bool own = (mem == DP_HOST);
+    if (own || !want_pix) { CK(ctx->pixel.ensure((size_t)cap * 4 + 16), "dp_project: pixel"); d_pixel = ctx->pixel.as<uint32_t>(); }
+    else d_pixel = out->pixel;
+    if (own || !want_int) { CK(ctx->inten.ensure((size_t)cap * 4 + 16), "dp_project: intensity"); d_int = ctx->inten.as<float>(); }
+    else d_int = out->intensity;
+    if (want_t) { if (own) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); } else d_t = out->t_hit; }
+    if (want_face) { if (own) { CK(ctx->face.ensure((size_t)cap * 4 + 16), "dp_project: face"); d_face = ctx->face.as<int32_t>(); } else d_face = out->face; }
+    if (want_p64) { if (own) { CK(ctx->point64.ensure((size_t)cap * 24 + 16), "dp_project: point64"); d_p64 = ctx->point64.as<double>(); } else d_p64 = out->point64; }
+    if (want_pt) { if (own) { CK(ctx->point.ensure((size_t)cap * 12 + 16), "dp_project: point"); d_pt = ctx->point.as<float>(); } else d_pt = out->point; }
+
+    CK(ctx->cscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_project: scratch");
+    long long *d_counts = ctx->counts.as<long long>();
+    CK(cudaMemsetAsync(d_counts, 0, 16, s), "dp_project: counts");
+    CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
+                      ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s),
+       "dp_project: compaction");
+    CK(cudaEventRecord(ctx->ev[1], s), "dp_project");
+
+    TraceStats *st = nullptr;
+    if (ctx->stats_on) {
+        CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TraceStats), s), "dp_project: stats");
+        st = ctx->stats.as<TraceStats>();
+    }
+    Accum acc{ctx->hist.as<int32_t>(), ctx->fmax.as<uint32_t>(), ctx->vmax.as<uint32_t>(), ctx->F.as<int32_t>()};
+    const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
+    CK(launch_trace_pixels(view_of(b), d_pixel, d_int, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_t, d_face,
+                           d_pt, d_p64, accumulate ? &acc : nullptr, d_counts + 1, st, s),
+       "dp_project: traversal");
+    CK(cudaEventRecord(ctx->ev[2], s), "dp_project");
+    ctx->timings_valid = true;
+
+    if (n_rays || n_hits) {
+        CK(cudaMemcpyAsync(ctx->h_counts, d_counts, 16, cudaMemcpyDeviceToHost, s), "dp_project: counts");
+        CK(cudaStreamSynchronize(s), "dp_project: kernels");
+        const int64_t total = ctx->h_counts[0];
+        if (n_rays) *n_rays = total;
+        if (n_hits) *n_hits = ctx->h_counts[1];
+        const int64_t nc = total < cap ? total : cap;
+        if (own && nc > 0) {
+            if (want_pix) CK(cudaMemcpyAsync(out->pixel, d_pixel, (size_t)nc * 4, cudaMemcpyDeviceToHost, s), "dp_project: D2H");
+            if (want_int) CK(cudaMemcpyAsync(out->intensity, d_int, (size_t)nc * 4, cudaMemcpyDeviceToHost, s), "dp_project: D2H");
+            if (want_t) CK(cudaMemcpyAsync(out->t_hit, d_t, (size_t)nc * 4, cudaMemcpyDeviceToHost, s), "dp_project: D2H");
+            if (want_face) CK(cudaMemcpyAsync(out->face, d_face, (size_t)nc * 4, cudaMemcpyDeviceToHost, s), "dp_project: D2H");
+            if (want_pt) CK(cudaMemcpyAsync(out->point, d_pt, (size_t)nc * 12, cudaMemcpyDeviceToHost, s), "dp_project: D2H");
+            if (want_p64) CK(cudaMemcpyAsync(out->point64, d_p64, (size_t)nc * 24, cudaMemcpyDeviceToHost, s), "dp_project: D2H");
+            CK(cudaStreamSynchronize(s), "dp_project: D2H");
+        }
+        if (total > cap) return fail(ctx, DP_E_NOMEM, "dp_project: output capacity too small for the selected pixels");
+    }
+    return DP_OK;
+}
+
+int dp_accum_reset(dp_ctx *ctx, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_reset: no mesh");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ctx->nF) {
+        CK(cudaMemsetAsync(ctx->hist.p, 0, (size_t)ctx->nF * 4, s), "dp_accum_reset");
+        CK(cudaMemsetAsync(ctx->fmax.p, 0, (size_t)ctx->nF * 4, s), "dp_accum_reset");
+    }
+    if (ctx->nV) CK(cudaMemsetAsync(ctx->vmax.p, 0, (size_t)ctx->nV * 4, s), "dp_accum_reset");
+    return DP_OK;
+}
+
+int dp_accum_get(dp_ctx *ctx, int32_t *hist, float *fmax, float *vmax, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_get: no mesh");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const cudaMemcpyKind kind = mem == DP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (hist && ctx->nF) CK(cudaMemcpyAsync(hist, ctx->hist.p, (size_t)ctx->nF * 4, kind, s), "dp_accum_get");
+    if (fmax && ctx->nF) CK(cudaMemcpyAsync(fmax, ctx->fmax.p, (size_t)ctx->nF * 4, kind, s), "dp_accum_get");
+    if (vmax && ctx->nV) CK(cudaMemcpyAsync(vmax, ctx->vmax.p, (size_t)ctx->nV * 4, kind, s), "dp_accum_get");
+    if (mem == DP_HOST) CK(cudaStreamSynchronize(s), "dp_accum_get");
+    return DP_OK;
+}
+
+int dp_accum_device_ptrs(dp_ctx *ctx, int32_t **hist, float **fmax, float **vmax)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_device_ptrs: no mesh");
+    if (hist) *hist = ctx->hist.as<int32_t>();
+    if (fmax) *fmax = ctx->fmax.as<float>();
+    if (vmax) *vmax = ctx->vmax.as<float>();
+    return DP_OK;
+}
+
+int dp_set_stats(dp_ctx *ctx, int enable)
+{
+    if (!ctx) return DP_E_ARG;
+    ctx->stats_on = enable != 0;
+    return DP_OK;
+}
+
+int dp_get_stats(dp_ctx *ctx, dp_stats *out)
+{
+    if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_get_stats: bad arguments");
+    DeviceGuard g(ctx->device);
+    CK(cudaDeviceSynchronize(), "dp_get_stats");
+    TraceStats st{};
+    CK(cudaMemcpy(&st, ctx->stats.p, sizeof(st), cudaMemcpyDeviceToHost), "dp_get_stats");
+    memset(out, 0, sizeof(*out));
+    out->rays = (int64_t)st.rays;
+    out->hits = (int64_t)st.hits;
+    out->nodes_fetched = (int64_t)st.nodes;
+    out->tris_tested = (int64_t)st.tris;
+    out->n_wide_nodes = ctx->has_bvh ? ctx->obj.n_nodes : 0;
+    out->n_tris = ctx->has_bvh ? ctx->obj.n_tris : 0;
+    out->wide_depth = ctx->has_bvh ? ctx->topo.n_levels : 0;
+    out->last_build_ms = ctx->build_ms;
+    if (ctx->has_cam && ctx->refit_ms < 0.0f) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->refit_ms = ms;
+    }
+    out->last_refit_ms = ctx->refit_ms < 0.0f ? 0.0f : ctx->refit_ms;
+    return DP_OK;
+}
+
+int dp_last_timings(dp_ctx *ctx, float *ms3)
+{
+    if (!ctx || !ms3) return fail(ctx, DP_E_ARG, "dp_last_timings: bad arguments");
+    if (!ctx->timings_valid) return fail(ctx, DP_E_STATE, "dp_last_timings: no dp_project call yet");
+    DeviceGuard g(ctx->device);
+    CK(cudaEventSynchronize(ctx->ev[2]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms3[0], ctx->ev[0], ctx->ev[1]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms3[1], ctx->ev[1], ctx->ev[2]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms3[2], ctx->ev[0], ctx->ev[2]), "dp_last_timings");
+    return DP_OK;
+}
+
+int dp_debug_dump_bvh(dp_ctx *ctx, int frame, void *nodes, int64_t *n_nodes, void *tris, int64_t *n_tris)
+{
+    if (!ctx) return DP_E_ARG;
+    if (frame == DP_FRAME_OBJECT ? !ctx->has_bvh : !ctx->has_cam) return fail(ctx, DP_E_STATE, "dp_debug_dump_bvh: no BVH");
+    DeviceGuard g(ctx->device);
+    const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
+    CK(cudaDeviceSynchronize(), "dp_debug_dump_bvh");
+    if (n_nodes) *n_nodes = b.n_nodes;
+    if (n_tris) *n_tris = b.n_tris;
+    if (nodes) CK(cudaMemcpy(nodes, b.nodes, (size_t)b.n_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost), "dp_debug_dump_bvh");
+    if (tris && b.n_tris) CK(cudaMemcpy(tris, b.tris, (size_t)b.n_tris * sizeof(TriRec), cudaMemcpyDeviceToHost), "dp_debug_dump_bvh");
+    return DP_OK;
+}
+
+int dp_debug_radix_sort(dp_ctx *ctx, uint32_t *keys, uint32_t *vals, int64_t n)
+{
+    if (!ctx || n < 0 || (n > 0 && (!keys || !vals))) return fail(ctx, DP_E_ARG, "dp_debug_radix_sort: bad arguments");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    DevBuf k, v, kt, vt, tb;
+    cudaError_t e = cudaSuccess;
+    if ((e = k.ensure((size_t)n * 4)) == cudaSuccess && (e = v.ensure((size_t)n * 4)) == cudaSuccess &&
+        (e = kt.ensure((size_t)n * 4)) == cudaSuccess && (e = vt.ensure((size_t)n * 4)) == cudaSuccess &&
+        (e = tb.ensure(radix_table_entries(n) * 4)) == cudaSuccess) {
+        bool in_tmp = false;
+        if ((e = cudaMemcpy(k.p, keys, (size_t)n * 4, cudaMemcpyHostToDevice)) == cudaSuccess &&
+            (e = cudaMemcpy(v.p, vals, (size_t)n * 4, cudaMemcpyHostToDevice)) == cudaSuccess &&
+            (e = radix_sort_pairs(k.as<uint32_t>(), v.as<uint32_t>(), kt.as<uint32_t>(), vt.as<uint32_t>(), n,
+                                  tb.as<uint32_t>(), nullptr, &in_tmp)) == cudaSuccess &&
+            (e = cudaDeviceSynchronize()) == cudaSuccess) {
+            e = cudaMemcpy(keys, in_tmp ? kt.p : k.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(vals, in_tmp ? vt.p : v.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        }
+    }
+    k.release(); v.release(); kt.release(); vt.release(); tb.release();
+    CK(e, "dp_debug_radix_sort");
+    return DP_OK;
+}
+
+int dp_debug_morton(dp_ctx *ctx, uint32_t *codes)
+{
+    if (!ctx || !codes) return fail(ctx, DP_E_ARG, "dp_debug_morton: bad arguments");
+    if (!ctx->has_bvh) return fail(ctx, DP_E_STATE, "dp_debug_morton: no BVH");
+    DeviceGuard g(ctx->device);
+    cudaError_t e = build_lbvh(ctx->V.as<float>(), ctx->nV, ctx->F.as<int32_t>(), ctx->nF, ctx->obj, ctx->topo,
+                               &ctx->build_scratch, &ctx->build_scratch_bytes, codes, nullptr);
+    CK(e, "dp_debug_morton");
+    CK(cudaDeviceSynchronize(), "dp_debug_morton");
+    ctx->has_cam = false;
+    return DP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,713 @@
+// Subsystem (3): BVH construction on the GPU.
+//
+// Replaces RaycastingScene().add_triangles (/root/reference/src/defect_projection.py:253-254,
+// Embree's rtcCommitScene on the host) and the mesh re-posing of :549-550 (float64 transform,
+// then the float32 cast of from_legacy, :245).
+//
+//   scene bounds -> 30-bit Morton codes of the triangle-box centres -> in-house LSD radix sort
+//   (4 x 8 bits, stable, key + triangle index) -> Karras 2012 binary hierarchy (duplicate codes
+//   disambiguated by the index) -> bottom-up binary boxes -> top-down, surface-area-guided
+//   collapse into 8-wide nodes with <= 3 triangles per leaf slot, children placed in the slot
+//   whose octant matches their direction from the node centre -> bottom-up fit that quantises
+//   the child boxes to 8 bits per plane (conservatively, in double precision).
+//
+// The same bottom-up fit is the refit used after dp_pose_mesh: the topology (meta bytes, child
+// and triangle bases) is shared, only boxes and triangle records are recomputed.
+#include "dp_internal.cuh"
+
+#include <math.h>
+
+namespace dp {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ void tri_box(const float *__restrict__ V, const int32_t *__restrict__ F, long long f,
+                                        float lo[3], float hi[3])
+{
+    const long long a = F[3 * f], b = F[3 * f + 1], c = F[3 * f + 2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = V[3 * a + k], y = V[3 * b + k], z = V[3 * c + k];
+        lo[k] = fminf(x, fminf(y, z));
+        hi[k] = fmaxf(x, fmaxf(y, z));
+    }
+}
+
+// bounds_u[0..2] = min (ordered uint), [3..5] = max, [6] = max |coordinate| (float bits)
+__global__ void k_scene_bounds(const float *__restrict__ V, const int32_t *__restrict__ F, long long n,
+                               unsigned *bounds_u)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (i < n) tri_box(V, F, i, lo, hi);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned mn = __reduce_min_sync(0xffffffffu, f2ord(lo[k]));
+        const unsigned mx = __reduce_max_sync(0xffffffffu, f2ord(hi[k]));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&bounds_u[k], mn);
+            atomicMax(&bounds_u[3 + k], mx);
+        }
+    }
+}
+
+__global__ void k_finish_bounds(const unsigned *bounds_u, float *sbounds, float *d_scale, long long n)
+{
+    float s = 0.0f;
+    for (int k = 0; k < 6; ++k) {
+        float v = n > 0 ? ord2f(bounds_u[k]) : 0.0f;
+        sbounds[k] = v;
+        s = fmaxf(s, fabsf(v));
+    }
+    *d_scale = s;
+}
+
+__device__ __forceinline__ unsigned expand10(unsigned v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+// code = interleave(x,y,z), x most significant; cell = min(1023, (c - lo) * (1024/ext))
+__global__ void k_morton(const float *__restrict__ V, const int32_t *__restrict__ F, long long n,
+                         const float *__restrict__ sbounds, uint32_t *keys, uint32_t *vals)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lo[3], hi[3];
+    tri_box(V, F, i, lo, hi);
+    unsigned q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float c = __fmul_rn(0.5f, __fadd_rn(lo[k], hi[k]));
+        const float ext = __fsub_rn(sbounds[3 + k], sbounds[k]);
+        float g = 0.0f;
+        if (ext > 0.0f) g = __fmul_rn(__fsub_rn(c, sbounds[k]), __fdiv_rn(1024.0f, ext));
+        g = fminf(fmaxf(g, 0.0f), 1023.0f);
+        q[k] = (unsigned)g;
+    }
+    keys[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------
+// LSD radix sort, 8 bits per pass, stable.  Tile = 256 threads x 16 keys; every warp owns a
+// contiguous 512-key slice of the tile so that warp-local ranks (match_any) are stable.
+// ------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const uint32_t *__restrict__ keys, long long n, int shift, uint32_t *__restrict__ table, int nblocks)
+{
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    table[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of table[0..m) in place, single block
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *table, long long m)
+{
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < m; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned x = i < m ? table[i] : 0u;
+        unsigned inc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned w = s_warp[lane];
+            unsigned winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += y;
+            }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const unsigned carry = s_carry;
+        if (i < m) table[i] = carry + s_warp[warp] + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t *__restrict__ keys_out,
+             uint32_t *__restrict__ vals_out, long long n, int shift, const uint32_t *__restrict__ table, int nblocks)
+{
+    __shared__ unsigned cnt[RS_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < RS_WARPS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * RS_TILE + (long long)warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS];
+    unsigned short rank[RS_ITEMS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = base + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys[i] : 0u;
+        val[r] = ok ? vals[i] : 0u;
+        const unsigned digit = ok ? ((key[r] >> shift) & 0xffu) : (0x100u | (unsigned)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        unsigned pre = 0;
+        if (ok) pre = cnt[warp][digit];
+        __syncwarp();
+        rank[r] = (unsigned short)(pre + __popc(peers & lt));
+        if (ok && lane == (31 - __clz(peers))) cnt[warp][digit] = pre + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // thread d turns the per-warp counts of digit d into starting offsets
+        unsigned run = table[(long long)tid * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const unsigned c = cnt[w][tid];
+            cnt[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = base + r * 32 + lane;
+        if (i < n) {
+            const unsigned digit = (key[r] >> shift) & 0xffu;
+            const unsigned pos = cnt[warp][digit] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Karras 2012.  Node ids: internal i in [0, n-1), leaf j -> (n-1) + j.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t *__restrict__ keys, long long n, long long i, long long j)
+{
+    if (j < 0 || j >= n) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((unsigned)(i ^ j));
+    return __clz(a ^ b);
+}
+
+__global__ void k_karras(const uint32_t *__restrict__ keys, long long n, int32_t *left, int32_t *right,
+                         int32_t *parent, int32_t *first, int32_t *last)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    long long lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    long long l = 0;
+    for (long long t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const long long j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    long long s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const long long gamma = i + s * d + (d < 0 ? -1 : 0);
+    const long long lo = i < j ? i : j, hi = i < j ? j : i;
+    const int32_t lc = (int32_t)((lo == gamma) ? (n - 1) + gamma : gamma);
+    const int32_t rc = (int32_t)((hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1);
+    left[i] = lc;
+    right[i] = rc;
+    parent[lc] = (int32_t)i;
+    parent[rc] = (int32_t)i;
+    first[i] = (int32_t)lo;
+    last[i] = (int32_t)hi;
+}
+
+__global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict__ F, const uint32_t *__restrict__ sorted_tri,
+                         long long n, const int32_t *__restrict__ parent, const int32_t *__restrict__ left,
+                         const int32_t *__restrict__ right, float *blo, float *bhi, int *flags)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float lo[3], hi[3];
+    tri_box(V, F, sorted_tri[j], lo, hi);
+    long long id = (n - 1) + j;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { blo[3 * id + k] = lo[k]; bhi[3 * id + k] = hi[k]; }
+    if (n == 1) return;
+    long long cur = parent[id];
+    for (;;) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1) == 0) return;       // the sibling subtree is not done yet
+        const long long sib = (left[cur] == id) ? right[cur] : left[cur];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __ldcg(&blo[3 * sib + k]));
+            hi[k] = fmaxf(hi[k], __ldcg(&bhi[3 * sib + k]));
+            blo[3 * cur + k] = lo[k];
+            bhi[3 * cur + k] = hi[k];
+        }
+        if (cur == 0) return;
+        id = cur;
+        cur = parent[cur];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// collapse: one thread per wide node of the current level
+// ------------------------------------------------------------------------------------------
+__global__ void k_collapse(long long n, long long begin, long long end, const int32_t *__restrict__ left,
+                           const int32_t *__restrict__ right, const int32_t *__restrict__ first,
+                           const int32_t *__restrict__ last, const float *__restrict__ blo,
+                           const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
+                           WideNode *nodes, int32_t *tri_face, unsigned *counters)
+{
+    const long long w = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    const int32_t r = wroot[w];
+    auto count = [&](int32_t id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
+    auto expandable = [&](int32_t id) -> bool { return id < n - 1 && (last[id] - first[id] + 1) > LEAF_MAX; };
+    auto area = [&](int32_t id) -> float {
+        const float dx = bhi[3ll * id] - blo[3ll * id], dy = bhi[3ll * id + 1] - blo[3ll * id + 1],
+                    dz = bhi[3ll * id + 2] - blo[3ll * id + 2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    int32_t cand[8];
+    float carea[8];
+    int nc;
+    if (!expandable(r)) {
+        cand[0] = r; carea[0] = -1.0f; nc = 1;
+    } else {
+        cand[0] = left[r]; cand[1] = right[r];
+        carea[0] = expandable(cand[0]) ? area(cand[0]) : -1.0f;
+        carea[1] = expandable(cand[1]) ? area(cand[1]) : -1.0f;
+        nc = 2;
+        while (nc < 8) {
+            int b = -1;
+            float ba = -1.0f;
+            for (int j = 0; j < nc; ++j)
+                if (carea[j] > ba) { ba = carea[j]; b = j; }
+            if (b < 0) break;
+            const int32_t id = cand[b];
+            const int32_t l = left[id], rr = right[id];
+            cand[b] = l; carea[b] = expandable(l) ? area(l) : -1.0f;
+            cand[nc] = rr; carea[nc] = expandable(rr) ? area(rr) : -1.0f;
+            ++nc;
+        }
+    }
+    // ---- slot assignment: slot s (bit k set = towards +axis k) is visited first by rays
+    //      whose direction is negative along exactly the axes set in s
+    float cen[8][3], nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int c = 0; c < nc; ++c)
+        for (int k = 0; k < 3; ++k) {
+            const float a = blo[3ll * cand[c] + k], b = bhi[3ll * cand[c] + k];
+            cen[c][k] = 0.5f * (a + b);
+            nlo[k] = fminf(nlo[k], a);
+            nhi[k] = fmaxf(nhi[k], b);
+        }
+    int slot_of[8], cand_at[8];
+    for (int k = 0; k < 8; ++k) { slot_of[k] = -1; cand_at[k] = -1; }
+    for (int it = 0; it < nc; ++it) {
+        float bc = -INFINITY;
+        int bci = -1, bs = -1;
+        for (int c = 0; c < nc; ++c) {
+            if (slot_of[c] >= 0) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (cand_at[s] >= 0) continue;
+                float cost = 0.0f;
+                for (int k = 0; k < 3; ++k) {
+                    const float dlt = cen[c][k] - 0.5f * (nlo[k] + nhi[k]);
+                    cost += ((s >> k) & 1) ? dlt : -dlt;
+                }
+                if (cost > bc) { bc = cost; bci = c; bs = s; }
+            }
+        }
+        slot_of[bci] = bs;
+        cand_at[bs] = bci;
+    }
+    int n_inner = 0, n_leaf_tris = 0;
+    for (int c = 0; c < nc; ++c) {
+        if (expandable(cand[c])) ++n_inner; else n_leaf_tris += count(cand[c]);
+    }
+    const unsigned cbase = n_inner ? atomicAdd(&counters[0], (unsigned)n_inner) : 0u;
+    const unsigned tbase = n_leaf_tris ? atomicAdd(&counters[1], (unsigned)n_leaf_tris) : 0u;
+    unsigned imask = 0, meta_lo = 0, meta_hi = 0;
+    int k_inner = 0, toff = 0;
+    for (int s = 0; s < 8; ++s) {
+        const int c = cand_at[s];
+        if (c < 0) continue;
+        const int32_t id = cand[c];
+        unsigned meta;
+        if (expandable(id)) {
+            imask |= 1u << s;
+            meta = 0x20u | (24u + (unsigned)s);
+            wroot[cbase + k_inner++] = id;
+        } else {
+            const int cnt = count(id);
+            const long long f0 = id < n - 1 ? first[id] : id - (n - 1);
+            meta = (((1u << cnt) - 1u) << 5) | (unsigned)toff;
+            for (int k = 0; k < cnt; ++k) tri_face[tbase + toff + k] = (int32_t)sorted_tri[f0 + k];
+            toff += cnt;
+        }
+        if (s < 4) meta_lo |= meta << (8 * s); else meta_hi |= meta << (8 * (s - 4));
+    }
+    nodes[w].w[0] = make_uint4(0u, 0u, 0u, imask << 24);
+    nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
+}
+
+__global__ void k_fill_tris(const float *__restrict__ V, const int32_t *__restrict__ F,
+                            const int32_t *__restrict__ tri_face, long long n, TriRec *tris)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t f = tri_face[i];
+    const long long a = F[3ll * f], b = F[3ll * f + 1], c = F[3ll * f + 2];
+    TriRec t;
+    t.v0 = make_float4(V[3 * a], V[3 * a + 1], V[3 * a + 2], __int_as_float(f));
+    t.v1 = make_float4(V[3 * b], V[3 * b + 1], V[3 * b + 2], 0.0f);
+    t.v2 = make_float4(V[3 * c], V[3 * c + 1], V[3 * c + 2], 0.0f);
+    tris[i] = t;
+}
+
+// bottom-up fit of one level: exact boxes into wlo/whi, quantised child boxes into dst
+__global__ void k_widefit(long long begin, long long end, const WideNode *__restrict__ src, WideNode *dst,
+                          const TriRec *__restrict__ tris, float *wlo, float *whi, const float *__restrict__ d_scale)
+{
+    const long long w = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    const uint4 w1 = src[w].w[1];
+    const unsigned imask = src[w].w[0].w >> 24;
+    const float pad = 3.8146973e-6f * (*d_scale);        // 2^-18 * max |coordinate|
+    float clo[8][3], chi[8][3];
+    bool valid[8];
+    float nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int k_inner = 0;
+    for (int s = 0; s < 8; ++s) {
+        const unsigned meta = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xffu;
+        valid[s] = meta != 0;
+        if (!valid[s]) continue;
+        if ((meta & 0x18u) == 0x18u) {
+            const long long c = (long long)w1.x + k_inner++;
+            for (int k = 0; k < 3; ++k) { clo[s][k] = wlo[3 * c + k]; chi[s][k] = whi[3 * c + k]; }
+        } else {
+            const int cnt = __popc(meta >> 5);
+            const long long t0 = (long long)w1.y + (meta & 31u);
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int k = 0; k < cnt; ++k) {
+                const TriRec t = tris[t0 + k];
+                lo[0] = fminf(lo[0], fminf(t.v0.x, fminf(t.v1.x, t.v2.x)));
+                lo[1] = fminf(lo[1], fminf(t.v0.y, fminf(t.v1.y, t.v2.y)));
+                lo[2] = fminf(lo[2], fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
+                hi[0] = fmaxf(hi[0], fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)));
+                hi[1] = fmaxf(hi[1], fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)));
+                hi[2] = fmaxf(hi[2], fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
+            }
+            for (int k = 0; k < 3; ++k) { clo[s][k] = lo[k] - pad; chi[s][k] = hi[k] + pad; }
+        }
+        for (int k = 0; k < 3; ++k) { nlo[k] = fminf(nlo[k], clo[s][k]); nhi[k] = fmaxf(nhi[k], chi[s][k]); }
+    }
+    if (!(nlo[0] <= nhi[0])) { for (int k = 0; k < 3; ++k) { nlo[k] = 0.0f; nhi[k] = 0.0f; } }   // empty node
+    for (int k = 0; k < 3; ++k) { wlo[3 * w + k] = nlo[k]; whi[3 * w + k] = nhi[k]; }
+
+    unsigned eb[3];
+    double sc[3];
+    for (int k = 0; k < 3; ++k) {
+        const double ext = (double)nhi[k] - (double)nlo[k];
+        int e = -126;
+        if (ext > 0.0) {
+            int ex;
+            frexp(ext / 255.0, &ex);      // ext/255 = m * 2^ex, m in [0.5, 1)  =>  2^ex >= ext/255
+            e = ex;
+            while (ldexp(255.0, e) < ext) ++e;
+        }
+        if (e < -126) e = -126;
+        if (e > 127) e = 127;
+        eb[k] = (unsigned)(e + 127);
+        sc[k] = ldexp(1.0, e);
+    }
+    unsigned ql[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qh[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int s = 0; s < 8; ++s) {
+        for (int k = 0; k < 3; ++k) {
+            unsigned a = 255u, b = 0u;
+            if (valid[s]) {
+                const double base = (double)nlo[k];
+                double x = floor(((double)clo[s][k] - base) / sc[k]);
+                x = x < 0.0 ? 0.0 : (x > 255.0 ? 255.0 : x);
+                while (x > 0.0 && base + x * sc[k] > (double)clo[s][k]) x -= 1.0;
+                double y = ceil(((double)chi[s][k] - base) / sc[k]);
+                y = y < 0.0 ? 0.0 : (y > 255.0 ? 255.0 : y);
+                while (y < 255.0 && base + y * sc[k] < (double)chi[s][k]) y += 1.0;
+                a = (unsigned)x;
+                b = (unsigned)y;
+            }
+            ql[k][s >> 2] |= a << (8 * (s & 3));
+            qh[k][s >> 2] |= b << (8 * (s & 3));
+        }
+    }
+    WideNode out;
+    out.w[0] = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]),
+                          eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+    out.w[1] = w1;
+    out.w[2] = make_uint4(ql[0][0], ql[0][1], ql[1][0], ql[1][1]);
+    out.w[3] = make_uint4(ql[2][0], ql[2][1], qh[0][0], qh[0][1]);
+    out.w[4] = make_uint4(qh[1][0], qh[1][1], qh[2][0], qh[2][1]);
+    dst[w] = out;
+}
+
+struct Mat34 {
+    double m[12];
+};
+
+// v' = float32(((T0*x + T1*y) + T2*z) + T3) in float64: TriangleMesh.transform (:550) then the
+// float32 cast of from_legacy (:245).  Also reduces max |v'| into scale_bits.
+template <typename TV>
+__global__ void k_pose_vertices(const TV *__restrict__ V, long long nV, Mat34 T, float *out, double *out64,
+                                unsigned *scale_bits)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (i < nV) {
+        const double x = V[3 * i], y = V[3 * i + 1], z = V[3 * i + 2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double r = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.m[4 * k], x), __dmul_rn(T.m[4 * k + 1], y)),
+                                                 __dmul_rn(T.m[4 * k + 2], z)),
+                                       T.m[4 * k + 3]);
+            const float f = (float)r;
+            out[3 * i + k] = f;
+            if (out64) out64[3 * i + k] = r;
+            m = fmaxf(m, fabsf(f));
+        }
+    }
+    const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(scale_bits, mx);
+}
+
+__global__ void k_f64_to_f32(const double *__restrict__ a, float *__restrict__ b, long long n)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (float)a[i];
+}
+
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+struct Bump {
+    char *p;
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t count)
+    {
+        off = (off + 255) & ~size_t(255);
+        T *r = reinterpret_cast<T *>(p + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+
+cudaError_t ensure_scratch(void **scratch, size_t *have, size_t need)
+{
+    if (*have >= need) return cudaSuccess;
+    if (*scratch) cudaFree(*scratch);
+    *scratch = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(scratch, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+}
+
+}  // namespace
+
+size_t radix_table_entries(int64_t n)
+{
+    const int64_t nb = (n + RS_TILE - 1) / RS_TILE;
+    return (size_t)(256 * (nb > 0 ? nb : 1));
+}
+
+cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
+                             uint32_t *table, cudaStream_t s, bool *result_in_tmp)
+{
+    *result_in_tmp = false;
+    if (n <= 1) return cudaSuccess;
+    const int nb = (int)((n + RS_TILE - 1) / RS_TILE);
+    uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        k_rs_hist<<<nb, RS_THREADS, 0, s>>>(ki, n, shift, table, nb);
+        k_rs_scan<<<1, 1024, 0, s>>>(table, 256ll * nb);
+        k_rs_scatter<<<nb, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, table, nb);
+        uint32_t *t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+    return cudaGetLastError();   // 4 passes: the result is back in keys / vals
+}
+
+cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF, BvhStorage &out, Topology &topo,
+                       void **scratch, size_t *scratch_bytes, uint32_t *morton_out_host, cudaStream_t s)
+{
+    cudaError_t e;
+    const long long n = nF;
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    size_t need = 4096 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
+                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + 1024;
+    if ((e = ensure_scratch(scratch, scratch_bytes, need)) != cudaSuccess) return e;
+    Bump b{static_cast<char *>(*scratch)};
+    unsigned *bounds_u = b.take<unsigned>(8);
+    float *sbounds = b.take<float>(8);
+    unsigned *counters = b.take<unsigned>(4);
+    uint32_t *keys = b.take<uint32_t>(N), *vals = b.take<uint32_t>(N);
+    uint32_t *keys_t = b.take<uint32_t>(N), *vals_t = b.take<uint32_t>(N);
+    uint32_t *table = b.take<uint32_t>(radix_table_entries(n));
+    int32_t *left = b.take<int32_t>(N), *right = b.take<int32_t>(N);
+    int32_t *first = b.take<int32_t>(N), *last = b.take<int32_t>(N);
+    int32_t *parent = b.take<int32_t>(2 * N);
+    float *blo = b.take<float>(2 * N * 3), *bhi = b.take<float>(2 * N * 3);
+    int *flags = b.take<int>(N);
+    int32_t *wroot = b.take<int32_t>(N);
+
+    out.n_tris = n;
+    topo.n_levels = 0;
+    topo.level_begin[0] = 0;
+
+    // scene bounds and scale
+    {
+        const unsigned init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+        if ((e = cudaMemcpyAsync(bounds_u, init, sizeof(init), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+        if (n > 0) k_scene_bounds<<<blocks_for(n, 256), 256, 0, s>>>(V, F, n, bounds_u);
+        k_finish_bounds<<<1, 1, 0, s>>>(bounds_u, sbounds, out.d_scale, n);
+    }
+    if (n == 0) {
+        // a root without children: every ray misses
+        WideNode root;
+        root.w[0] = make_uint4(0, 0, 0, 127u | (127u << 8) | (127u << 16));
+        root.w[1] = make_uint4(0, 0, 0, 0);
+        root.w[2] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        root.w[3] = make_uint4(0xffffffffu, 0xffffffffu, 0, 0);
+        root.w[4] = make_uint4(0, 0, 0, 0);
+        if ((e = cudaMemcpyAsync(out.nodes, &root, sizeof(root), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        out.n_nodes = 1;
+        topo.n_levels = 1;
+        topo.level_begin[1] = 1;
+        return cudaSuccess;
+    }
+    k_morton<<<blocks_for(n, 256), 256, 0, s>>>(V, F, n, sbounds, keys, vals);
+    if (morton_out_host) {
+        if ((e = cudaMemcpyAsync(morton_out_host, keys, n * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    }
+    bool in_tmp = false;
+    if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, n, table, s, &in_tmp)) != cudaSuccess) return e;
+
+    if ((e = cudaMemsetAsync(parent, 0xff, 2 * N * 4, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
+    if (n > 1) k_karras<<<blocks_for(n - 1, 256), 256, 0, s>>>(keys, n, left, right, parent, first, last);
+    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, blo, bhi, flags);
+
+    // top-down collapse, one launch per level of the wide tree
+    {
+        const unsigned init[4] = {1u, 0u, 0u, 0u};    // node 0 is the root
+        const int32_t root_id = 0;
+        if ((e = cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(wroot, &root_id, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    }
+    long long begin = 0, end = 1;
+    int L = 0;
+    while (begin < end) {
+        if (L + 1 >= 127) return cudaErrorInvalidValue;
+        k_collapse<<<blocks_for(end - begin, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
+                                                                wroot, out.nodes, topo.tri_face, counters);
+        unsigned cnt[2];
+        if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        topo.level_begin[++L] = end;
+        begin = end;
+        end = cnt[0];
+        if (end > out.cap_nodes) return cudaErrorMemoryAllocation;
+    }
+    topo.n_levels = L;
+    out.n_nodes = end;
+    k_fill_tris<<<blocks_for(n, 256), 256, 0, s>>>(V, F, topo.tri_face, n, out.tris);
+    for (int l = L - 1; l >= 0; --l) {
+        const long long lb = topo.level_begin[l], le = topo.level_begin[l + 1];
+        k_widefit<<<blocks_for(le - lb, 128), 128, 0, s>>>(lb, le, out.nodes, out.nodes, out.tris, out.wlo, out.whi,
+                                                           out.d_scale);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t convert_f64_to_f32(const double *src, float *dst, int64_t n, cudaStream_t s)
+{
+    if (n > 0) k_f64_to_f32<<<blocks_for(n, 256), 256, 0, s>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t *F, int64_t nF, const double *T_host,
+                           float *Vposed, double *Vposed64, const BvhStorage &src, BvhStorage &dst,
+                           const Topology &topo, cudaStream_t s)
+{
+    cudaError_t e;
+    Mat34 T;
+    for (int k = 0; k < 12; ++k) T.m[k] = T_host[k];
+    if ((e = cudaMemsetAsync(dst.d_scale, 0, 4, s)) != cudaSuccess) return e;
+    if (nV > 0) {
+        if (vdtype == 1)
+            k_pose_vertices<double><<<blocks_for(nV, 256), 256, 0, s>>>(static_cast<const double *>(V), nV, T, Vposed,
+                                                                        Vposed64, reinterpret_cast<unsigned *>(dst.d_scale));
+        else
+            k_pose_vertices<float><<<blocks_for(nV, 256), 256, 0, s>>>(static_cast<const float *>(V), nV, T, Vposed,
+                                                                       Vposed64, reinterpret_cast<unsigned *>(dst.d_scale));
+    }
+    dst.n_nodes = src.n_nodes;
+    dst.n_tris = src.n_tris;
+    if (nF == 0) {
+        return cudaMemcpyAsync(dst.nodes, src.nodes, sizeof(WideNode), cudaMemcpyDeviceToDevice, s);
+    }
+    k_fill_tris<<<blocks_for(nF, 256), 256, 0, s>>>(Vposed, F, topo.tri_face, nF, dst.tris);
+    for (int l = topo.n_levels - 1; l >= 0; --l) {
+        const long long lb = topo.level_begin[l], le = topo.level_begin[l + 1];
+        k_widefit<<<blocks_for(le - lb, 128), 128, 0, s>>>(lb, le, src.nodes, dst.nodes, dst.tris, dst.wlo, dst.whi,
+                                                           dst.d_scale);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dp

@@ -1,0 +1,207 @@
+// Subsystem (1): heatmap threshold filtering + order-preserving stream compaction.
+//
+// Replaces heatmap_to_points (/root/reference/src/defect_projection.py:165-179):
+//     y, x = np.where(heatmap > threshold); intensities = heatmap[y, x]
+// Output order is row-major (y ascending, then x), one entry per pixel with value > thr
+// (strict; NaN never passes).  A batch of frames is one flat array, so the emitted pixel
+// index is frame*H*W + y*W + x.
+//
+// One pass over the heatmap (HBM streaming, 16-byte loads), ranks from warp ballots,
+// tile offsets by decoupled look-back (tiles take their id from an atomic ticket so a
+// waiting tile only ever waits for a tile that is already running).
+#include "dp_internal.cuh"
+
+namespace dp {
+
+namespace {
+
+constexpr int CT_THREADS = 256;
+constexpr int CT_CHUNKS = 4;                       // 16-byte (f32) / 32-byte (f64) loads per thread
+constexpr int CT_TILE = CT_THREADS * CT_CHUNKS * 4;  // 4096 pixels per tile
+
+constexpr unsigned long long ST_AGG = 1ull << 62;   // tile aggregate published
+constexpr unsigned long long ST_INC = 2ull << 62;   // inclusive prefix published
+constexpr unsigned long long ST_VAL = (1ull << 62) - 1;
+
+template <typename T>
+struct Vec4 {
+    T v[4];
+};
+
+__device__ __forceinline__ void load4(const float *p, Vec4<float> &o)
+{
+    float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+    o.v[0] = q.x; o.v[1] = q.y; o.v[2] = q.z; o.v[3] = q.w;
+}
+__device__ __forceinline__ void load4(const double *p, Vec4<double> &o)
+{
+    double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
+          float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *d_count,
+          int aligned)
+{
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_warp_tot[CT_CHUNKS * (CT_THREADS / 32)];
+    __shared__ unsigned s_warp_off[CT_CHUNKS * (CT_THREADS / 32)];
+    __shared__ unsigned s_block_total;
+    __shared__ long long s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned *>(scratch), 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long tile_base = (long long)tile * CT_TILE;
+    unsigned long long *state = scratch + 1;
+
+    Vec4<T> val[CT_CHUNKS];
+    unsigned m[CT_CHUNKS];
+    unsigned excl[CT_CHUNKS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int c = 0; c < CT_CHUNKS; ++c) {
+        const long long e0 = tile_base + (long long)c * (CT_THREADS * 4) + tid * 4;
+        if (aligned && e0 + 3 < n) {
+            load4(heat + e0, val[c]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) val[c].v[j] = (e0 + j < n) ? heat[e0 + j] : thr;   // thr > thr is false
+        }
+        unsigned mm = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mm |= (val[c].v[j] > thr) ? (1u << j) : 0u;
+        m[c] = mm;
+        // rank of this thread's first selected pixel among the warp's 128 pixels of chunk c
+        unsigned r = 0, tot = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned b = __ballot_sync(0xffffffffu, (mm >> j) & 1u);
+            r += __popc(b & lt);
+            tot += __popc(b);
+        }
+        excl[c] = r;
+        if (lane == 0) s_warp_tot[c * (CT_THREADS / 32) + warp] = tot;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // 32 partial counts in pixel order (chunk-major, then warp): exclusive scan by shuffles
+        const unsigned x = s_warp_tot[lane];
+        unsigned inc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        s_warp_off[lane] = inc - x;
+        if (lane == 31) s_block_total = inc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long total = s_block_total;
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            atomicExch(&state[0], ST_INC | total);
+        } else {
+            atomicExch(&state[tile], ST_AGG | total);
+            long long j = (long long)tile - 1;
+            for (;;) {
+                unsigned long long s;
+                do {
+                    s = *reinterpret_cast<volatile unsigned long long *>(&state[j]);
+                } while ((s >> 62) == 0);
+                prefix += s & ST_VAL;
+                if (s & ST_INC) break;
+                --j;
+            }
+            atomicExch(&state[tile], ST_INC | (prefix + total));
+        }
+        s_base = (long long)prefix;
+        if (tile_base + CT_TILE >= n) *d_count = (long long)(prefix + total);   // last tile
+    }
+    __syncthreads();
+    const long long base = s_base;
+#pragma unroll
+    for (int c = 0; c < CT_CHUNKS; ++c) {
+        if (!m[c]) continue;
+        long long off = base + s_warp_off[c * (CT_THREADS / 32) + warp] + excl[c];
+        const long long e0 = tile_base + (long long)c * (CT_THREADS * 4) + tid * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((m[c] >> j) & 1u) {
+                if (off < cap) {
+                    pixel[off] = (uint32_t)(e0 + j);
+                    if (intensity) intensity[off] = (float)val[c].v[j];
+                }
+                ++off;
+            }
+        }
+    }
+}
+
+// per-frame counts from the sorted pixel list: count[f] = lb((f+1)*HW) - lb(f*HW)
+__global__ void k_frame_counts(const uint32_t *__restrict__ pixel, const long long *d_count, long long cap,
+                               long long frame_elems, long long nframes, long long *frame_count)
+{
+    const long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    long long n = *d_count;
+    if (n > cap) n = cap;
+    long long bounds[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const unsigned long long key = (unsigned long long)(f + k) * (unsigned long long)frame_elems;
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if ((unsigned long long)pixel[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        bounds[k] = lo;
+    }
+    frame_count[f] = bounds[1] - bounds[0];
+}
+
+}  // namespace
+
+size_t compact_scratch_bytes(int64_t n_elems)
+{
+    const int64_t ntiles = (n_elems + CT_TILE - 1) / CT_TILE;
+    return (size_t)(ntiles + 2) * sizeof(unsigned long long);
+}
+
+cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t frame_elems, double thr,
+                           uint32_t *pixel, float *intensity, int64_t cap, unsigned long long *scratch,
+                           long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s)
+{
+    cudaError_t e;
+    if (n_elems <= 0) {
+        if ((e = cudaMemsetAsync(d_count, 0, sizeof(long long), s)) != cudaSuccess) return e;
+        if (d_frame_count && nframes > 0)
+            if ((e = cudaMemsetAsync(d_frame_count, 0, sizeof(long long) * nframes, s)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    const int64_t ntiles = (n_elems + CT_TILE - 1) / CT_TILE;
+    if ((e = cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n_elems), s)) != cudaSuccess) return e;
+    const int aligned = ((uintptr_t)heat % 16) == 0;
+    if (dtype == 1) {
+        k_compact<double><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const double *>(heat), n_elems, thr,
+                                                                   pixel, intensity, cap, scratch, d_count, aligned);
+    } else {
+        k_compact<float><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const float *>(heat), n_elems,
+                                                                  (float)thr, pixel, intensity, cap, scratch,
+                                                                  d_count, aligned);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (d_frame_count && nframes > 0) {
+        k_frame_counts<<<(unsigned)((nframes + 127) / 128), 128, 0, s>>>(pixel, d_count, cap, frame_elems, nframes,
+                                                                          d_frame_count);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace dp

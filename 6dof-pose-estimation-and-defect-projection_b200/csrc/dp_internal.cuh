@@ -1,0 +1,111 @@
+// Internal declarations shared by the translation units of libdefectproj.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dp {
+
+// ------------------------------------------------------------------------------------------
+// Wide BVH node: 80 bytes = five 16-byte words (loaded as 5 x LDG.128).
+//   w0: origin x,y,z (float bits) | ex | ey<<8 | ez<<16 | imask<<24
+//   w1: child_base, tri_base, meta[0..3], meta[4..7]
+//   w2: qlo_x[0..7], qlo_y[0..7]            (x,y = slots 0..3 / 4..7 of x; z,w = y)
+//   w3: qlo_z[0..7], qhi_x[0..7]
+//   w4: qhi_y[0..7], qhi_z[0..7]
+// meta[slot]: 0 = empty; inner child = 0x20 | (24 + slot); leaf = (unary count) << 5 | offset,
+//             unary count = 1, 3, 7 for 1, 2, 3 triangles, offset = first record relative to
+//             tri_base (0..23).  e* are biased float exponents: scale = bits(e << 23).
+// ------------------------------------------------------------------------------------------
+struct __align__(16) WideNode {
+    uint4 w[5];
+};
+static_assert(sizeof(WideNode) == 80, "wide node must be 80 bytes");
+
+// triangle record: 48 bytes = 3 x float4.  v0.w carries the original face id bits.
+struct __align__(16) TriRec {
+    float4 v0, v1, v2;
+};
+static_assert(sizeof(TriRec) == 48, "triangle record must be 48 bytes");
+
+constexpr int LEAF_MAX = 3;           // triangles per leaf slot
+constexpr int STACK_SMEM = 10;        // per-ray stack entries kept in shared memory
+constexpr int STACK_LOCAL = 54;       // overflow entries in local memory
+constexpr int MAX_WIDE_DEPTH = STACK_SMEM + STACK_LOCAL - 2;
+constexpr float T_SLACK = 1.0001f;    // culling bound = best * T_SLACK (same as oracle.c)
+
+struct BvhView {
+    const WideNode *nodes;
+    const TriRec *tris;
+    const float *d_scale;  // device: max |vertex coordinate| of the mesh the BVH was fitted to
+};
+
+// per-frame ray generation constants: fx fy cx cy | Rinv (row-major) | tinv
+struct FrameXf {
+    double v[16];
+};
+
+struct Accum {
+    int32_t *hist;     // [nF]
+    uint32_t *fmax;    // [nF] float bits (non-negative floats order like unsigned ints)
+    uint32_t *vmax;    // [nV]
+    const int32_t *F;  // [nF*3]
+};
+
+struct TraceStats {
+    unsigned long long rays, hits, nodes, tris;
+};
+
+// ---- compact.cu ----------------------------------------------------------------------------
+// tile_state: [ntiles+1] u64 scratch (zeroed by the call); d_count: device int64 total;
+// d_frame_count: [nframes] device int64 (zeroed by the call) or nullptr.
+size_t compact_scratch_bytes(int64_t n_elems);
+cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t frame_elems, double thr,
+                           uint32_t *pixel, float *intensity, int64_t cap, unsigned long long *scratch,
+                           long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s);
+
+// ---- trace.cu ------------------------------------------------------------------------------
+// rays from pixels: pixel[i] = frame*HW + y*W + x ; xf[frame] ; n read from *d_n (<= n_max)
+cudaError_t launch_trace_pixels(const BvhView &bvh, const uint32_t *pixel, const float *intensity,
+                                const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
+                                int64_t n_xf, float *t_hit, int32_t *face, float *point, double *point64,
+                                const Accum *acc, long long *d_hits, TraceStats *stats, cudaStream_t s);
+cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
+                                cudaStream_t s);
+cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,
+                               TraceStats *stats, cudaStream_t s);
+
+// ---- build.cu ------------------------------------------------------------------------------
+struct BuildScratch;   // opaque, owned by the context
+
+struct BvhStorage {
+    WideNode *nodes = nullptr;     // [cap_nodes]
+    TriRec *tris = nullptr;        // [nF]
+    float *wlo = nullptr;          // [cap_nodes*3] exact wide-node boxes (refit)
+    float *whi = nullptr;
+    int64_t cap_nodes = 0;
+    int64_t n_nodes = 0;
+    int64_t n_tris = 0;
+    float *d_scale = nullptr;      // device scalar: max |vertex coordinate|
+};
+
+struct Topology {                  // shared by the object-frame and camera-frame node sets
+    int32_t *tri_face = nullptr;   // [nF] record -> original face id
+    int64_t level_begin[128];      // wide nodes of level l are [level_begin[l], level_begin[l+1])
+    int n_levels = 0;
+};
+
+// all launches on `s`; performs one small blocking read-back per tree level
+cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF, BvhStorage &out, Topology &topo,
+                       void **scratch, size_t *scratch_bytes, uint32_t *morton_out_host, cudaStream_t s);
+// v' = float32(T*v) for every vertex, then new triangle records and a bottom-up refit of
+// `dst` that copies the topology (meta, bases) of `src`.
+// V: float32 (vdtype 0) or float64 (vdtype 1); Vposed64 may be nullptr.
+cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t *F, int64_t nF, const double *T_host,
+                           float *Vposed, double *Vposed64, const BvhStorage &src, BvhStorage &dst,
+                           const Topology &topo, cudaStream_t s);
+cudaError_t convert_f64_to_f32(const double *src, float *dst, int64_t n, cudaStream_t s);
+cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
+                             uint32_t *table, cudaStream_t s, bool *result_in_tmp);
+size_t radix_table_entries(int64_t n);
+
+}  // namespace dp

@@ -1,0 +1,82 @@
+"""ctypes binding of libdefectproj.so (include/defectproj.h).
+
+The library is the product: there is no Python or CPU fallback.  Importing this
+module without the built .so raises; creating a context without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libdefectproj.so")
+
+DP_OK, DP_E_ARG, DP_E_CUDA, DP_E_NOMEM, DP_E_STATE = 0, -1, -2, -3, -4
+DP_HOST, DP_DEVICE = 0, 1
+DP_F32, DP_F64 = 0, 1
+DP_FRAME_OBJECT, DP_FRAME_CAMERA = 0, 1
+ABI_VERSION = 1
+
+i64, i32, f64, vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
+
+
+class RaysOut(C.Structure):
+    _fields_ = [("pixel", vp), ("intensity", vp), ("t_hit", vp), ("face", vp), ("point", vp), ("point64", vp),
+                ("cap", i64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays", i64), ("hits", i64), ("nodes_fetched", i64), ("tris_tested", i64),
+                ("n_wide_nodes", i64), ("n_tris", i64), ("wide_depth", C.c_int32), ("reserved", C.c_int32),
+                ("last_build_ms", C.c_float), ("last_refit_ms", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol include/defectproj.h declares
+SYMBOLS = {
+    "dp_abi_version": (i32, []),
+    "dp_create": (i32, [i32, C.POINTER(vp)]),
+    "dp_destroy": (None, [vp]),
+    "dp_last_error": (C.c_char_p, [vp]),
+    "dp_synchronize": (i32, [vp, vp]),
+    "dp_set_mesh": (i32, [vp, vp, i32, i64, vp, i64, i32, vp]),
+    "dp_build_bvh": (i32, [vp, vp]),
+    "dp_pose_mesh": (i32, [vp, vp, vp]),
+    "dp_get_posed_vertices": (i32, [vp, vp, i32, i32, vp]),
+    "dp_compact": (i32, [vp, vp, i32, i64, i32, i32, f64, vp, vp, i64, C.POINTER(i64), vp, i32, vp]),
+    "dp_frame_xform": (None, [vp, vp, vp]),
+    "dp_compute_rays": (i32, [vp, vp, vp, i64, vp, vp, i32, vp]),
+    "dp_cast_rays": (i32, [vp, i32, vp, i64, vp, vp, i32, vp]),
+    "dp_project": (i32, [vp, i32, vp, i32, i64, i32, i32, f64, vp, i64, vp, i32, C.POINTER(RaysOut),
+                         C.POINTER(i64), C.POINTER(i64), i32, vp]),
+    "dp_accum_reset": (i32, [vp, vp]),
+    "dp_accum_get": (i32, [vp, vp, vp, vp, i32, vp]),
+    "dp_accum_device_ptrs": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "dp_set_stats": (i32, [vp, i32]),
+    "dp_get_stats": (i32, [vp, C.POINTER(Stats)]),
+    "dp_last_timings": (i32, [vp, vp]),
+    "dp_debug_dump_bvh": (i32, [vp, i32, vp, C.POINTER(i64), vp, C.POINTER(i64)]),
+    "dp_debug_radix_sort": (i32, [vp, vp, vp, i64]),
+    "dp_debug_morton": (i32, [vp, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  defectproj has no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if L.dp_abi_version() != ABI_VERSION:
+        raise ImportError(f"libdefectproj.so ABI {L.dp_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = L
+    return L

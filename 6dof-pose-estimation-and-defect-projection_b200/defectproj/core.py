@@ -1,0 +1,329 @@
+"""Thin object wrapper over the C ABI (include/defectproj.h).
+
+Host (numpy) arguments are staged by the library; CUDA tensors (torch) are passed by
+address and stay on the device.  Nothing here computes: it marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (DP_DEVICE, DP_E_ARG, DP_E_NOMEM, DP_E_STATE, DP_F32, DP_F64, DP_FRAME_CAMERA,
+                   DP_FRAME_OBJECT, DP_HOST, RaysOut, Stats)
+
+__all__ = ["Context", "DefectProjError", "FRAME_OBJECT", "FRAME_CAMERA"]
+
+FRAME_OBJECT, FRAME_CAMERA = DP_FRAME_OBJECT, DP_FRAME_CAMERA
+
+
+class DefectProjError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[defectproj {code}] {msg}")
+        self.code = code
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _frame(frame):
+    if frame in ("object", FRAME_OBJECT):
+        return FRAME_OBJECT
+    if frame in ("camera", FRAME_CAMERA):
+        return FRAME_CAMERA
+    raise ValueError(f"frame must be 'object' or 'camera', got {frame!r}")
+
+
+class Context:
+    """One dp_ctx: a mesh, its BVH(s), accumulators and scratch on one B200.  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.dp_create(int(device), C.byref(h))
+        if rc != 0:
+            raise DefectProjError(rc, self._L.dp_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.nV = self.nF = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self._L.dp_last_error(self._h).decode()
+        if rc == DP_E_ARG:
+            raise ValueError(msg)
+        if rc == DP_E_NOMEM:
+            raise MemoryError(msg)
+        raise DefectProjError(rc, msg)
+
+    @staticmethod
+    def _stream(stream):
+        if stream is None:
+            return None
+        if hasattr(stream, "cuda_stream"):
+            return C.c_void_p(stream.cuda_stream)
+        return C.c_void_p(int(stream))
+
+    def synchronize(self, stream=None):
+        self._check(self._L.dp_synchronize(self._h, self._stream(stream)))
+
+    # ------------------------------------------------------------------ mesh / BVH
+    def set_mesh(self, V, F, stream=None):
+        """V [nV,3] float32 or float64, F [nF,3] int32 (numpy or CUDA tensors)."""
+        if _is_torch(V):
+            import torch
+            if not (V.is_cuda and F.is_cuda):
+                raise ValueError("tensor meshes must live on the device; pass numpy arrays for host data")
+            V = V.contiguous()
+            F = F.to(torch.int32).contiguous()
+            vd = DP_F64 if V.dtype == torch.float64 else DP_F32
+            if V.dtype not in (torch.float32, torch.float64):
+                V = V.float()
+            nV, nF, mem = V.shape[0], F.shape[0], DP_DEVICE
+        else:
+            V = np.asarray(V)
+            vd = DP_F64 if V.dtype == np.float64 else DP_F32
+            V = np.ascontiguousarray(V, dtype=np.float64 if vd == DP_F64 else np.float32)
+            F = np.ascontiguousarray(F, dtype=np.int32)
+            if V.ndim != 2 or (V.size and V.shape[1] != 3) or F.ndim != 2 or (F.size and F.shape[1] != 3):
+                raise ValueError("V must be [nV,3] and F [nF,3]")
+            nV, nF, mem = len(V), len(F), DP_HOST
+        self._check(self._L.dp_set_mesh(self._h, _ptr(V), vd, nV, _ptr(F), nF, mem, self._stream(stream)))
+        self.nV, self.nF = nV, nF
+        return self
+
+    def build_bvh(self, stream=None):
+        self._check(self._L.dp_build_bvh(self._h, self._stream(stream)))
+        return self
+
+    def pose_mesh(self, T, stream=None):
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        self._check(self._L.dp_pose_mesh(self._h, _ptr(T), self._stream(stream)))
+        return self
+
+    def posed_vertices(self, dtype=np.float32, stream=None):
+        dtype = np.dtype(dtype)
+        out = np.empty((self.nV, 3), dtype)
+        self._check(self._L.dp_get_posed_vertices(self._h, _ptr(out), DP_F64 if dtype == np.float64 else DP_F32,
+                                                  DP_HOST, self._stream(stream)))
+        return out
+
+    # ------------------------------------------------------------------ H1
+    def compact(self, heat, thr, want_intensity=True, stream=None):
+        """np.where(heat > thr) on the GPU.  heat [H,W] or [B,H,W], float32/float64 numpy.
+        Returns (pixel uint32 [N] = frame*H*W + y*W + x, intensity float32 [N] | None, counts int64 [B])."""
+        heat = np.asarray(heat)
+        if heat.dtype not in (np.float32, np.float64):
+            heat = heat.astype(np.float64)
+        heat = np.ascontiguousarray(heat)
+        if heat.ndim == 2:
+            heat = heat[None]
+        if heat.ndim != 3:
+            raise ValueError("heat must be [H,W] or [B,H,W]")
+        B, H, W = heat.shape
+        cap = heat.size
+        pix = np.empty(cap, np.uint32)
+        inten = np.empty(cap, np.float32) if want_intensity else None
+        counts = np.zeros(B, np.int64)
+        n = C.c_int64(0)
+        self._check(self._L.dp_compact(self._h, _ptr(heat), DP_F64 if heat.dtype == np.float64 else DP_F32, B, H, W,
+                                       float(thr), _ptr(pix), _ptr(inten), cap, C.byref(n), _ptr(counts), DP_HOST,
+                                       self._stream(stream)))
+        k = n.value
+        return pix[:k], (inten[:k] if want_intensity else None), counts
+
+    # ------------------------------------------------------------------ H2
+    def compute_rays(self, xs, ys, K, stream=None):
+        xs = np.ascontiguousarray(xs, dtype=np.int32)
+        ys = np.ascontiguousarray(ys, dtype=np.int32)
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        out = np.empty((len(xs), 3), np.float64)
+        self._check(self._L.dp_compute_rays(self._h, _ptr(xs), _ptr(ys), len(xs), _ptr(K), _ptr(out), DP_HOST,
+                                            self._stream(stream)))
+        return out
+
+    @staticmethod
+    def frame_xform(K, pose=None):
+        """The 16 per-frame constants the kernels use (fx fy cx cy | Rinv | tinv)."""
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        P = None if pose is None else np.ascontiguousarray(pose, dtype=np.float64).reshape(16)
+        out = np.empty(16, np.float64)
+        _lib.load().dp_frame_xform(_ptr(K), _ptr(P), _ptr(out))
+        return out
+
+    # ------------------------------------------------------------------ H4
+    def cast_rays(self, rays6, frame="object", want_face=True, stream=None):
+        """Closest hit of explicit float32 rays [N,6] -> (t_hit float32 [N], face int32 [N])."""
+        fr = _frame(frame)
+        if _is_torch(rays6):
+            import torch
+            r = rays6.contiguous().float()
+            n = r.shape[0]
+            t = torch.empty(n, dtype=torch.float32, device=r.device)
+            f = torch.empty(n, dtype=torch.int32, device=r.device) if want_face else None
+            self._check(self._L.dp_cast_rays(self._h, fr, _ptr(r), n, _ptr(t), _ptr(f), DP_DEVICE,
+                                             self._stream(stream if stream is not None else torch.cuda.current_stream())))
+            return t, f
+        r = np.ascontiguousarray(rays6, dtype=np.float32)
+        if r.ndim != 2 or (r.size and r.shape[1] != 6):
+            raise ValueError("rays6 must be [N,6]")
+        n = len(r)
+        t = np.empty(n, np.float32)
+        f = np.empty(n, np.int32) if want_face else None
+        self._check(self._L.dp_cast_rays(self._h, fr, _ptr(r), n, _ptr(t), _ptr(f), DP_HOST, self._stream(stream)))
+        return t, f
+
+    # ------------------------------------------------------------------ fused path
+    def project(self, heat, K, poses=None, thr=0.5, frame="object", accumulate=True,
+                want=("pixel", "intensity", "t_hit", "face", "point"), cap=None, stream=None):
+        """Host-buffer end-to-end call: heat (numpy [H,W] or [B,H,W]) in, per-ray arrays out.
+
+        Returns dict(n=rays, hits=..., pixel=..., intensity=..., t_hit=..., face=..., point=..., point64=...)
+        with only the requested arrays, each cut to n.
+        """
+        fr = _frame(frame)
+        heat = np.asarray(heat)
+        if heat.dtype not in (np.float32, np.float64):
+            heat = heat.astype(np.float64)
+        heat = np.ascontiguousarray(heat)
+        if heat.ndim == 2:
+            heat = heat[None]
+        B, H, W = heat.shape
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(-1, 9)
+        P = None
+        if fr == FRAME_OBJECT:
+            if poses is None:
+                raise ValueError("object-frame projection needs the model->camera pose(s)")
+            P = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+            if len(P) != B:
+                raise ValueError(f"{B} frames but {len(P)} poses")
+        cap = heat.size if cap is None else int(cap)
+        shapes = {"pixel": ((cap,), np.uint32), "intensity": ((cap,), np.float32), "t_hit": ((cap,), np.float32),
+                  "face": ((cap,), np.int32), "point": ((cap, 3), np.float32), "point64": ((cap, 3), np.float64)}
+        arrs = {}
+        ro = RaysOut()
+        ro.cap = cap
+        for k in want:
+            shp, dt = shapes[k]
+            arrs[k] = np.empty(shp, dt)
+            setattr(ro, k, _ptr(arrs[k]))
+        n, nh = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.dp_project(self._h, fr, _ptr(heat), DP_F64 if heat.dtype == np.float64 else DP_F32, B, H, W,
+                                       float(thr), _ptr(K), len(K), _ptr(P), int(bool(accumulate)), C.byref(ro),
+                                       C.byref(n), C.byref(nh), DP_HOST, self._stream(stream)))
+        res = {k: v[:n.value] for k, v in arrs.items()}
+        res["n"], res["hits"] = n.value, nh.value
+        return res
+
+    def project_device(self, heat, K, poses=None, thr=0.5, frame="object", accumulate=True, out=None,
+                       sync=False, stream=None):
+        """Device-resident call: `heat` is a CUDA tensor [B,H,W] (float32/float64); `out` maps
+        names to preallocated CUDA tensors.  Asynchronous on the current torch stream unless sync."""
+        import torch
+        fr = _frame(frame)
+        if not heat.is_cuda:
+            raise ValueError("project_device needs a CUDA tensor")
+        heat = heat.contiguous()
+        if heat.dim() == 2:
+            heat = heat[None]
+        B, H, W = heat.shape
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(-1, 9)
+        P = None
+        if fr == FRAME_OBJECT:
+            P = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+            if len(P) != B:
+                raise ValueError(f"{B} frames but {len(P)} poses")
+        ro = RaysOut()
+        ro.cap = 0
+        if out:
+            caps = []
+            for k, tsr in out.items():
+                setattr(ro, k, _ptr(tsr))
+                caps.append(tsr.shape[0])
+            ro.cap = min(caps)
+        n, nh = C.c_int64(0), C.c_int64(0)
+        st = self._stream(stream if stream is not None else torch.cuda.current_stream())
+        self._check(self._L.dp_project(self._h, fr, _ptr(heat), DP_F64 if heat.dtype == torch.float64 else DP_F32, B, H,
+                                       W, float(thr), _ptr(K), len(K), _ptr(P), int(bool(accumulate)),
+                                       C.byref(ro) if out else None, C.byref(n) if sync else None,
+                                       C.byref(nh) if sync else None, DP_DEVICE, st))
+        return (n.value, nh.value) if sync else None
+
+    # ------------------------------------------------------------------ H6 / H7
+    def accum_reset(self, stream=None):
+        self._check(self._L.dp_accum_reset(self._h, self._stream(stream)))
+
+    def accum_get(self, stream=None):
+        hist = np.empty(self.nF, np.int32)
+        fmax = np.empty(self.nF, np.float32)
+        vmax = np.empty(self.nV, np.float32)
+        self._check(self._L.dp_accum_get(self._h, _ptr(hist), _ptr(fmax), _ptr(vmax), DP_HOST, self._stream(stream)))
+        return hist, fmax, vmax
+
+    def accum_device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.dp_accum_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # ------------------------------------------------------------------ instrumentation
+    def set_stats(self, on: bool):
+        self._check(self._L.dp_set_stats(self._h, int(bool(on))))
+
+    def stats(self):
+        st = Stats()
+        self._check(self._L.dp_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
+
+    def last_timings(self):
+        ms = (C.c_float * 3)()
+        self._check(self._L.dp_last_timings(self._h, ms))
+        return {"compact_ms": ms[0], "trace_ms": ms[1], "total_ms": ms[2]}
+
+    def dump_bvh(self, frame="object"):
+        fr = _frame(frame)
+        nn, nt = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.dp_debug_dump_bvh(self._h, fr, None, C.byref(nn), None, C.byref(nt)))
+        nodes = np.empty((nn.value, 20), np.uint32)
+        tris = np.empty((nt.value, 12), np.float32)
+        self._check(self._L.dp_debug_dump_bvh(self._h, fr, _ptr(nodes), C.byref(nn), _ptr(tris), C.byref(nt)))
+        return nodes, tris
+
+    def radix_sort(self, keys, vals):
+        keys = np.array(keys, dtype=np.uint32, copy=True)
+        vals = np.array(vals, dtype=np.uint32, copy=True)
+        self._check(self._L.dp_debug_radix_sort(self._h, _ptr(keys), _ptr(vals), len(keys)))
+        return keys, vals
+
+    def morton_codes(self):
+        codes = np.empty(self.nF, np.uint32)
+        self._check(self._L.dp_debug_morton(self._h, _ptr(codes)))
+        return codes

@@ -1,0 +1,173 @@
+/*
+ * defectproj.h -- C ABI of libdefectproj.so, the B200 (sm_100a) implementation of the
+ * 2D-defect -> 3D-mesh back-projection hot path of
+ *     /root/reference/src/defect_projection.py::ray_tracing            (:527-563)
+ *
+ * The reference has no native boundary on this path: it is Python that calls numpy and
+ * open3d.t.geometry.RaycastingScene (Embree).  Each entry point below names the reference
+ * lines it replaces; INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add to src/defect_projection.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  No torch / CUDA types in any signature:
+ *     `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - every buffer argument is described by one `mem` flag per call:
+ *     DP_HOST (pageable or pinned host memory; the call stages it) or DP_DEVICE (memory of
+ *     the context's device; the call neither copies nor synchronises more than stated).
+ *   - all functions return 0 (DP_OK) or a negative DP_E_* code; the message of the last
+ *     failure of a context is returned by dp_last_error().  Nothing throws across the ABI.
+ *   - a context is bound to one device and is NOT thread-safe (one context per host thread).
+ *   - matrices are row-major doubles.  `pose` is the 4x4 rigid model->camera transform
+ *     (what run.py:109-110 followed by src/defect_projection.py:549-550 apply to the mesh).
+ *   - there is no CPU fallback: without a CUDA device dp_create() fails with DP_E_CUDA.
+ */
+#ifndef DEFECTPROJ_H
+#define DEFECTPROJ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DP_API
+#else
+#define DP_API __attribute__((visibility("default")))
+#endif
+
+#define DP_ABI_VERSION 1
+
+enum {
+    DP_OK = 0,
+    DP_E_ARG = -1,    /* bad argument (null pointer, negative size, index out of range ...) */
+    DP_E_CUDA = -2,   /* a CUDA runtime call or kernel failed; see dp_last_error()          */
+    DP_E_NOMEM = -3,  /* host or device allocation failed / caller capacity too small       */
+    DP_E_STATE = -4   /* call order (no mesh, no BVH ...) or BVH too deep for the ray stack */
+};
+
+enum { DP_HOST = 0, DP_DEVICE = 1 };
+enum { DP_F32 = 0, DP_F64 = 1 };
+
+/* which mesh the rays are cast against */
+enum {
+    DP_FRAME_OBJECT = 0,  /* static BVH in the model frame; rays go through the inverse pose  */
+    DP_FRAME_CAMERA = 1   /* BVH over the mesh posed by dp_pose_mesh(); rays leave (0,0,0)
+                             exactly as the reference builds them (:247-251, :545)          */
+};
+
+typedef struct dp_ctx dp_ctx;
+
+/* per-ray outputs of dp_project / dp_cast_rays; any pointer may be NULL (not wanted).
+ * All arrays are indexed by compacted ray number (row-major pixel order, :165-179). */
+typedef struct dp_rays_out {
+    uint32_t *pixel;   /* [cap]   frame*H*W + y*W + x        (heatmap_to_points, :175-179)   */
+    float *intensity;  /* [cap]   heatmap value as float32                                   */
+    float *t_hit;      /* [cap]   +inf on miss                (cast_rays 't_hit', :258-259)  */
+    int32_t *face;     /* [cap]   original face id, -1 miss   (cast_rays 'primitive_ids')    */
+    float *point;      /* [cap*3] hit point, camera frame     (:261-263); NaN on miss        */
+    double *point64;   /* [cap*3] the same in float64: d (float64) * t (float32), as :261-263 */
+    int64_t cap;       /* capacity in rays of every non-NULL array above                     */
+} dp_rays_out;
+
+typedef struct dp_stats {
+    int64_t rays;           /* rays traced by the last counted launch                        */
+    int64_t hits;
+    int64_t nodes_fetched;  /* 80-byte wide nodes fetched (sum over rays)                    */
+    int64_t tris_tested;    /* 48-byte triangle records fetched (sum over rays)              */
+    int64_t n_wide_nodes;   /* BVH size                                                      */
+    int64_t n_tris;
+    int32_t wide_depth;
+    int32_t reserved;
+    float last_build_ms;    /* device time of the last dp_build_bvh (CUDA events)            */
+    float last_refit_ms;    /* device time of the last dp_pose_mesh                          */
+} dp_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+DP_API int dp_abi_version(void);
+DP_API int dp_create(int device, dp_ctx **out);
+DP_API void dp_destroy(dp_ctx *ctx);
+DP_API const char *dp_last_error(const dp_ctx *ctx);   /* ctx may be NULL: last create error */
+DP_API int dp_synchronize(dp_ctx *ctx, void *stream);
+
+/* ---- mesh + BVH  (replaces RaycastingScene() + add_triangles, :245, :253-254) ----------- */
+/* V: [nV*3] model-frame vertices, float32 or float64 (`vdtype`).  The object-frame BVH uses
+ * the float32 rounding of V (the cast of from_legacy, :245); dp_pose_mesh transforms the
+ * vertices at the precision given here, as the reference does with its float64 mesh.
+ * F: [nF*3] int32.  The arrays are copied; the caller may free them on return. */
+DP_API int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const int32_t *F, int64_t nF, int mem,
+                       void *stream);
+/* LBVH over the current object-frame mesh: 30-bit Morton codes, radix sort, Karras hierarchy,
+ * surface-area-guided collapse into compressed 8-wide nodes.  Asynchronous apart from one
+ * 8-byte read-back per tree level. */
+DP_API int dp_build_bvh(dp_ctx *ctx, void *stream);
+/* Camera-frame copy of the mesh: v' = float32(T * (double)v) (:549-550 then :245), followed by
+ * a bottom-up refit of a second set of wide nodes that shares the object-frame topology.
+ * T: 16 doubles on the HOST, row-major. */
+DP_API int dp_pose_mesh(dp_ctx *ctx, const double *T, void *stream);
+/* copy the camera-frame vertices of the last dp_pose_mesh out: [nV*3]; DP_F32 gives the
+ * float32 values the BVH holds, DP_F64 the float64 values before that cast (:550). */
+DP_API int dp_get_posed_vertices(dp_ctx *ctx, void *V, int vdtype, int mem, void *stream);
+
+/* ---- H1: heatmap threshold + order-preserving compaction (:165-179) ---------------------- */
+/* heat: [nframes*H*W] of `dtype`; strict '>' as np.where(heatmap > thr); NaN never passes.
+ * pixel/intensity: [cap]; *n (HOST) receives the total count (the call synchronises on it).
+ * frame_count: optional [nframes] int64 HOST array receiving the per-frame counts. */
+DP_API int dp_compact(dp_ctx *ctx, const void *heat, int dtype, int64_t nframes, int H, int W, double thr,
+                      uint32_t *pixel, float *intensity, int64_t cap, int64_t *n, int64_t *frame_count,
+                      int mem, void *stream);
+
+/* ---- H2: host helper shared with the tests ---------------------------------------------- */
+/* xf[16] = fx fy cx cy | Rinv row-major | tinv for intrinsics K[9] and a rigid pose[16];
+ * Rinv = R^T, tinv_k = -((R0k*t0 + R1k*t1) + R2k*t2).  pose == NULL gives the identity. */
+DP_API void dp_frame_xform(const double *K, const double *pose, double *xf);
+
+/* compute_rays (:196-223): rays3[i] = normalize(((xs[i]-cx)/fx, (ys[i]-cy)/fy, 1)) in float64,
+ * K: 9 HOST doubles; xs, ys: [n] int32; rays3: [n*3] float64. */
+DP_API int dp_compute_rays(dp_ctx *ctx, const int32_t *xs, const int32_t *ys, int64_t n, const double *K,
+                           double *rays3, int mem, void *stream);
+
+/* ---- H4: closest hit on explicit rays (replaces cast_rays, :256) ------------------------- */
+/* rays6: [n*6] float32 (ox,oy,oz,dx,dy,dz) as the reference builds them (:247-251).
+ * t_hit: [n] (+inf on miss); face: [n] or NULL. */
+DP_API int dp_cast_rays(dp_ctx *ctx, int frame, const float *rays6, int64_t n, float *t_hit, int32_t *face,
+                        int mem, void *stream);
+
+/* ---- H1+H2+H4+H6+H7 fused: one call per batch of frames (replaces the body of ray_tracing) */
+/* heat: [nframes*H*W]; K: [nK*9] HOST doubles, nK == 1 or nframes; pose: [nframes*16] HOST
+ * doubles (ignored, may be NULL, when frame == DP_FRAME_CAMERA: the mesh is already posed).
+ * accumulate != 0 adds every hit to the context's per-face / per-vertex accumulators.
+ * n_rays / n_hits: HOST, optional; when n_rays != NULL the call synchronises on the stream
+ * and, for mem == DP_HOST, copies only the first *n_rays entries of each array back. */
+DP_API int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nframes, int H, int W,
+                      double thr, const double *K, int64_t nK, const double *pose, int accumulate,
+                      dp_rays_out *out, int64_t *n_rays, int64_t *n_hits, int mem, void *stream);
+
+/* ---- H6/H7: accumulators (extensions named by north_star) ------------------ */
+DP_API int dp_accum_reset(dp_ctx *ctx, void *stream);
+/* hist: [nF] int32, fmax: [nF] float32, vmax: [nV] float32; any may be NULL */
+DP_API int dp_accum_get(dp_ctx *ctx, int32_t *hist, float *fmax, float *vmax, int mem, void *stream);
+/* device addresses of the accumulators, for in-place NCCL reductions by the host layer */
+DP_API int dp_accum_device_ptrs(dp_ctx *ctx, int32_t **hist, float **fmax, float **vmax);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+/* enable != 0: the next traversal launches use the counting variant of the kernel */
+DP_API int dp_set_stats(dp_ctx *ctx, int enable);
+DP_API int dp_get_stats(dp_ctx *ctx, dp_stats *out);
+/* device time (ms, CUDA events on the caller's stream) of the stages of the last dp_project:
+ * [0] compaction, [1] traversal+accumulation, [2] whole call on the device */
+DP_API int dp_last_timings(dp_ctx *ctx, float *ms3);
+/* structural dump of the wide BVH for the tests: nodes [n*80 bytes], triangle records
+ * [nt*48 bytes] (v0.xyz, face id bits, v1.xyz, 0, v2.xyz, 0).  Pass NULL to query sizes. */
+DP_API int dp_debug_dump_bvh(dp_ctx *ctx, int frame, void *nodes, int64_t *n_nodes, void *tris,
+                             int64_t *n_tris);
+/* the in-house radix sort on its own, for the structural tests: sorts (key,value) pairs
+ * of HOST arrays in place, stable, ascending by key. */
+DP_API int dp_debug_radix_sort(dp_ctx *ctx, uint32_t *keys, uint32_t *vals, int64_t n);
+/* Morton codes of the current mesh's triangles in input order: codes [nF] HOST */
+DP_API int dp_debug_morton(dp_ctx *ctx, uint32_t *codes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFECTPROJ_H */
