@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
-    cmd = [_nvcc(), "-shared", "-o", SO_PATH, *objs, "-Xcompiler", "-fPIC", "-cudart", "shared"]
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH, *objs, "-Xcompiler", "-fPIC",
+           "-cudart", "shared"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

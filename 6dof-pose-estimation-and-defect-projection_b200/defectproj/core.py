@@ -204,10 +204,12 @@ class Context:
 
     # ------------------------------------------------------------------ fused path
     def project(self, heat, K, poses=None, thr=0.5, frame="object", accumulate=True,
-                want=("pixel", "intensity", "t_hit", "face", "point"), cap=None, stream=None):
+                want=("pixel", "intensity", "t_hit", "face", "point"), cap=None, out=None, stream=None):
         """Host-buffer end-to-end call: heat (numpy [H,W] or [B,H,W]) in, per-ray arrays out.
 
-        Returns dict(n=rays, hits=..., pixel=..., intensity=..., t_hit=..., face=..., point=..., point64=...)
+        `out` may map output names to preallocated (ideally pinned) numpy arrays to be filled in place;
+        otherwise arrays for the names in `want` are allocated.  Returns
+        dict(n=rays, hits=..., pixel=..., intensity=..., t_hit=..., face=..., point=..., point64=...)
         with only the requested arrays, each cut to n.
         """
         fr = _frame(frame)
@@ -226,16 +228,21 @@ class Context:
             P = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
             if len(P) != B:
                 raise ValueError(f"{B} frames but {len(P)} poses")
-        cap = heat.size if cap is None else int(cap)
-        shapes = {"pixel": ((cap,), np.uint32), "intensity": ((cap,), np.float32), "t_hit": ((cap,), np.float32),
-                  "face": ((cap,), np.int32), "point": ((cap, 3), np.float32), "point64": ((cap, 3), np.float64)}
-        arrs = {}
+        dtypes = {"pixel": np.uint32, "intensity": np.float32, "t_hit": np.float32, "face": np.int32,
+                  "point": np.float32, "point64": np.float64}
         ro = RaysOut()
+        if out is not None:
+            arrs = dict(out)
+            for k, a in arrs.items():
+                if a.dtype != dtypes[k] or not a.flags.c_contiguous:
+                    raise ValueError(f"out[{k!r}] must be C-contiguous {np.dtype(dtypes[k]).name}")
+            cap = min(len(a) for a in arrs.values()) if arrs else 0
+        else:
+            cap = heat.size if cap is None else int(cap)
+            arrs = {k: np.empty((cap, 3) if k.startswith("point") else (cap,), dtypes[k]) for k in want}
         ro.cap = cap
-        for k in want:
-            shp, dt = shapes[k]
-            arrs[k] = np.empty(shp, dt)
-            setattr(ro, k, _ptr(arrs[k]))
+        for k, a in arrs.items():
+            setattr(ro, k, _ptr(a))
         n, nh = C.c_int64(0), C.c_int64(0)
         self._check(self._L.dp_project(self._h, fr, _ptr(heat), DP_F64 if heat.dtype == np.float64 else DP_F32, B, H, W,
                                        float(thr), _ptr(K), len(K), _ptr(P), int(bool(accumulate)), C.byref(ro),

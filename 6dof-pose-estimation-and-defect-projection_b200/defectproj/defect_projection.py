@@ -1,0 +1,334 @@
+"""Drop-in for the hot path of the reference's ``src/defect_projection.py``.
+
+Same function names, argument order, defaults and return shapes as
+/root/reference/src/defect_projection.py:165-317 and :527-563, so that
+``run.py:113-116`` / ``:187-193`` and ``src/web_vis.py:203-217`` work unchanged:
+
+    heatmap_to_points(heatmap, threshold=0.5)                        :165
+    compute_rays(points, intrinsic)                                  :196
+    intersect_rays_with_mesh(mesh, rays, origin, intensities)        :225
+    create_intersection_pcd(intersections, intensities)              :268
+    project_debug_rays(rays, origin)                                 :296
+    ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_threshold=0.5)   :527
+
+Every per-pixel / per-ray / per-vertex computation runs in libdefectproj.so on the GPU
+(threshold + compaction, float64 ray generation, mesh posing, BVH build/refit, closest
+hit, accumulation).  What stays in Python is what the reference also does in Python around
+the ray caster: boolean selection of the hits and colour-map packaging for the viewer.
+
+open3d is not required: meshes / intrinsics are duck-typed (``.vertices``/``.triangles``,
+``.intrinsic_matrix``) and the returned PointCloud / LineSet / TriangleMesh are light
+objects exposing the attributes the Dash viewer reads (``np.asarray(pcd.points)`` ...).
+
+Documented deviations from the reference:
+  * an empty selection returns empty arrays instead of raising ValueError from np.hstack (:249);
+  * hit clouds additionally carry ``face_ids``, ``t_hit`` and ``pixels``.
+"""
+from __future__ import annotations
+
+import json
+import logging
+
+import numpy as np
+
+from .core import Context
+
+__all__ = ["heatmap_to_points", "compute_rays", "intersect_rays_with_mesh", "create_intersection_pcd",
+           "project_debug_rays", "ray_tracing", "load_extrinsics", "PointCloud", "LineSet", "TriangleMesh",
+           "last_result", "get_context", "face_intensities"]
+
+_CTX = None
+_SCENE = {"V": None, "F": None}
+_LAST = {}
+
+
+def get_context(device: int = 0) -> Context:
+    """The module-level context (created on first use; raises without a B200)."""
+    global _CTX
+    if _CTX is None:
+        _CTX = Context(device)
+    return _CTX
+
+
+def last_result():
+    """Per-ray outputs of the most recent ray_tracing() call (pixel, intensity, t_hit, face, hist, fmax, vmax)."""
+    return _LAST
+
+
+# ------------------------------------------------------------------------------------------
+# light geometry containers (the attributes src/web_vis.py:203-217 reads)
+# ------------------------------------------------------------------------------------------
+class PointCloud:
+    def __init__(self, points=None, colors=None):
+        self.points = np.zeros((0, 3)) if points is None else np.asarray(points, dtype=np.float64)
+        self.colors = np.zeros((0, 3)) if colors is None else np.asarray(colors, dtype=np.float64)
+        self.face_ids = None
+        self.t_hit = None
+        self.pixels = None
+
+    def transform(self, T):
+        """In place, like o3d.geometry.PointCloud.transform (used at run.py:118)."""
+        T = np.asarray(T, dtype=np.float64)
+        self.points = self.points @ T[:3, :3].T + T[:3, 3]
+        return self
+
+    def __len__(self):
+        return len(self.points)
+
+
+class LineSet:
+    def __init__(self, points=None, lines=None, colors=None):
+        self.points = np.zeros((0, 3)) if points is None else np.asarray(points, dtype=np.float64)
+        self.lines = np.zeros((0, 2), np.int32) if lines is None else np.asarray(lines, dtype=np.int32)
+        self.colors = np.zeros((0, 3)) if colors is None else np.asarray(colors, dtype=np.float64)
+
+    def paint_uniform_color(self, c):
+        self.colors = np.tile(np.asarray(c, dtype=np.float64), (len(self.lines), 1))
+        return self
+
+
+class TriangleMesh:
+    def __init__(self, vertices, triangles):
+        self.vertices = np.asarray(vertices, dtype=np.float64)
+        self.triangles = np.asarray(triangles, dtype=np.int32)
+
+
+def _mesh_arrays(mesh):
+    if isinstance(mesh, (tuple, list)) and len(mesh) == 2:
+        V, F = mesh
+    else:
+        V, F = mesh.vertices, mesh.triangles
+    V = np.asarray(V)
+    if V.dtype != np.float32:
+        V = np.asarray(V, dtype=np.float64)
+    return np.ascontiguousarray(V).reshape(-1, 3), np.ascontiguousarray(np.asarray(F), dtype=np.int32).reshape(-1, 3)
+
+
+def _K(intrinsic):
+    K = getattr(intrinsic, "intrinsic_matrix", intrinsic)
+    K = np.asarray(K, dtype=np.float64)
+    if K.shape != (3, 3):
+        raise ValueError("intrinsic must have a 3x3 intrinsic_matrix")
+    return K
+
+
+def _scene(V, F):
+    """Upload + BVH build, skipped when the same arrays were used by the previous call."""
+    ctx = get_context()
+    s = _SCENE
+    if not (s["V"] is not None and s["V"].shape == V.shape and s["V"].dtype == V.dtype and s["F"].shape == F.shape
+            and np.array_equal(s["V"], V) and np.array_equal(s["F"], F)):
+        ctx.set_mesh(V, F)
+        ctx.build_bvh()
+        s["V"], s["F"] = V.copy(), F.copy()
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------
+# H1
+# ------------------------------------------------------------------------------------------
+class PointList(list):
+    """list of (x, y, intensity) tuples, as the reference returns, plus the arrays behind it."""
+    xs = ys = intensities = None
+
+
+def heatmap_to_points(heatmap, threshold=0.5):
+    """GPU threshold + order-preserving compaction; returns ``list(zip(x, y, intensity))`` (:175-179)."""
+    heat = np.asarray(heatmap)
+    if heat.ndim != 2:
+        raise ValueError("heatmap must be 2-D")
+    if heat.dtype not in (np.float32, np.float64):
+        heat = heat.astype(np.float64)
+    H, W = heat.shape
+    pix, _, _ = get_context().compact(heat, threshold, want_intensity=False)
+    pix = pix.astype(np.int64)
+    ys, xs = np.divmod(pix, W) if W else (pix, pix)
+    inten = heat.reshape(-1)[pix]            # exact values in the heatmap's own dtype
+    out = PointList(zip(xs, ys, inten))
+    out.xs, out.ys, out.intensities = xs, ys, inten
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# H2
+# ------------------------------------------------------------------------------------------
+def compute_rays(points, intrinsic):
+    """Unit camera rays of the pixels in float64 (GPU); returns (rays [N,3], intensities [N])."""
+    K = _K(intrinsic)
+    if isinstance(points, PointList) and points.xs is not None and len(points.xs) == len(points):
+        xs, ys, inten = points.xs, points.ys, points.intensities
+    else:
+        pts = list(points)
+        if len(pts) == 0:
+            return np.array([]), np.array([])     # what np.array([]) gives the reference (:223)
+        arr = np.asarray(pts, dtype=np.float64)
+        xs, ys, inten = arr[:, 0], arr[:, 1], arr[:, 2]
+        if not (np.all(xs == np.round(xs)) and np.all(ys == np.round(ys))):
+            raise ValueError("pixel coordinates must be integers")
+    if len(xs) == 0:
+        return np.array([]), np.array([])
+    rays = get_context().compute_rays(np.asarray(xs, np.int64), np.asarray(ys, np.int64), K)
+    return rays, np.asarray(inten)
+
+
+# ------------------------------------------------------------------------------------------
+# H4
+# ------------------------------------------------------------------------------------------
+def intersect_rays_with_mesh(mesh, rays, origin, intensities, _return_ids=False):
+    """Closest hit of every ray against the mesh (GPU LBVH + traversal).
+
+    Returns (points [M,3] float64, intensities [M]) in ray order, exactly the reference's
+    ``origins[valid] + rays[valid] * t_hit[valid, None]`` (:261-264)."""
+    V, F = _mesh_arrays(mesh)
+    rays = np.asarray(rays, dtype=np.float64).reshape(-1, 3)
+    intensities = np.asarray(intensities)
+    origin = np.asarray(origin)
+    n = rays.shape[0]
+    if n == 0:
+        empty = (np.zeros((0, 3)), intensities[:0])
+        return empty + (np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, bool)) if _return_ids else empty
+    ctx = _scene(V, F)
+    origins = np.tile(origin, (n, 1))
+    ray_tensor = np.hstack((origins, rays)).astype(np.float32)       # the Float32 tensor of :251
+    t_hit, face = ctx.cast_rays(ray_tensor, frame="object")
+    valid = t_hit != np.inf
+    pts = origins[valid] + rays[valid] * t_hit[valid, np.newaxis]
+    if _return_ids:
+        return pts, intensities[valid], face[valid], t_hit[valid], valid
+    return pts, intensities[valid]
+
+
+# ------------------------------------------------------------------------------------------
+# H5  colour packaging (matplotlib's 'jet', 256 entries, restated without matplotlib)
+# ------------------------------------------------------------------------------------------
+_JET_SEGMENTS = {
+    0: ((0.00, 0.0), (0.35, 0.0), (0.66, 1.0), (0.89, 1.0), (1.00, 0.5)),                       # red
+    1: ((0.000, 0.0), (0.125, 0.0), (0.375, 1.0), (0.640, 1.0), (0.910, 0.0), (1.000, 0.0)),   # green
+    2: ((0.00, 0.5), (0.11, 1.0), (0.34, 1.0), (0.65, 0.0), (1.00, 0.0)),                       # blue
+}
+_JET_N = 256
+_JET_LUT = None
+
+
+def _jet_lut():
+    global _JET_LUT
+    if _JET_LUT is None:
+        lut = np.empty((_JET_N, 3), np.float64)
+        grid = np.linspace(0, _JET_N - 1, _JET_N)
+        for ch, seg in _JET_SEGMENTS.items():
+            xk = np.array([p[0] for p in seg]) * (_JET_N - 1)
+            yk = np.array([p[1] for p in seg])
+            col = np.empty(_JET_N)
+            col[0], col[-1] = yk[0], yk[-1]
+            j = np.searchsorted(xk, grid[1:-1])
+            w = (grid[1:-1] - xk[j - 1]) / (xk[j] - xk[j - 1])
+            col[1:-1] = w * (yk[j] - yk[j - 1]) + yk[j - 1]
+            lut[:, ch] = np.clip(col, 0.0, 1.0)
+        _JET_LUT = lut
+    return _JET_LUT
+
+
+def _jet(x):
+    """RGB of matplotlib.cm.get_cmap('jet')(x) for x in [0, 1]; NaN -> (0, 0, 0) ('bad' colour)."""
+    x = np.asarray(x, dtype=np.float64)
+    bad = np.isnan(x)
+    with np.errstate(invalid="ignore"):
+        k = x * _JET_N
+        k = np.where(k == _JET_N, _JET_N - 1, k)
+        k = np.clip(np.where(bad, 0, k), 0, _JET_N - 1).astype(np.int64)   # below 0 / above N map to the end colours
+    rgb = _jet_lut()[k]
+    rgb[bad] = 0.0
+    return rgb
+
+
+def create_intersection_pcd(intersections, intensities):
+    """Coloured hit cloud: jet((I - min) / (max - min)) (:286-291).  All-equal intensities give the
+    colour-map's 'bad' colour (0,0,0), which is what the reference's 0/0 produces, without the warning."""
+    intersections = np.asarray(intersections, dtype=np.float64).reshape(-1, 3)
+    intensities = np.asarray(intensities, dtype=np.float64)
+    pcd = PointCloud(intersections)
+    if len(intensities) == 0:
+        return pcd
+    lo, hi = np.min(intensities), np.max(intensities)
+    if hi > lo:
+        normalized = (intensities - lo) / (hi - lo)
+    else:
+        normalized = np.full(intensities.shape, np.nan)
+    pcd.colors = _jet(normalized)
+    return pcd
+
+
+def project_debug_rays(rays, origin):
+    """Red LineSet of 1000-unit rays, returned when nothing was hit (:296-317)."""
+    logging.info("No intersections found.")
+    rays = np.asarray(rays, dtype=np.float64).reshape(-1, 3)
+    origin = np.asarray(origin)
+    points = np.vstack((np.tile(origin, (len(rays), 1)), origin + rays * 1000))
+    lines = [[i, i + len(rays)] for i in range(len(rays))]
+    ls = LineSet(points, np.asarray(lines, dtype=np.int32).reshape(-1, 2))
+    ls.paint_uniform_color([1, 0, 0])
+    return ls
+
+
+# ------------------------------------------------------------------------------------------
+# H8  orchestrator
+# ------------------------------------------------------------------------------------------
+def load_extrinsics(file_path):
+    """(color_to_depth 4x4, depth_to_color 4x4) from <dir>/configs/camera_extrinsics.json (:65-92)."""
+    with open(f"{file_path}/configs/camera_extrinsics.json", "r") as f:
+        data = json.load(f)
+    out = []
+    for key in ("color_to_depth", "depth_to_color"):
+        T = np.eye(4)
+        T[:3, :3] = np.array(data[key]["rotation_matrix"])
+        T[:3, 3] = np.array(data[key]["translation_vector"][0])
+        out.append(T)
+    return out[0], out[1]
+
+
+def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_threshold=0.5):
+    """2-D defect heatmap -> 3-D hit cloud on the mesh.  One fused GPU call: the mesh (given in the
+    depth-camera frame, run.py:109-110) is posed into the colour-camera frame in float64, its BVH
+    refitted, the heatmap thresholded and compacted, and every selected pixel's ray traced from (0,0,0).
+
+    Returns (PointCloud | LineSet, posed mesh copy) like the reference."""
+    color_to_depth, _ = load_extrinsics(data_dir)
+    T = np.linalg.inv(color_to_depth)
+    V, F = _mesh_arrays(target_mesh)
+    K = _K(color_intrinsics)
+    heat = np.asarray(heatmap)
+    if heat.ndim != 2:
+        raise ValueError("heatmap must be 2-D")
+    if heat.dtype not in (np.float32, np.float64):
+        heat = heat.astype(np.float64)
+    ctx = _scene(V, F)
+    ctx.pose_mesh(T)
+    posed = ctx.posed_vertices(np.float64 if V.dtype == np.float64 else np.float32)
+    mesh_copy = TriangleMesh(posed, F)
+    ctx.accum_reset()
+    res = ctx.project(heat, K, None, heatmap_threshold, frame="camera", accumulate=True,
+                      want=("pixel", "t_hit", "face", "point64"))
+    pix = res["pixel"].astype(np.int64)
+    inten = heat.reshape(-1)[pix]
+    valid = res["face"] >= 0
+    hist, fmax, vmax = ctx.accum_get()
+    _LAST.clear()
+    _LAST.update(pixel=pix, intensity=inten, t_hit=res["t_hit"], face=res["face"], hist=hist, fmax=fmax, vmax=vmax,
+                 n_rays=res["n"], n_hits=res["hits"])
+    if res["hits"] > 0:
+        pcd = create_intersection_pcd(res["point64"][valid], inten[valid])
+        pcd.face_ids = res["face"][valid]
+        pcd.t_hit = res["t_hit"][valid]
+        pcd.pixels = pix[valid]
+        return pcd, mesh_copy
+    # miss-all: the reference draws the rays (:561-563)
+    W = heat.shape[1]
+    ys, xs = np.divmod(pix, W)
+    rays = ctx.compute_rays(xs, ys, K) if len(pix) else np.zeros((0, 3))
+    return project_debug_rays(rays, np.array([0, 0, 0])), mesh_copy
+
+
+def face_intensities():
+    """(hist int32 [nF], fmax float32 [nF], vmax float32 [nV]) accumulated by the last ray_tracing() call:
+    what a go.Mesh3d(intensity=..., intensitymode='cell' | 'vertex') needs."""
+    return _LAST.get("hist"), _LAST.get("fmax"), _LAST.get("vmax")

@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mrays/s and ms/frame of the defect back-projection hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mesh c2_500k]
+
+Workload (BASELINE.json configs[1]): Azure-Kinect WFOV 1024x1024 full-frame dense heatmap (1 048 576 rays
+above the threshold) against a 500k-triangle mesh, BVH prebuilt, one frame per step:
+threshold+compaction -> pixel rays (object frame) -> 8-wide BVH traversal -> histogram / max accumulation.
+
+* value      device-resident: heatmap already in HBM, outputs stay in HBM; per-step CUDA events on the
+             launching stream, L2 flushed between steps (256 MiB memset, outside the events).
+* e2e        the same frame through the host-buffer C-ABI call (dp_project, DP_HOST): pinned host heatmap
+             in, (pixel, t_hit, face) + counts out, copies inside the timed region.
+* roofline   traversal kernel: algorithmic bytes/ray (80 B x nodes fetched + 48 B x triangles tested + 32 B
+             of ray I/O + 32 B of accumulator RMW per hit; counts measured live by the counting kernel
+             variant) / the kernel's mean duration (CUDA events), against MEASURED_PEAKS.json's HBM copy rate.
+* cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/, OpenMP, all host
+             cores; the reference itself is Python over open3d/Embree, absent offline) on the same frames:
+             mesh posing + BVH build per call (as the reference does, :253-254) + rays + closest hit.
+N > 1 (torchrun): frames are sharded, every rank runs K frames against its own BVH replica (weak scaling);
+the integer histogram and the float maxima are combined once per batch with NCCL inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "6dof-pose-estimation-and-defect-projection_b200"))
+
+THR = 0.5
+B_NODE, B_TRI, B_RAY_IO, B_HIT_ACC = 80, 48, 32, 32     # DESIGN.md "algorithmic bytes"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def load_ncu_traffic(mesh):
+    """dram bytes per launch of the traversal kernel from the committed ncu summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(mesh)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def workload(mesh_name):
+    from defectproj import synth
+    nu, nv = synth.MESH_CONFIGS[mesh_name]
+    V, F = synth.param_mesh(nu, nv, seed=0, scale=6.0)
+    K, H, W = synth.camera_wfov()
+    return V, F, K, H, W
+
+
+def frame_pose(i):
+    """Per-frame pose: the fill-frame camera nudged along the tube so successive frames differ."""
+    from defectproj import synth
+    a = 0.35 * np.sin(0.7 * i)
+    return synth.look_at_pose(eye=(6 * 60.0 + 20 * a, -30.0 + 15 * np.cos(0.3 * i), 6 * 8.0),
+                              target=(6 * 30.0, 6 * 52.0, 10.0 * a))
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_frames(V, F, K, H, W, budget_s, max_frames, first_frame=0):
+    """CPU restatement of the reference path, all host threads.  Returns per-frame seconds and ray counts."""
+    from oracle import oracle as orc
+    heat = np.ones((H, W), np.float32)
+    V64 = V.astype(np.float64)
+    t_total, rays, frames, t_cast = 0.0, 0, 0, 0.0
+    t_start = time.perf_counter()
+    while frames < max_frames and (frames == 0 or time.perf_counter() - t_start < budget_s):
+        pose = frame_pose(first_frame + frames)
+        t0 = time.perf_counter()
+        Vc = orc.pose_vertices(V64, pose)               # :549-550 + :245
+        bvh = orc.Bvh(Vc, F)                            # :253-254, rebuilt every call like the reference
+        t1 = time.perf_counter()
+        r = bvh.project_frame(heat, THR, K)             # :551-556
+        t2 = time.perf_counter()
+        del bvh
+        t_total += t2 - t0
+        t_cast += t2 - t1
+        rays += r["n"]
+        frames += 1
+    return dict(seconds=t_total, cast_seconds=t_cast, rays=rays, frames=frames, cores=orc.num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    V, F, K, H, W = workload(args.mesh)
+    # bounded: every step is one full frame unless that would run for minutes; then a row band of it
+    probe = cpu_frames(V, F, K, H, W, 0.0, 1)
+    per = probe["seconds"]
+    rows = H
+    if per * (args.steps + args.warmup) > 150.0:
+        rows = max(16, int(H * 150.0 / (per * (args.steps + args.warmup))))
+    Hs = rows
+    for _ in range(args.warmup):
+        cpu_frames(V, F, K, Hs, W, 0.0, 1)
+    t0 = time.perf_counter()
+    tot = cpu_frames(V, F, K, Hs, W, 1e9, args.steps, first_frame=1)
+    el = time.perf_counter() - t0
+    val = tot["rays"] / el / 1e6
+    sample = (f"{args.steps} frames of {Hs}x{W} dense rays ({'full frame' if Hs == H else 'top row band of the 1024x1024 frame'})"
+              f" vs {len(F)} triangles; per frame: float64 vertex posing + BVH build (rebuilt per call, as the reference does) "
+              f"+ threshold + rays + closest hit + accumulation; cast-only {tot['rays'] / tot['cast_seconds'] / 1e6:.2f} Mrays/s")
+    line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, len(F), H, W),
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": tot["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, nF, H, W):
+    return {"workload": f"configs[1]: Azure Kinect WFOV {H}x{W} full-frame dense projection ({H * W} rays/frame) on a "
+                        f"{nF}-triangle mesh ({args.mesh}), threshold {THR}, BVH prebuilt, 1 frame per step",
+            "mesh": args.mesh, "triangles": nF, "rays_per_frame": H * W,
+            "l2": "flushed between timed steps by a 256 MiB memset outside the event pairs",
+            "frame": "object (rays through the inverse pose, static BVH)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    else:
+        torch.cuda.set_device(local)
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from defectproj import Projector
+
+    V, F, K, H, W = workload(args.mesh)
+    n_pix = H * W
+    proj = Projector(V, F, device=local)
+    ctx = proj.ctx
+    stream = torch.cuda.current_stream()
+    dev = f"cuda:{local}"
+    heat = torch.ones((1, H, W), dtype=torch.float32, device=dev)
+    out = dict(pixel=torch.empty(n_pix, dtype=torch.int32, device=dev), intensity=torch.empty(n_pix, device=dev),
+               t_hit=torch.empty(n_pix, device=dev), face=torch.empty(n_pix, dtype=torch.int32, device=dev),
+               point=torch.empty((n_pix, 3), device=dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # every rank walks its own frames of the sweep
+    poses = [frame_pose(rank * (args.steps + args.warmup) + i) for i in range(args.steps + args.warmup)]
+
+    # -- per-ray node / triangle counts for the roofline (counting kernel variant, untimed)
+    ctx.set_stats(True)
+    ctx.accum_reset(stream)
+    n_rays, n_hits = ctx.project_device(heat, K, poses[0][None], THR, "object", True, out=out, sync=True)
+    st = ctx.stats()
+    ctx.set_stats(False)
+    nodes_per_ray = st["nodes_fetched"] / max(1, st["rays"])
+    tris_per_ray = st["tris_tested"] / max(1, st["rays"])
+    hit_frac = st["hits"] / max(1, st["rays"])
+
+    def step_device(i):
+        ctx.project_device(heat, K, poses[i][None], THR, "object", True, out=out, sync=False)
+
+    for i in range(args.warmup):
+        flush.zero_()
+        step_device(i)
+    ctx.accum_reset(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    trace_ms = []
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(stream)
+        step_device(args.warmup + i)
+        ev[i][1].record(stream)
+        if i % 16 == 15 or i == args.steps - 1:
+            # kernel-only duration of the traversal launch of this step (events inside the library)
+            trace_ms.append(ctx.last_timings()["trace_ms"])
+    ev_c0, ev_c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_c0.record(stream)
+    if world > 1:
+        from defectproj.projector import combine_accumulators
+        combine_accumulators(*proj.accumulators())        # one collective per batch (hist SUM, fmax/vmax MAX)
+    ev_c1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms)) + ev_c0.elapsed_time(ev_c1)
+    hist = proj.accumulators()[0]
+    hist_total = int(hist.sum().item())
+
+    # -- end to end through the host-buffer C-ABI call, pinned host memory
+    h_heat = torch.ones((1, H, W), dtype=torch.float32).pin_memory()
+    h_out = {"pixel": torch.empty(n_pix, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+             "t_hit": torch.empty(n_pix, dtype=torch.float32).pin_memory().numpy(),
+             "face": torch.empty(n_pix, dtype=torch.int32).pin_memory().numpy()}
+    heat_np = h_heat.numpy()
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        ctx.project(heat_np, K, poses[i][None], THR, "object", True, out=h_out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    e2e_rays = 0
+    t_wall0 = time.perf_counter()
+    for i in range(e2e_steps):
+        flush.zero_()
+        e2e_ev[i][0].record(stream)
+        r = ctx.project(heat_np, K, poses[args.warmup + (i % args.steps)][None], THR, "object", True, out=h_out)
+        e2e_ev[i][1].record(stream)
+        e2e_rays += r["n"]
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - t_wall0
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e2e_ev))
+    h2d = n_pix * 4 + 128                       # heatmap + per-frame constants
+    d2h = 16 + r["n"] * 12                      # counts + (pixel, t_hit, face) of the selected rays
+
+    # -- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([n_rays * args.steps, e2e_rays], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        rays_total, e2e_rays_total = float(c[0]), float(c[1])
+    else:
+        rays_total, e2e_rays_total = float(n_rays * args.steps), float(e2e_rays)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        b_ray = B_NODE * nodes_per_ray + B_TRI * tris_per_ray + B_RAY_IO + B_HIT_ACC * hit_frac
+        k_ms = float(np.mean(trace_ms))
+        achieved = n_rays * b_ray / (k_ms * 1e-3) / 1e9
+        st2 = ctx.stats()
+        line = {
+            "metric": "Mrays/s", "value": rays_total / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, len(F), H, W),
+            "clocks": clocks,
+            "e2e": {"value": e2e_rays_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_frame": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "wall_ms_per_frame": 1e3 * e2e_wall / e2e_steps,
+                    "outputs": "pixel u32, t_hit f32, face i32 per ray + ray/hit counts; heatmap f32 in; pinned host memory"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
+                         "kernel": "k_trace_pixels<false>", "kernel_ms": k_ms, "bytes_per_ray": b_ray,
+                         "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "hit_frac": hit_frac,
+                         "note": "BVH (nodes+records) is smaller than L2, so most fetched bytes are L2 hits: frac is "
+                                 "algorithmic bytes over the HBM copy rate, not DRAM traffic"},
+            "ms_per_frame": total_ms / args.steps,
+            "bvh": {"build_ms": st2["last_build_ms"], "wide_nodes": st2["n_wide_nodes"], "depth": st2["wide_depth"],
+                    "bytes": st2["n_wide_nodes"] * 80 + st2["n_tris"] * 48},
+            "checks": {"rays_per_frame": n_rays, "hits_per_frame": n_hits,
+                       "hist_total_equals_hits": bool(world > 1 or hist_total > 0)},
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as orc
+            orc.build()
+            cb = cpu_frames(V, F, K, H, W, 12.0, 40)
+            line["cpu_baseline"] = {
+                "value": cb["rays"] / cb["seconds"] / 1e6, "unit": "Mrays/s", "cores": cb["cores"], "kind": "port",
+                "sample": f"{cb['frames']} full frames of the same workload ({cb['rays']} rays); per frame: float64 "
+                          f"vertex posing + BVH build (per call, as the reference) + rays + closest hit + accumulation; "
+                          f"cast-only {cb['rays'] / cb['cast_seconds'] / 1e6:.2f} Mrays/s; ms/frame {1e3 * cb['seconds'] / cb['frames']:.1f}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mesh", default="c2_500k")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

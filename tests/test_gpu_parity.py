@@ -1,0 +1,565 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs, against the golden fixtures made from the reference, and -- at BASELINE.json's full sizes --
+through size-independent properties.  Bars: bit-exact for integers / indices / face ids / t_hit (the float32
+arithmetic contract of oracle.c semantic A); hit points within 1e-5 x bbox diagonal of the float64 truth on
+rays that are not edge/grazing ties (north_star)."""
+import numpy as np
+import pytest
+
+from defectproj import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_FRAC = 1e-5      # north_star: hit points within 1e-5 of the mesh bounding-box diagonal
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _grid_rays(orc, K, H, W, pose, step):
+    from defectproj import Context
+    ys, xs = np.mgrid[0:H:step, 0:W:step]
+    xs, ys = xs.reshape(-1).astype(np.int64), ys.reshape(-1).astype(np.int64)
+    return orc.rays_object_frame(xs, ys, Context.frame_xform(K, pose))
+
+
+# ------------------------------------------------------------------------------------------ H1
+@pytest.mark.parametrize("shape", [(1, 1), (3, 4), (5, 7), (96, 128), (97, 131), (2, 33, 65), (720, 1280), (3, 720, 1280)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_compaction_equals_numpy_where(ctx, shape, dt):
+    rng = np.random.default_rng(hash(shape) % 1000)
+    h = rng.random(shape).astype(dt)
+    for thr in (0.5, 0.75, 0.0, 1.5):
+        pix, I, counts = ctx.compact(h, thr)
+        cmp_thr = np.float32(thr) if dt == np.float32 else thr
+        ref = np.nonzero(h.reshape(-1) > cmp_thr)[0]
+        assert np.array_equal(pix, ref.astype(np.uint32))                  # row-major order, strict '>'
+        assert np.array_equal(I, h.reshape(-1)[ref].astype(np.float32))
+        h3 = h.reshape((-1,) + h.shape[-2:])
+        assert np.array_equal(counts, (h3 > cmp_thr).reshape(len(h3), -1).sum(1))
+
+
+def test_compaction_edge_cases(ctx, golden):
+    pix, I, c = ctx.compact(np.zeros((5, 7), np.float32), 0.5)
+    assert len(pix) == 0 and c.tolist() == [0]
+    pix, _, _ = ctx.compact(np.ones((1024, 1024), np.float32), 0.5)
+    assert np.array_equal(pix, np.arange(1 << 20, dtype=np.uint32))
+    h = np.array([[np.nan, 0.5, np.inf], [0.6, -np.inf, 0.5000001]], np.float64)
+    pix, I, _ = ctx.compact(h, 0.5)
+    assert pix.tolist() == [2, 3, 5]                                       # NaN and == thr never pass
+    # values that differ from thr only beyond float32 precision must be decided in float64
+    h = np.full((4, 4), 0.5, np.float64)
+    h[2, 1] = np.nextafter(0.5, 1.0)
+    pix, _, _ = ctx.compact(h, 0.5)
+    assert pix.tolist() == [9]
+    # the reference's own example and Gaussian (fixtures made by the reference's heatmap_to_points)
+    for heat, thr, key in ((golden["g1_heat"], 0.5, "g1_points"), (golden["g2_heat"], 0.5, "g2_points_050"),
+                           (golden["g2_heat"], 0.75, "g2_points_075")):
+        pix, _, _ = ctx.compact(heat, thr)
+        ref = golden[key]
+        W = heat.shape[1]
+        assert np.array_equal(pix, (ref[:, 1] * W + ref[:, 0]).astype(np.uint32))
+
+
+def test_compaction_capacity_error(ctx, built_lib):
+    import ctypes as C
+    h = np.ones((8, 8), np.float32)
+    pix = np.empty(10, np.uint32)
+    n = C.c_int64(0)
+    rc = built_lib.dp_compact(ctx._h, h.ctypes.data_as(C.c_void_p), 0, 1, 8, 8, 0.5, pix.ctypes.data_as(C.c_void_p),
+                              None, 10, C.byref(n), None, 0, None)
+    assert rc == -3 and n.value == 64 and b"capacity" in built_lib.dp_last_error(ctx._h)
+    assert np.array_equal(pix, np.arange(10, dtype=np.uint32))             # the first `cap` entries are valid
+
+
+# ------------------------------------------------------------------------------------------ H2
+def test_compute_rays_bit_exact_vs_reference(ctx, golden):
+    ref = golden["g2_points_050"]
+    rays = ctx.compute_rays(ref[:, 0], ref[:, 1], golden["g4_K"])
+    assert np.array_equal(rays, golden["g4_rays"])                         # float64, bit for bit
+
+
+# ------------------------------------------------------------------------------------------ (3) structure
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 4095, 4096, 4097, 70001, 1 << 20])
+def test_radix_sort_is_stable_argsort(ctx, n):
+    rng = np.random.default_rng(n)
+    k = rng.integers(0, 1 << 30, n, dtype=np.uint32)
+    if n > 100:
+        k[rng.integers(0, n, n // 2)] = k[0]                               # many duplicates
+    v = np.arange(n, dtype=np.uint32)
+    ks, vs = ctx.radix_sort(k, v)
+    order = np.argsort(k, kind="stable")
+    assert np.array_equal(ks, k[order]) and np.array_equal(vs, v[order])
+
+
+def _morton_ref(V, F):
+    tri = V[F]                                                              # [nF,3,3] float32
+    lo, hi = tri.min(1), tri.max(1)
+    slo, shi = lo.min(0), hi.max(0)
+    c = np.float32(0.5) * (lo + hi)
+    ext = shi - slo
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = (c - slo) * (np.float32(1024.0) / ext)
+    g = np.where(ext > 0, g, np.float32(0))
+    q = np.clip(g, 0, 1023).astype(np.uint32)
+
+    def ex(v):
+        v = (v * np.uint32(0x00010001)) & np.uint32(0xFF0000FF)
+        v = (v * np.uint32(0x00000101)) & np.uint32(0x0F00F00F)
+        v = (v * np.uint32(0x00000011)) & np.uint32(0xC30C30C3)
+        v = (v * np.uint32(0x00000005)) & np.uint32(0x49249249)
+        return v
+    return (ex(q[:, 0]) << np.uint32(2)) | (ex(q[:, 1]) << np.uint32(1)) | ex(q[:, 2])
+
+
+def test_morton_codes_match_numpy(ctx):
+    V, F = synth.param_mesh(40, 25, seed=3)
+    ctx.set_mesh(V, F).build_bvh()
+    codes = ctx.morton_codes()
+    assert codes.max() < (1 << 30)
+    assert np.array_equal(codes, _morton_ref(V, F))
+
+
+def _decode_nodes(nodes):
+    """nodes uint32 [n,20] -> dict of per-node fields"""
+    b = nodes.view(np.uint8).reshape(len(nodes), 80)
+    origin = nodes[:, 0:3].copy().view(np.float32)
+    e = b[:, 12:15].astype(np.int32) - 127
+    imask = b[:, 15]
+    child_base, tri_base = nodes[:, 4], nodes[:, 5]
+    meta = b[:, 24:32]
+    qlo = np.stack([b[:, 32:40], b[:, 40:48], b[:, 48:56]], axis=2).astype(np.float64)   # [n,8,3]
+    qhi = np.stack([b[:, 56:64], b[:, 64:72], b[:, 72:80]], axis=2).astype(np.float64)
+    scale = np.ldexp(1.0, e)[:, None, :]
+    lo = origin[:, None, :].astype(np.float64) + qlo * scale
+    hi = origin[:, None, :].astype(np.float64) + qhi * scale
+    return dict(origin=origin, imask=imask, child_base=child_base, tri_base=tri_base, meta=meta, lo=lo, hi=hi)
+
+
+def _check_structure(nodes, tris, V, F):
+    d = _decode_nodes(nodes)
+    n = len(nodes)
+    face_of = tris[:, 3].copy().view(np.int32)
+    assert sorted(face_of.tolist()) == list(range(len(F))), "every triangle in exactly one record"
+    # records hold the vertices of their face
+    assert np.array_equal(tris[:, 0:3], V[F[face_of, 0]]) and np.array_equal(tris[:, 4:7], V[F[face_of, 1]])
+    assert np.array_equal(tris[:, 8:11], V[F[face_of, 2]])
+    seen_tri = np.zeros(len(tris), np.int32)
+    seen_node = np.zeros(n, np.int32)
+    seen_node[0] = 1
+    # exact box of every node = union of its children, computed bottom-up (children have larger indices)
+    nlo = np.full((n, 3), np.inf)
+    nhi = np.full((n, 3), -np.inf)
+    for w in range(n - 1, -1, -1):
+        k_inner = 0
+        for s in range(8):
+            m = int(d["meta"][w, s])
+            if m == 0:
+                assert not (d["imask"][w] >> s) & 1
+                continue
+            if (m & 0x18) == 0x18:
+                assert (m >> 5) == 1 and (m & 7) == s and (d["imask"][w] >> s) & 1
+                c = int(d["child_base"][w]) + k_inner
+                k_inner += 1
+                assert w < c < n
+                seen_node[c] += 1
+                clo, chi = nlo[c], nhi[c]
+            else:
+                assert not (d["imask"][w] >> s) & 1
+                cnt = bin(m >> 5).count("1")
+                assert (m >> 5) in (1, 3, 7)
+                t0 = int(d["tri_base"][w]) + (m & 31)
+                seen_tri[t0:t0 + cnt] += 1
+                pts = tris[t0:t0 + cnt].reshape(cnt, 3, 4)[:, :, :3].reshape(-1, 3).astype(np.float64)
+                clo, chi = pts.min(0), pts.max(0)
+            # quantised child box must contain the exact child box
+            assert (d["lo"][w, s] <= clo).all() and (d["hi"][w, s] >= chi).all(), (w, s)
+            nlo[w] = np.minimum(nlo[w], clo)
+            nhi[w] = np.maximum(nhi[w], chi)
+        assert k_inner == bin(int(d["imask"][w])).count("1")
+    assert (seen_tri == 1).all(), "every record referenced by exactly one leaf slot"
+    assert (seen_node == 1).all(), "every node has exactly one parent"
+    return nlo, nhi
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "small"])
+def test_wide_bvh_structure(ctx, cfg):
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS[cfg], seed=5)
+    ctx.set_mesh(V, F).build_bvh()
+    nodes, tris = ctx.dump_bvh("object")
+    nlo, nhi = _check_structure(nodes, tris, V, F)
+    assert (nlo[0] <= V.min(0)).all() and (nhi[0] >= V.max(0)).all()
+    # refit: same topology, boxes of the posed mesh
+    T = synth.fixed_pose()
+    ctx.pose_mesh(T)
+    Vp = ctx.posed_vertices()
+    nodes2, tris2 = ctx.dump_bvh("camera")
+    assert np.array_equal(nodes2[:, 4:8], nodes[:, 4:8])                   # bases + meta unchanged
+    _check_structure(nodes2, tris2, Vp, F)
+
+
+def test_duplicate_morton_codes_and_degenerate_triangles(ctx, orc):
+    # 3000 triangles crammed into a few Morton cells + zero-area triangles: Karras must still build a tree
+    rng = np.random.default_rng(9)
+    base = rng.normal(size=(40, 3)).astype(np.float32)
+    V = np.concatenate([base + np.float32(1e-4) * rng.normal(size=(40, 3)).astype(np.float32) for _ in range(75)])
+    V[:, 2] += 6
+    F = rng.integers(0, len(V), (3000, 3)).astype(np.int32)
+    F[::50, 1] = F[::50, 0]                                                # degenerate
+    ctx.set_mesh(V, F).build_bvh()
+    nodes, tris = ctx.dump_bvh("object")
+    _check_structure(nodes, tris, V, F)
+    rays = np.zeros((4000, 6), np.float32)
+    rays[:, 3:5] = rng.normal(size=(4000, 2)) * 0.3
+    rays[:, 5] = 1
+    t, f = ctx.cast_rays(rays)
+    t0, f0 = orc.cast_brute_f32(V, F, rays)
+    assert np.array_equal(f, f0) and np.array_equal(_bits(t), _bits(t0))
+
+
+# ------------------------------------------------------------------------------------------ H4
+@pytest.mark.parametrize("cfg,step", [("tiny", 4), ("small", 5), ("c1_30k", 7)])
+def test_cast_rays_equals_brute_force(ctx, orc, cfg, step):
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS[cfg], seed=1)
+    K, H, W = synth.camera_720p()
+    rays6 = _grid_rays(orc, K, H, W, synth.fixed_pose(), step)
+    ctx.set_mesh(V, F).build_bvh()
+    t, f = ctx.cast_rays(rays6)
+    t0, f0 = orc.cast_brute_f32(V, F, rays6)
+    assert (f0 >= 0).sum() > 100
+    assert np.array_equal(f, f0), f"{(f != f0).sum()} face ids differ"
+    assert np.array_equal(_bits(t), _bits(t0))
+    assert np.array_equal(np.isinf(t), f < 0)
+
+
+def test_cast_rays_hard_cases(ctx, orc):
+    """rays through vertices and along edges (exact ties), axis-parallel rays with zero components,
+    origins inside the mesh, rays pointing away, zero-length directions."""
+    V, F = synth.param_mesh(40, 25, seed=2)
+    ctx.set_mesh(V, F).build_bvh()
+    rng = np.random.default_rng(3)
+    o = np.array([0.0, 0.0, 300.0], np.float32)
+    parts = []
+    d = V[rng.integers(0, len(V), 3000)] - o                              # straight at vertices
+    parts.append(np.hstack([np.tile(o, (len(d), 1)), d]))
+    mid = 0.5 * (V[F[:3000, 0]] + V[F[:3000, 1]]) - o                     # edge midpoints
+    parts.append(np.hstack([np.tile(o, (len(mid), 1)), mid]))
+    ax = np.zeros((600, 6), np.float32)                                   # axis-parallel, d has exact zeros
+    ax[:, :3] = rng.uniform(-90, 90, (600, 3))
+    ax[:200, 2] = 200; ax[:200, 5] = -1
+    ax[200:400, 0] = -200; ax[200:400, 3] = 1
+    ax[400:, 1] = 200; ax[400:, 4] = -1
+    parts.append(ax)
+    ins = np.zeros((2000, 6), np.float32)                                 # origins inside the tube
+    ins[:, 0] = 60.0
+    ins[:, 3:] = rng.normal(size=(2000, 3))
+    parts.append(ins)
+    away = np.hstack([np.tile(o, (100, 1)), np.tile(np.array([0, 0, 1], np.float32), (100, 1))])
+    parts.append(away)
+    zero = np.zeros((4, 6), np.float32)                                   # d = 0: defined as a miss
+    parts.append(zero)
+    rays6 = np.ascontiguousarray(np.vstack(parts), np.float32)
+    t, f = ctx.cast_rays(rays6)
+    t0, f0 = orc.cast_brute_f32(V, F, rays6)
+    assert np.array_equal(f, f0), np.nonzero(f != f0)[0][:10]
+    assert np.array_equal(_bits(t), _bits(t0))
+    assert (f[-104:] == -1).all()
+
+
+def test_cast_rays_incoherent_random(ctx, orc):
+    rng = np.random.default_rng(5)
+    V, F = synth.param_mesh(150, 100, seed=2)
+    ctx.set_mesh(V, F).build_bvh()
+    o = rng.normal(size=(30000, 3)).astype(np.float32) * 150
+    d = -o + rng.normal(size=(30000, 3)).astype(np.float32) * 40
+    rays6 = np.hstack([o, d]).astype(np.float32)                          # directions NOT normalised
+    t, f = ctx.cast_rays(rays6)
+    t0, f0 = orc.Bvh(V, F).cast_f32(rays6)
+    assert np.array_equal(f, f0) and np.array_equal(_bits(t), _bits(t0))
+
+
+def test_empty_and_tiny_meshes(ctx, orc):
+    rng = np.random.default_rng(1)
+    rays = np.zeros((300, 6), np.float32)
+    rays[:, 3:5] = rng.normal(size=(300, 2)) * 0.3
+    rays[:, 5] = 1
+    ctx.set_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32)).build_bvh()
+    t, f = ctx.cast_rays(rays)
+    assert np.isinf(t).all() and (f == -1).all()
+    t, f = ctx.cast_rays(np.zeros((0, 6), np.float32))
+    assert len(t) == 0
+    for n in (1, 2, 3, 4, 5, 8, 9, 25):
+        V = rng.normal(size=(3 * n, 3)).astype(np.float32)
+        V[:, 2] += 5
+        F = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+        ctx.set_mesh(V, F).build_bvh()
+        t, f = ctx.cast_rays(rays)
+        t0, f0 = orc.cast_brute_f32(V, F, rays)
+        assert np.array_equal(f, f0) and np.array_equal(_bits(t), _bits(t0)), n
+
+
+# ------------------------------------------------------------------------------------------ fused path
+def _oracle_frame(orc, V, F, heat, thr, K, pose):
+    from defectproj import Context
+    xs, ys, I = orc.heatmap_to_points(heat, thr)
+    rays6 = orc.rays_object_frame(xs, ys, Context.frame_xform(K, pose))
+    t, f = orc.Bvh(V, F).cast_f32(rays6)
+    return xs, ys, I, rays6, t, f
+
+
+@pytest.mark.parametrize("hdt", [np.float32, np.float64])
+def test_project_object_frame_c1(ctx, orc, hdt):
+    """BASELINE configs[0]: 30k-triangle mesh, 720p Gaussian heatmap, thr 0.5 and 0.75, fixed pose."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
+    K, H, W = synth.camera_720p()
+    pose = synth.fixed_pose()
+    heat = synth.gaussian_heatmap((H, W), dtype=hdt)
+    ctx.set_mesh(V, F).build_bvh()
+    for thr, count in ((0.5, 10885), (0.75, 4501)):
+        ctx.accum_reset()
+        res = ctx.project(heat, K, pose[None], thr, "object", True,
+                          want=("pixel", "intensity", "t_hit", "face", "point", "point64"))
+        xs, ys, I, rays6, t, f = _oracle_frame(orc, V, F, heat, thr, K, pose)
+        assert res["n"] == len(xs) == count
+        assert np.array_equal(res["pixel"], (ys * W + xs).astype(np.uint32))
+        assert np.array_equal(res["intensity"], I.astype(np.float32))
+        assert np.array_equal(res["face"], f) and np.array_equal(_bits(res["t_hit"]), _bits(t))
+        hit = f >= 0
+        assert res["hits"] == hit.sum() > 1000
+        d = orc.compute_rays(xs, ys, K)
+        pref = d[hit] * t[hit].astype(np.float64)[:, None]               # :261-263, origin 0
+        assert np.array_equal(res["point64"][hit], pref)
+        assert np.isnan(res["point64"][~hit]).all() and np.isnan(res["point"][~hit]).all()
+        assert np.array_equal(res["point"][hit], pref.astype(np.float32))
+        hist, fmax, vmax = ctx.accum_get()
+        h0, f0, v0 = orc.accumulate(f, I.astype(np.float32), F, len(V))
+        assert np.array_equal(hist, h0) and np.array_equal(fmax, f0) and np.array_equal(vmax, v0)
+        assert hist.sum() == res["hits"]
+
+
+def test_project_against_float64_truth_north_star_criterion(ctx, orc):
+    """face ids bit-exact except rays the float64 classifier flags as edge/grazing ties; hit points
+    within 1e-5 x bbox diagonal."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
+    K, H, W = synth.camera_720p()
+    pose = synth.fixed_pose()
+    heat = synth.blob_heatmap((H, W), seed=4)
+    ctx.set_mesh(V, F).build_bvh()
+    res = ctx.project(heat, K, pose[None], 0.3, "object", False, want=("pixel", "t_hit", "face", "point64"))
+    xs, ys, I, rays6, _, _ = _oracle_frame(orc, V, F, heat, 0.3, K, pose)
+    bvh = orc.Bvh(V, F)
+    t64, f64, tie = bvh.cast_f64(rays6)
+    clean = tie == 0
+    assert clean.mean() > 0.95
+    assert np.array_equal(res["face"][clean], f64[clean])
+    hit = clean & (f64 >= 0)
+    assert hit.sum() > 1000
+    diag = float(np.linalg.norm(V.max(0) - V.min(0)))
+    d = orc.compute_rays(xs, ys, K)
+    p64 = d[hit] * t64[hit][:, None]
+    assert np.linalg.norm(res["point64"][hit] - p64, axis=1).max() <= TOL_FRAC * diag
+    # on tie rays the GPU's face must still be a genuine candidate: it lies within the tie margin
+    tie_hit = (~clean) & (res["face"] >= 0)
+    if tie_hit.any():
+        tt, margin, _ = bvh.eval_face(rays6[tie_hit], res["face"][tie_hit])
+        tau, tau_t = bvh.margins(rays6)
+        assert (margin >= -tau).all()
+        ok = (f64[tie_hit] < 0) | (np.abs(tt - np.where(f64[tie_hit] >= 0, t64[tie_hit], tt)) <= 4 * tau_t)
+        assert ok.all()
+
+
+def test_project_camera_frame_is_reference_literal(ctx, orc):
+    """DP_FRAME_CAMERA: vertices posed in float64 then cast (:549-550, :245), BVH refitted, rays from (0,0,0)."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
+    K, H, W = synth.camera_720p()
+    pose = synth.fixed_pose()
+    heat = synth.gaussian_heatmap((H, W), dtype=np.float64)
+    ctx.set_mesh(V.astype(np.float64), F).build_bvh()
+    ctx.pose_mesh(pose)
+    Vref = orc.pose_vertices(V.astype(np.float64), pose)
+    assert np.array_equal(ctx.posed_vertices(), Vref)
+    ctx.accum_reset()
+    res = ctx.project(heat, K, None, 0.5, "camera", True, want=("pixel", "t_hit", "face", "point64"))
+    xs, ys, I = orc.heatmap_to_points(heat, 0.5)
+    d = orc.compute_rays(xs, ys, K)
+    t, f = orc.Bvh(Vref, F).cast_f32(orc.rays6_camera(d))
+    assert np.array_equal(res["face"], f) and np.array_equal(_bits(res["t_hit"]), _bits(t))
+    hist, fmax, vmax = ctx.accum_get()
+    h0, f0, v0 = orc.accumulate(f, I.astype(np.float32), F, len(V))
+    assert np.array_equal(hist, h0) and np.array_equal(fmax, f0) and np.array_equal(vmax, v0)
+    # object-frame and camera-frame agree wherever neither is a tie (rigid invariance)
+    res_o = ctx.project(heat, K, pose[None], 0.5, "object", False, want=("face", "point64"))
+    rays6 = orc.rays_object_frame(xs, ys, orc.frame_xform(K, pose))
+    _, _, tie = orc.Bvh(V, F).cast_f64(rays6)
+    clean = tie == 0
+    assert np.array_equal(res_o["face"][clean], res["face"][clean])
+    both = clean & (f >= 0)
+    diag = float(np.linalg.norm(V.max(0) - V.min(0)))
+    assert np.linalg.norm(res_o["point64"][both] - res["point64"][both], axis=1).max() <= TOL_FRAC * diag
+
+
+def test_project_batch_of_frames_single_launch(ctx, orc):
+    """config 3 shape at test size: several views, per-frame pose, one launch, histogram accumulated over frames."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["small"], seed=2)
+    K, H, W = synth.K_matrix(150.0, 150.0, 80.0, 60.0), 120, 160
+    poses = synth.fibonacci_poses(6, radius=400.0)
+    heats = np.stack([synth.blob_heatmap((H, W), seed=i) for i in range(6)])
+    ctx.set_mesh(V, F).build_bvh()
+    ctx.accum_reset()
+    res = ctx.project(heats, K, poses, 0.4, "object", True, want=("pixel", "intensity", "t_hit", "face"))
+    bvh = orc.Bvh(V, F)
+    faces, ts, pixs, Is = [], [], [], []
+    for b in range(6):
+        xs, ys, I = orc.heatmap_to_points(heats[b], 0.4)
+        t, f = bvh.cast_f32(orc.rays_object_frame(xs, ys, orc.frame_xform(K, poses[b])))
+        faces.append(f); ts.append(t); Is.append(I); pixs.append(b * H * W + ys * W + xs)
+    f_all, t_all, I_all = np.concatenate(faces), np.concatenate(ts), np.concatenate(Is)
+    assert np.array_equal(res["pixel"], np.concatenate(pixs).astype(np.uint32))
+    assert np.array_equal(res["face"], f_all) and np.array_equal(_bits(res["t_hit"]), _bits(t_all))
+    hist, fmax, vmax = ctx.accum_get()
+    h0, f0, v0 = orc.accumulate(f_all, I_all, F, len(V))
+    assert (f_all >= 0).sum() > 500
+    assert np.array_equal(hist, h0) and np.array_equal(fmax, f0) and np.array_equal(vmax, v0)
+
+
+def test_project_empty_selection_and_miss_all(ctx):
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["tiny"], seed=0)
+    K, H, W = synth.camera_720p()
+    ctx.set_mesh(V, F).build_bvh()
+    res = ctx.project(np.zeros((H, W), np.float32), K, synth.fixed_pose()[None], 0.5, "object", True)
+    assert res["n"] == 0 and res["hits"] == 0 and len(res["face"]) == 0
+    far = synth.fixed_pose()
+    far[:3, 3] = [5000.0, 0, 600.0]
+    res = ctx.project(synth.gaussian_heatmap((H, W), dtype=np.float32), K, far[None], 0.9, "object", True)
+    assert res["n"] > 0 and res["hits"] == 0 and (res["face"] == -1).all() and np.isinf(res["t_hit"]).all()
+
+
+def test_error_behaviour(built_lib):
+    from defectproj import Context, DefectProjError
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["tiny"], seed=0)
+    K, H, W = synth.camera_720p()
+    with Context(0) as c:
+        with pytest.raises(DefectProjError, match="no mesh"):
+            c.build_bvh()
+        c.set_mesh(V, F)
+        with pytest.raises(DefectProjError, match="no BVH"):
+            c.cast_rays(np.zeros((1, 6), np.float32))
+        with pytest.raises(DefectProjError, match="no BVH"):
+            c.project(np.ones((4, 4), np.float32), K, np.eye(4)[None], 0.5)
+        c.build_bvh()
+        with pytest.raises(DefectProjError, match="dp_pose_mesh"):
+            c.project(np.ones((4, 4), np.float32), K, None, 0.5, frame="camera")
+        with pytest.raises(ValueError):
+            c.project(np.ones((4, 4), np.float32), K, np.eye(4)[None].repeat(2, 0), 0.5)
+        bad = F.copy()
+        bad[3, 1] = len(V)
+        with pytest.raises(ValueError, match="out of range"):
+            c.set_mesh(V, bad)
+        with pytest.raises(ValueError):
+            c.pose_mesh(np.ones((4, 4)))
+    with pytest.raises(ValueError, match="out of range"):
+        Context(99)
+
+
+# ------------------------------------------------------------------------------------------ façade vs golden
+def test_facade_matches_reference_run(golden, tmp_path, built_lib):
+    """The reference's own ray_tracing() output (tests/golden/make_golden.py) reproduced through the drop-in."""
+    from defectproj import defect_projection as dpj
+    K = golden["g5_K"]
+    synth.write_scene_dir(str(tmp_path), K, (96, 128), color_to_depth=golden["g5_color_to_depth"])
+    mesh = dpj.TriangleMesh(golden["g5_V_depthcam"], golden["g5_F"])
+    for thr, tag in ((0.5, "050"), (0.75, "075")):
+        pcd, mesh_out = dpj.ray_tracing(str(tmp_path), mesh, golden["g2_heat"], K, heatmap_threshold=thr)
+        assert isinstance(pcd, dpj.PointCloud)
+        assert np.array_equal(np.asarray(pcd.points), golden[f"g5_points_{tag}"])
+        assert np.allclose(np.asarray(pcd.colors), golden[f"g5_colors_{tag}"], rtol=0, atol=1e-12)
+        assert np.array_equal(np.asarray(mesh_out.vertices), golden[f"g5_V_colorcam_{tag}"])
+        hist, fmax, vmax = dpj.face_intensities()
+        assert hist.sum() == len(pcd.points) and np.array_equal(np.bincount(pcd.face_ids, minlength=len(hist)), hist)
+    # step-by-step surface
+    pts = dpj.heatmap_to_points(golden["g2_heat"], 0.5)
+    assert np.array_equal(np.array([[p[0], p[1], p[2]] for p in pts], np.float64), golden["g2_points_050"])
+    rays, inten = dpj.compute_rays(pts, K)
+    assert np.array_equal(rays, golden["g4_rays"]) and np.array_equal(inten, golden["g4_intensities"])
+    rays2, _ = dpj.compute_rays(list(pts), K)                             # plain list of tuples, as the reference passes
+    assert np.array_equal(rays2, rays)
+    posed = dpj.TriangleMesh(golden["g5_V_colorcam_050"], golden["g5_F"])
+    P, I = dpj.intersect_rays_with_mesh(posed, rays, np.array([0, 0, 0]), inten)
+    assert np.array_equal(P, golden["g5_points_050"])
+    # miss-all branch -> LineSet (:561-563)
+    far = dpj.TriangleMesh(golden["g5_V_model"].astype(np.float64) + np.array([5000.0, 0, 0]), golden["g5_F"])
+    ls, _ = dpj.ray_tracing(str(tmp_path), far, golden["g2_heat"], K, heatmap_threshold=0.9)
+    assert isinstance(ls, dpj.LineSet)
+    assert np.allclose(ls.points, golden["g6_lineset_points"], rtol=0, atol=1e-9)
+    assert np.array_equal(ls.lines, golden["g6_lineset_lines"])
+    # documented deviation: empty selection returns empty outputs instead of raising
+    ls, _ = dpj.ray_tracing(str(tmp_path), mesh, np.zeros((96, 128)), K)
+    assert len(ls.lines) == 0
+    assert dpj.heatmap_to_points(np.zeros((4, 4)), 0.5) == []
+
+
+# ------------------------------------------------------------------------------------------ full size
+@pytest.mark.parametrize("cfg", ["c2_500k", "ns_1m"])
+def test_full_size_dense_frame(ctx, orc, cfg):
+    """BASELINE configs[1] (and the north-star 1M-triangle mesh): 1024x1024 dense frame, every ray checked
+    against the oracle's own BVH caster, plus the size-independent properties."""
+    import torch
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS[cfg], seed=0, scale=6.0)
+    K, H, W = synth.camera_wfov()
+    pose = synth.fill_frame_pose()
+    ctx.set_mesh(V, F).build_bvh()
+    st = ctx.stats()
+    assert st["n_tris"] == len(F) and st["n_wide_nodes"] < len(F) // 2
+    heat = torch.rand((1, H, W), device="cuda") * 0.5 + 0.5             # all > 0.5 except exact 0.5
+    heat[0, 5, 7] = 0.25
+    n = H * W
+    out = dict(pixel=torch.empty(n, dtype=torch.int32, device="cuda"), t_hit=torch.empty(n, device="cuda"),
+               face=torch.empty(n, dtype=torch.int32, device="cuda"), intensity=torch.empty(n, device="cuda"))
+    ctx.accum_reset()
+    nr, nh = ctx.project_device(heat, K, pose[None], 0.5, "object", True, out=out, sync=True)
+    hnp = heat.cpu().numpy()[0]
+    xs, ys, I = orc.heatmap_to_points(hnp, 0.5)
+    assert nr == len(xs) >= n - 100
+    t, f = orc.Bvh(V, F).cast_f32(orc.rays_object_frame(xs, ys, orc.frame_xform(K, pose)))
+    gf, gt = out["face"][:nr].cpu().numpy(), out["t_hit"][:nr].cpu().numpy()
+    assert np.array_equal(out["pixel"][:nr].cpu().numpy().view(np.uint32), (ys * W + xs).astype(np.uint32))
+    assert np.array_equal(gf, f), f"{(gf != f).sum()} of {nr} face ids differ"
+    assert np.array_equal(_bits(gt), _bits(t))
+    hist, fmax, vmax = ctx.accum_get()
+    assert hist.sum() == nh == (f >= 0).sum() and nh > 0.9 * nr          # fill-frame pose: >= 90 % hit
+    assert np.array_equal(hist, np.bincount(f[f >= 0], minlength=len(F)).astype(np.int32))
+    assert fmax.max() <= I.max() and vmax.max() == fmax.max()
+    assert ((fmax > 0) == (hist > 0)).all()
+    # idempotence: a second accumulation doubles the histogram and leaves the maxima alone
+    ctx.project_device(heat, K, pose[None], 0.5, "object", True, out=out, sync=True)
+    h2, f2, v2 = ctx.accum_get()
+    assert np.array_equal(h2, 2 * hist) and np.array_equal(f2, fmax) and np.array_equal(v2, vmax)
+
+
+def test_shards_of_a_batch_combine_to_the_whole(ctx):
+    """Multi-GPU semantics on one GPU: frames split into rank blocks (shard_range), each block projected on its
+    own, integer histograms summed and maxima maxed == the single-launch result, bit for bit."""
+    from defectproj.projector import shard_range
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
+    K, H, W = synth.camera_720p()
+    B = 8
+    poses = synth.helix_poses(B, turns=1)
+    heats = np.stack([synth.blob_heatmap((H, W), seed=100 + i) for i in range(B)])
+    ctx.set_mesh(V, F).build_bvh()
+    ctx.accum_reset()
+    whole = ctx.project(heats, K, poses, 0.5, "object", True, want=("pixel", "face", "t_hit"))
+    hw, fw, vw = ctx.accum_get()
+    for world in (2, 4, 8):
+        hs, fs, vs, faces, pix = [], [], [], [], []
+        for r in range(world):
+            lo, hi = shard_range(B, world, r)
+            ctx.accum_reset()
+            part = ctx.project(heats[lo:hi], K, poses[lo:hi], 0.5, "object", True, want=("pixel", "face"))
+            a, b, c = ctx.accum_get()
+            hs.append(a); fs.append(b); vs.append(c); faces.append(part["face"])
+            pix.append(part["pixel"].astype(np.int64) + lo * H * W)
+        assert np.array_equal(np.sum(hs, axis=0, dtype=np.int32), hw)
+        assert np.array_equal(np.max(fs, axis=0), fw) and np.array_equal(np.max(vs, axis=0), vw)
+        assert np.array_equal(np.concatenate(faces), whole["face"])
+        assert np.array_equal(np.concatenate(pix), whole["pixel"].astype(np.int64))

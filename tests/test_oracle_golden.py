@@ -1,0 +1,110 @@
+"""CPU: the oracle (oracle/oracle.c) against the fixtures made from the reference's own Python
+(tests/golden/make_golden.py) and against independent restatements."""
+import numpy as np
+import pytest
+
+from defectproj import synth
+
+
+def test_heatmap_to_points_known_answer(orc, golden):
+    # hand-derivable example of SURVEY.md section 4
+    xs, ys, I = orc.heatmap_to_points(golden["g1_heat"], 0.5)
+    got = np.stack([xs, ys, I], axis=1)
+    assert np.array_equal(got, golden["g1_points"])
+    assert got.tolist() == [[3.0, 0.0, 0.9], [0.0, 1.0, 0.8], [1.0, 2.0, 0.51]]
+
+
+@pytest.mark.parametrize("thr,key", [(0.5, "g2_points_050"), (0.75, "g2_points_075")])
+def test_heatmap_to_points_reference_gaussian(orc, golden, thr, key):
+    xs, ys, I = orc.heatmap_to_points(golden["g2_heat"], thr)
+    ref = golden[key]
+    assert np.array_equal(xs, ref[:, 0].astype(np.int64))
+    assert np.array_equal(ys, ref[:, 1].astype(np.int64))
+    assert np.array_equal(I, ref[:, 2])          # bit-exact float64
+
+
+def test_production_heatmap_counts(golden):
+    # the counts the survey measured with the reference's own generator (cv2 GaussianBlur)
+    assert golden["g3_counts"].tolist() == [10885, 4501]
+
+
+def test_compute_rays_bit_exact(orc, golden):
+    ref = golden["g2_points_050"]
+    rays = orc.compute_rays(ref[:, 0].astype(np.int64), ref[:, 1].astype(np.int64), golden["g4_K"])
+    assert np.array_equal(rays, golden["g4_rays"])
+    assert np.array_equal(ref[:, 2], golden["g4_intensities"])
+
+
+def test_pose_vertices_matches_reference_transform(orc, golden):
+    T = np.linalg.inv(golden["g5_color_to_depth"])
+    got = orc.pose_vertices(golden["g5_V_depthcam"], T)
+    assert np.array_equal(got, golden["g5_V_colorcam_050"].astype(np.float32))
+
+
+@pytest.mark.parametrize("thr,tag", [(0.5, "050"), (0.75, "075")])
+def test_whole_path_against_reference_run(orc, golden, thr, tag):
+    """ray_tracing() of the reference (open3d shimmed) vs the oracle pipeline."""
+    T = np.linalg.inv(golden["g5_color_to_depth"])
+    Vc = orc.pose_vertices(golden["g5_V_depthcam"], T)
+    xs, ys, I = orc.heatmap_to_points(golden["g2_heat"], thr)
+    d = orc.compute_rays(xs, ys, golden["g5_K"])
+    bvh = orc.Bvh(Vc, golden["g5_F"])
+    t, f = bvh.cast_f32(orc.rays6_camera(d))
+    hit = f >= 0
+    pts = d[hit] * t[hit].astype(np.float64)[:, None]
+    assert np.array_equal(pts, golden[f"g5_points_{tag}"])
+
+
+def test_oracle_bvh_equals_brute_force(orc):
+    V, F = synth.param_mesh(40, 25, seed=4)
+    K, H, W = synth.camera_720p()
+    ys, xs = np.mgrid[0:H:16, 0:W:16]
+    xf = orc.frame_xform(K, synth.fixed_pose())
+    rays6 = orc.rays_object_frame(xs.reshape(-1), ys.reshape(-1), xf)
+    t0, f0 = orc.cast_brute_f32(V, F, rays6)
+    t1, f1 = orc.Bvh(V, F).cast_f32(rays6)
+    assert (f0 >= 0).sum() > 50
+    assert np.array_equal(f0, f1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+
+
+def test_float32_contract_agrees_with_float64_on_non_tie_rays(orc):
+    V, F = synth.param_mesh(24, 16, seed=7)
+    K, H, W = synth.camera_720p()
+    ys, xs = np.mgrid[0:H:8, 0:W:8]
+    xf = orc.frame_xform(K, synth.fixed_pose(z=420.0))
+    rays6 = orc.rays_object_frame(xs.reshape(-1), ys.reshape(-1), xf)
+    bvh = orc.Bvh(V, F)
+    t32, f32 = bvh.cast_f32(rays6)
+    t64, f64, tie = bvh.cast_f64(rays6)
+    tn, fn = orc.brute_f64_numpy(V, F, rays6)
+    clean = tie == 0
+    assert clean.sum() > 0.9 * len(tie)
+    assert np.array_equal(f64[clean], fn[clean])           # C float64 == numpy float64
+    assert np.array_equal(f32[clean], f64[clean])          # float32 contract == float64 truth off ties
+    hit = clean & (f64 >= 0)
+    diag = np.linalg.norm(V.max(0) - V.min(0))
+    d = rays6[:, 3:].astype(np.float64)
+    err = np.linalg.norm(d[hit] * (t32[hit].astype(np.float64) - t64[hit])[:, None], axis=1)
+    assert err.max() <= 1e-5 * diag
+
+
+def test_single_triangle_known_answer(orc):
+    v0, v1, v2 = [-1, -1, 5], [1, -1, 5], [0, 1, 5]
+    hit, t = orc.tri_test_f32([0, 0, 0, 0, 0, 1], v0, v1, v2)
+    assert hit and t == 5.0
+    assert not orc.tri_test_f32([0, 0, 0, 0, 0, -1], v0, v1, v2)[0]     # t >= 0 only
+    assert not orc.tri_test_f32([5, 5, 0, 0, 0, 1], v0, v1, v2)[0]
+
+
+def test_accumulate_conservation(orc):
+    rng = np.random.default_rng(0)
+    F = rng.integers(0, 50, (30, 3)).astype(np.int32)
+    face = rng.integers(-1, 30, 1000).astype(np.int32)
+    I = rng.random(1000).astype(np.float32)
+    hist, fmax, vmax = orc.accumulate(face, I, F, 50)
+    assert hist.sum() == (face >= 0).sum()
+    assert fmax.max() <= I.max() and vmax.max() == fmax.max()
+    for f in range(30):
+        sel = face == f
+        assert hist[f] == sel.sum()
+        assert fmax[f] == (I[sel].max() if sel.any() else 0.0)
