@@ -52,7 +52,8 @@ class Context:
         h = C.c_void_p()
         rc = self._L.dp_create(int(device), C.byref(h))
         if rc != 0:
-            raise DefectProjError(rc, self._L.dp_last_error(None).decode())
+            msg = self._L.dp_last_error(None).decode()
+            raise ValueError(msg) if rc == DP_E_ARG else DefectProjError(rc, msg)
         self._h = h
         self.device = int(device)
         self.nV = self.nF = 0
