@@ -64,11 +64,12 @@ struct dp_ctx {
     DevBuf hist, fmax, vmax;
 
     // per-call scratch
-    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, cscratch, counts, fcounts, xf, stats;
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, cscratch, counts, fcounts, xf, stats;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
     bool stats_on = false;
+    int64_t ray_nodes_n = 0;
     dp_stats last_stats{};
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timings_valid = false;
     float build_ms = 0.f, refit_ms = 0.f;
 };
@@ -151,7 +152,7 @@ int dp_create(int device, dp_ctx **out)
     if (!ctx) return fail(nullptr, DP_E_NOMEM, "dp_create: out of host memory");
     ctx->device = device;
     DeviceGuard g(device);
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 10; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) { delete ctx; return fail(nullptr, DP_E_CUDA, "dp_create: event", e); }
     if ((e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_counts), 64)) != cudaSuccess) {
         delete ctx;
@@ -175,12 +176,12 @@ void dp_destroy(dp_ctx *ctx)
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face,
                       &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
-                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
+                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats};
     for (DevBuf *b : bufs) b->release();
     if (ctx->build_scratch) cudaFree(ctx->build_scratch);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 10; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
 }
@@ -263,14 +264,14 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
     ctx->obj.d_scale = ctx->scales.as<float>();
     ctx->topo.tri_face = ctx->tri_face.as<int32_t>();
     ctx->has_bvh = ctx->has_cam = false;
-    CK(cudaEventRecord(ctx->ev[3], s), "dp_build_bvh");
+    CK(cudaEventRecord(ctx->ev[8], s), "dp_build_bvh");
     cudaError_t e = build_lbvh(ctx->V.as<float>(), ctx->nV, ctx->F.as<int32_t>(), ctx->nF, ctx->obj, ctx->topo,
                                &ctx->build_scratch, &ctx->build_scratch_bytes, nullptr, s);
     if (e == cudaErrorInvalidValue) return fail(ctx, DP_E_STATE, "dp_build_bvh: hierarchy deeper than 126 levels");
     CK(e, "dp_build_bvh");
-    CK(cudaEventRecord(ctx->ev[4], s), "dp_build_bvh");
-    CK(cudaEventSynchronize(ctx->ev[4]), "dp_build_bvh: kernels");
-    cudaEventElapsedTime(&ctx->build_ms, ctx->ev[3], ctx->ev[4]);
+    CK(cudaEventRecord(ctx->ev[9], s), "dp_build_bvh");
+    CK(cudaEventSynchronize(ctx->ev[9]), "dp_build_bvh: kernels");
+    cudaEventElapsedTime(&ctx->build_ms, ctx->ev[8], ctx->ev[9]);
     if (ctx->topo.n_levels > MAX_WIDE_DEPTH) return fail(ctx, DP_E_STATE, "dp_build_bvh: BVH too deep for the ray stack");
     ctx->has_bvh = true;
     return DP_OK;
@@ -431,7 +432,8 @@ int dp_cast_rays(dp_ctx *ctx, int frame, const float *rays6, int64_t n, float *t
         st = ctx->stats.as<TraceStats>();
     }
     const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
-    CK(launch_trace_rays6(view_of(b), d_rays, n, d_t, d_f, st, s), "dp_cast_rays: launch");
+    CK(launch_trace_rays6(view_of(b), d_rays, n, d_t, d_f, ctx->counts.as<unsigned long long>() + 2, st, s),
+       "dp_cast_rays: launch");
     if (mem == DP_HOST) {
         CK(cudaMemcpyAsync(t_hit, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_cast_rays: D2H");
         if (face) CK(cudaMemcpyAsync(face, d_f, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_cast_rays: D2H");
@@ -507,14 +509,29 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
 
     TraceStats *st = nullptr;
     if (ctx->stats_on) {
-        CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TraceStats), s), "dp_project: stats");
+        CK(ctx->ray_nodes.ensure((size_t)cap * 4 + 16), "dp_project: stats");
+        TraceStats init{};
+        init.ray_nodes = ctx->ray_nodes.as<unsigned>();
+        CK(cudaMemsetAsync(ctx->ray_nodes.p, 0, (size_t)cap * 4, s), "dp_project: stats");
+        CK(cudaMemcpyAsync(ctx->stats.p, &init, sizeof(TraceStats), cudaMemcpyHostToDevice, s), "dp_project: stats");
         st = ctx->stats.as<TraceStats>();
+        ctx->ray_nodes_n = cap;
     }
     Accum acc{ctx->hist.as<int32_t>(), ctx->fmax.as<uint32_t>(), ctx->vmax.as<uint32_t>(), ctx->F.as<int32_t>()};
     const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
-    CK(launch_trace_pixels(view_of(b), d_pixel, d_int, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_t, d_face,
-                           d_pt, d_p64, accumulate ? &acc : nullptr, d_counts + 1, st, s),
+    // t_hit is needed by the hit-point kernel even when the caller does not want it
+    if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
+    CK(ctx->dir4.ensure((size_t)cap * 16 + 16), "dp_project: rays");
+    CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s),
+       "dp_project: ray generation");
+    CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
+    CK(launch_trace_pixels(view_of(b), ctx->dir4.as<float4>(), d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
+                           d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
+                           d_counts + 1, st, s),
        "dp_project: traversal");
+    CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
+    CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s),
+       "dp_project: hit points");
     CK(cudaEventRecord(ctx->ev[2], s), "dp_project");
     ctx->timings_valid = true;
 
@@ -608,15 +625,16 @@ int dp_get_stats(dp_ctx *ctx, dp_stats *out)
     return DP_OK;
 }
 
-int dp_last_timings(dp_ctx *ctx, float *ms3)
+int dp_last_timings(dp_ctx *ctx, float *ms4)
 {
-    if (!ctx || !ms3) return fail(ctx, DP_E_ARG, "dp_last_timings: bad arguments");
+    if (!ctx || !ms4) return fail(ctx, DP_E_ARG, "dp_last_timings: bad arguments");
     if (!ctx->timings_valid) return fail(ctx, DP_E_STATE, "dp_last_timings: no dp_project call yet");
     DeviceGuard g(ctx->device);
     CK(cudaEventSynchronize(ctx->ev[2]), "dp_last_timings");
-    CK(cudaEventElapsedTime(&ms3[0], ctx->ev[0], ctx->ev[1]), "dp_last_timings");
-    CK(cudaEventElapsedTime(&ms3[1], ctx->ev[1], ctx->ev[2]), "dp_last_timings");
-    CK(cudaEventElapsedTime(&ms3[2], ctx->ev[0], ctx->ev[2]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms4[0], ctx->ev[0], ctx->ev[1]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms4[1], ctx->ev[1], ctx->ev[7]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms4[2], ctx->ev[7], ctx->ev[3]), "dp_last_timings");
+    CK(cudaEventElapsedTime(&ms4[3], ctx->ev[0], ctx->ev[2]), "dp_last_timings");
     return DP_OK;
 }
 
@@ -631,6 +649,16 @@ int dp_debug_dump_bvh(dp_ctx *ctx, int frame, void *nodes, int64_t *n_nodes, voi
     if (n_tris) *n_tris = b.n_tris;
     if (nodes) CK(cudaMemcpy(nodes, b.nodes, (size_t)b.n_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost), "dp_debug_dump_bvh");
     if (tris && b.n_tris) CK(cudaMemcpy(tris, b.tris, (size_t)b.n_tris * sizeof(TriRec), cudaMemcpyDeviceToHost), "dp_debug_dump_bvh");
+    return DP_OK;
+}
+
+int dp_debug_ray_nodes(dp_ctx *ctx, uint32_t *counts, int64_t n)
+{
+    if (!ctx || !counts || n < 0) return fail(ctx, DP_E_ARG, "dp_debug_ray_nodes: bad arguments");
+    if (n > ctx->ray_nodes_n) return fail(ctx, DP_E_STATE, "dp_debug_ray_nodes: no counted dp_project launch of that size");
+    DeviceGuard g(ctx->device);
+    CK(cudaDeviceSynchronize(), "dp_debug_ray_nodes");
+    if (n) CK(cudaMemcpy(counts, ctx->ray_nodes.p, (size_t)n * 4, cudaMemcpyDeviceToHost), "dp_debug_ray_nodes");
     return DP_OK;
 }
 

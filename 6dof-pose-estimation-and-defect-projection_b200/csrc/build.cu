@@ -470,10 +470,11 @@ __global__ void k_widefit(long long begin, long long end, const WideNode *__rest
             unsigned a = 255u, b = 0u;
             if (valid[s]) {
                 const double base = (double)nlo[k];
-                double x = floor(((double)clo[s][k] - base) / sc[k]);
+                // 1/128 of a step of slack: the traversal's plane arithmetic is exact to 1/512 step
+                double x = floor(((double)clo[s][k] - base) / sc[k] - 0.0078125);
                 x = x < 0.0 ? 0.0 : (x > 255.0 ? 255.0 : x);
                 while (x > 0.0 && base + x * sc[k] > (double)clo[s][k]) x -= 1.0;
-                double y = ceil(((double)chi[s][k] - base) / sc[k]);
+                double y = ceil(((double)chi[s][k] - base) / sc[k] + 0.0078125);
                 y = y < 0.0 ? 0.0 : (y > 255.0 ? 255.0 : y);
                 while (y < 255.0 && base + y * sc[k] < (double)chi[s][k]) y += 1.0;
                 a = (unsigned)x;

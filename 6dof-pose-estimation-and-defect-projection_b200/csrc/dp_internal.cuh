@@ -53,6 +53,7 @@ struct Accum {
 
 struct TraceStats {
     unsigned long long rays, hits, nodes, tris;
+    unsigned *ray_nodes;   // optional [n]: nodes fetched by each ray (debug)
 };
 
 // ---- compact.cu ----------------------------------------------------------------------------
@@ -65,14 +66,19 @@ cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t
 
 // ---- trace.cu ------------------------------------------------------------------------------
 // rays from pixels: pixel[i] = frame*HW + y*W + x ; xf[frame] ; n read from *d_n (<= n_max)
-cudaError_t launch_trace_pixels(const BvhView &bvh, const uint32_t *pixel, const float *intensity,
-                                const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
-                                int64_t n_xf, float *t_hit, int32_t *face, float *point, double *point64,
-                                const Accum *acc, long long *d_hits, TraceStats *stats, cudaStream_t s);
+cudaError_t launch_raygen(const uint32_t *pixel, const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
+                          int64_t n_xf, float4 *dir4, cudaStream_t s);
+cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long long *d_n, int64_t n_max, int H, int W,
+                          const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s);
+// dir4[i] = (object-frame direction, frame index bits) of compacted ray i, written by launch_raygen
+cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
+                                int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
+                                int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
+                                TraceStats *stats, cudaStream_t s);
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
                                 cudaStream_t s);
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,
-                               TraceStats *stats, cudaStream_t s);
+                               unsigned long long *work_counter, TraceStats *stats, cudaStream_t s);
 
 // ---- build.cu ------------------------------------------------------------------------------
 struct BuildScratch;   // opaque, owned by the context

@@ -19,6 +19,8 @@
 // padding of the leaf boxes plus the per-ray plane padding below guarantee.
 #include "dp_internal.cuh"
 
+#include <stdlib.h>
+
 namespace dp {
 
 namespace {
@@ -88,259 +90,411 @@ __device__ __forceinline__ float safe_inv(float d)
 
 __device__ __forceinline__ float byte_f(unsigned w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
 
-// Closest hit of one ray.  stack: shared-memory column of this thread (stride TR_THREADS).
-template <bool STATS>
-__device__ __forceinline__ void traverse(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris,
-                                         float pad_abs, float ox, float oy, float oz, float dx, float dy,
-                                         float dz, uint2 *stack, float &best_t, int &best_f, unsigned &n_nodes,
-                                         unsigned &n_tris)
+// ------------------------------------------------------------------------------------------
+// Per-lane traversal state.  A warp traces packets of 32 rays in lock step (coherent rays share
+// node fetches); packets are handed out by a global counter to persistent warps so that no SM
+// idles behind a long-running CTA.
+// ------------------------------------------------------------------------------------------
+struct RayState {
+    RayCtx w;                 // watertight constants
+    float ox, oy, oz;         // origin
+    float ix, iy, iz;         // clamped reciprocal direction
+    float px, py, pz;         // slab padding in t
+    unsigned octinv;
+    uint2 ng;                 // current node group: (child base, hit bits | imask)
+    int sp;
+};
+
+__device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          float scale)
 {
-    RayCtx r;
-    {
-        const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-        int kz = 0;
-        float m = ax;
-        if (ay > m) { kz = 1; m = ay; }
-        if (az > m) { kz = 2; }
-        int kx = kz + 1; if (kx == 3) kx = 0;
-        int ky = kx + 1; if (ky == 3) ky = 0;
-        const float dkz = sel3(dx, dy, dz, kz);
-        if (dkz < 0.0f) { const int t = kx; kx = ky; ky = t; }
-        r.kx = kx; r.ky = ky; r.kz = kz;
-        r.Sx = __fdiv_rn(sel3(dx, dy, dz, kx), dkz);
-        r.Sy = __fdiv_rn(sel3(dx, dy, dz, ky), dkz);
-        r.Sz = __fdiv_rn(1.0f, dkz);
-        r.ox = sel3(ox, oy, oz, kx);
-        r.oy = sel3(ox, oy, oz, ky);
-        r.oz = sel3(ox, oy, oz, kz);
-    }
-    const float ix = safe_inv(dx), iy = safe_inv(dy), iz = safe_inv(dz);
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    int kz = 0;
+    float m = ax;
+    if (ay > m) { kz = 1; m = ay; }
+    if (az > m) { kz = 2; }
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    const float dkz = sel3(dx, dy, dz, kz);
+    if (dkz < 0.0f) { const int t = kx; kx = ky; ky = t; }
+    r.w.kx = kx; r.w.ky = ky; r.w.kz = kz;
+    r.w.Sx = __fdiv_rn(sel3(dx, dy, dz, kx), dkz);
+    r.w.Sy = __fdiv_rn(sel3(dx, dy, dz, ky), dkz);
+    r.w.Sz = __fdiv_rn(1.0f, dkz);
+    r.w.ox = sel3(ox, oy, oz, kx);
+    r.w.oy = sel3(ox, oy, oz, ky);
+    r.w.oz = sel3(ox, oy, oz, kz);
+    r.ox = ox; r.oy = oy; r.oz = oz;
+    r.ix = safe_inv(dx); r.iy = safe_inv(dy); r.iz = safe_inv(dz);
     // every slab plane is moved outwards by pad_abs (in space), i.e. pad_abs*|1/d| in t
-    const float px = pad_abs * fabsf(ix), py = pad_abs * fabsf(iy), pz = pad_abs * fabsf(iz);
+    const float pad_abs = 1.9073486e-6f * (scale + fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))));
+    r.px = pad_abs * fabsf(r.ix); r.py = pad_abs * fabsf(r.iy); r.pz = pad_abs * fabsf(r.iz);
     const unsigned oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
-    const unsigned octinv = 7u ^ oct;
-
-    uint2 lstack[STACK_LOCAL];
-    int sp = 0;
-    float best = best_t;
-    int bf = best_f;
-    float tlimit = best * T_SLACK;
-
-    uint2 ng = make_uint2(0u, 0x80000000u);
-    for (;;) {
-        // ---- take the nearest-ordered inner child of the current node group
-        const unsigned hits = ng.y;
-        const int bit = 31 - __clz(hits);
-        ng.y &= ~(1u << bit);
-        if (ng.y & 0xff000000u) {
-            if (sp < STACK_SMEM) stack[sp * TR_THREADS] = ng; else lstack[sp - STACK_SMEM] = ng;
-            ++sp;
-        }
-        const unsigned slot = (unsigned)(bit - 24) ^ octinv;
-        const unsigned rel = __popc(hits & 0xffu & ((1u << slot) - 1u));
-        const uint4 *np = reinterpret_cast<const uint4 *>(nodes + (ng.x + rel));
-        const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), w2 = __ldg(np + 2), w3 = __ldg(np + 3), w4 = __ldg(np + 4);
-        if (STATS) ++n_nodes;
-
-        const float adjx = __uint_as_float((w0.w & 0xffu) << 23) * ix;
-        const float adjy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23) * iy;
-        const float adjz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23) * iz;
-        const float orgx = (__uint_as_float(w0.x) - ox) * ix;
-        const float orgy = (__uint_as_float(w0.y) - oy) * iy;
-        const float orgz = (__uint_as_float(w0.z) - oz) * iz;
-        const float nox = orgx - px, fox = orgx + px;
-        const float noy = orgy - py, foy = orgy + py;
-        const float noz = orgz - pz, foz = orgz + pz;
-        // near/far quantised planes per axis, swapped once per node by the ray's sign
-        const bool sx = ix < 0.0f, sy = iy < 0.0f, sz = iz < 0.0f;
-        const unsigned nx0 = sx ? w3.z : w2.x, nx1 = sx ? w3.w : w2.y;
-        const unsigned fx0 = sx ? w2.x : w3.z, fx1 = sx ? w2.y : w3.w;
-        const unsigned ny0 = sy ? w4.x : w2.z, ny1 = sy ? w4.y : w2.w;
-        const unsigned fy0 = sy ? w2.z : w4.x, fy1 = sy ? w2.w : w4.y;
-        const unsigned nz0 = sz ? w4.z : w3.x, nz1 = sz ? w4.w : w3.y;
-        const unsigned fz0 = sz ? w3.x : w4.z, fz1 = sz ? w3.y : w4.w;
-
-        unsigned hitmask = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const unsigned meta4 = half ? w1.w : w1.z;
-            const unsigned nxw = half ? nx1 : nx0, fxw = half ? fx1 : fx0;
-            const unsigned nyw = half ? ny1 : ny0, fyw = half ? fy1 : fy0;
-            const unsigned nzw = half ? nz1 : nz0, fzw = half ? fz1 : fz0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float tnx = fmaf(byte_f(nxw, j), adjx, nox);
-                const float tny = fmaf(byte_f(nyw, j), adjy, noy);
-                const float tnz = fmaf(byte_f(nzw, j), adjz, noz);
-                const float tfx = fmaf(byte_f(fxw, j), adjx, fox);
-                const float tfy = fmaf(byte_f(fyw, j), adjy, foy);
-                const float tfz = fmaf(byte_f(fzw, j), adjz, foz);
-                const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-                const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
-                if (tmin <= tmax) {
-                    const unsigned meta = (meta4 >> (8 * j)) & 0xffu;
-                    const bool inner = (meta & 0x18u) == 0x18u;
-                    const unsigned bi = (inner ? (meta ^ octinv) : meta) & 31u;
-                    hitmask |= (meta >> 5) << bi;
-                }
-            }
-        }
-        ng = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
-        unsigned tmask = hitmask & 0x00ffffffu;
-        const unsigned tbase = w1.y;
-
-        // ---- triangles of this node
-        while (tmask) {
-            const int b = __ffs(tmask) - 1;
-            tmask &= tmask - 1u;
-            const float4 *tp = reinterpret_cast<const float4 *>(tris + (tbase + b));
-            const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-            if (STATS) ++n_tris;
-            float t;
-            if (tri_test(r, p0, p1, p2, t)) {
-                const int f = __float_as_int(p0.w);
-                if (t < best || (t == best && f < bf)) {
-                    best = t;
-                    bf = f;
-                    tlimit = best * T_SLACK;
-                }
-            }
-        }
-
-        // ---- next node group
-        if (!(ng.y & 0xff000000u)) {
-            if (sp == 0) break;
-            --sp;
-            ng = (sp < STACK_SMEM) ? stack[sp * TR_THREADS] : lstack[sp - STACK_SMEM];
-        }
-    }
-    best_t = best;
-    best_f = bf;
+    r.octinv = 7u ^ oct;
+    r.ng = make_uint2(0u, 0x80000000u);      // the root as the only inner child of a virtual group
+    r.sp = 0;
 }
 
-__device__ __forceinline__ void warp_stats(TraceStats *stats, bool valid, bool hit, unsigned nn, unsigned nt)
+// 8-bit plane index -> float without the conversion (XU) pipe: PRMT drops the byte into the low
+// mantissa bits of 2^23, giving 8388608 + q exactly, and one FADD removes the 2^23 again (exact).
+// DP_PLANE_MODE 1 = plain I2F.U8; 2 = byte in mantissa bits 8..15 of 2^15 with the bias folded into
+// the FMA addend (one instruction less per plane, but 2^-9 of a quantisation step of rounding).
+#ifndef DP_PLANE_MODE
+#define DP_PLANE_MODE 0
+#endif
+#if DP_PLANE_MODE == 0
+__device__ __forceinline__ float qf(unsigned w, int i)
 {
-    unsigned long long a = nn, b = nt;
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (unsigned)i)) - 8388608.0f;
+}
+#define DP_QBIAS 0.0f
+#elif DP_PLANE_MODE == 1
+__device__ __forceinline__ float qf(unsigned w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+#define DP_QBIAS 0.0f
+#else
+__device__ __forceinline__ float qf(unsigned w, int i)
+{
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (unsigned)(i << 4)));
+}
+#define DP_QBIAS 32768.0f
+#endif
+
+// One node step: visit the nearest pending inner child (fetch its 80-byte node, test the 8 child
+// boxes against [0, tlimit]), hand the triangle hits back as (tbase, tmask) and advance to the next
+// node group.  Returns false when nothing is left to visit.
+template <bool STATS>
+__device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restrict__ nodes, uint2 *stack, uint2 *lstack,
+                                          float tlimit, unsigned &tbase, unsigned &tmask, unsigned &n_nodes)
+{
+    uint2 ng = r.ng;
+    const unsigned hits = ng.y;
+    const int bit = 31 - __clz(hits);
+    ng.y &= ~(1u << bit);
+    if (ng.y & 0xff000000u) {
+        if (r.sp < STACK_SMEM) stack[r.sp * TR_THREADS] = ng; else lstack[r.sp - STACK_SMEM] = ng;
+        ++r.sp;
+    }
+    const unsigned slot = (unsigned)(bit - 24) ^ r.octinv;
+    const unsigned rel = __popc(hits & 0xffu & ((1u << slot) - 1u));
+    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + (ng.x + rel));
+    const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), w2 = __ldg(np + 2), w3 = __ldg(np + 3), w4 = __ldg(np + 4);
+    if (STATS) ++n_nodes;
+
+    const float adjx = __uint_as_float((w0.w & 0xffu) << 23) * r.ix;
+    const float adjy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23) * r.iy;
+    const float adjz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23) * r.iz;
+    const float orgx = fmaf(-DP_QBIAS, adjx, (__uint_as_float(w0.x) - r.ox) * r.ix);
+    const float orgy = fmaf(-DP_QBIAS, adjy, (__uint_as_float(w0.y) - r.oy) * r.iy);
+    const float orgz = fmaf(-DP_QBIAS, adjz, (__uint_as_float(w0.z) - r.oz) * r.iz);
+    const float nox = orgx - r.px, fox = orgx + r.px;
+    const float noy = orgy - r.py, foy = orgy + r.py;
+    const float noz = orgz - r.pz, foz = orgz + r.pz;
+    // near/far quantised planes per axis, swapped once per node by the ray's sign
+    const bool sx = r.ix < 0.0f, sy = r.iy < 0.0f, sz = r.iz < 0.0f;
+    const unsigned nx0 = sx ? w3.z : w2.x, nx1 = sx ? w3.w : w2.y;
+    const unsigned fx0 = sx ? w2.x : w3.z, fx1 = sx ? w2.y : w3.w;
+    const unsigned ny0 = sy ? w4.x : w2.z, ny1 = sy ? w4.y : w2.w;
+    const unsigned fy0 = sy ? w2.z : w4.x, fy1 = sy ? w2.w : w4.y;
+    const unsigned nz0 = sz ? w4.z : w3.x, nz1 = sz ? w4.w : w3.y;
+    const unsigned fz0 = sz ? w3.x : w4.z, fz1 = sz ? w3.y : w4.w;
+    const unsigned octinv4 = r.octinv * 0x01010101u;
+
+    unsigned hitmask = 0;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, d);
-        b += __shfl_xor_sync(0xffffffffu, b, d);
+    for (int half = 0; half < 2; ++half) {
+        const unsigned meta4 = half ? w1.w : w1.z;
+        const unsigned nxw = half ? nx1 : nx0, fxw = half ? fx1 : fx0;
+        const unsigned nyw = half ? ny1 : ny0, fyw = half ? fy1 : fy0;
+        const unsigned nzw = half ? nz1 : nz0, fzw = half ? fz1 : fz0;
+        // four children at a time: bit index of each child in the hit word (inner children are
+        // placed by slot ^ octinv so that the highest set bit is the nearest), and its unary count
+        const unsigned inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;           // bit 4 set <=> inner
+        const unsigned imask4 = (inner4 >> 4) * 0x07u;                          // 0x07 per inner byte
+        const unsigned bidx4 = (meta4 ^ (octinv4 & imask4)) & 0x1f1f1f1fu;
+        const unsigned cbits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float tnx = fmaf(qf(nxw, j), adjx, nox);
+            const float tny = fmaf(qf(nyw, j), adjy, noy);
+            const float tnz = fmaf(qf(nzw, j), adjz, noz);
+            const float tfx = fmaf(qf(fxw, j), adjx, fox);
+            const float tfy = fmaf(qf(fyw, j), adjy, foy);
+            const float tfz = fmaf(qf(fzw, j), adjz, foz);
+            const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
+            if (tmin <= tmax) hitmask |= ((cbits4 >> (8 * j)) & 0xffu) << ((bidx4 >> (8 * j)) & 0xffu);
+        }
     }
-    const unsigned vm = __ballot_sync(0xffffffffu, valid), hm = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&stats->rays, (unsigned long long)__popc(vm));
-        atomicAdd(&stats->hits, (unsigned long long)__popc(hm));
-        atomicAdd(&stats->nodes, a);
-        atomicAdd(&stats->tris, b);
+    ng = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
+    tmask = hitmask & 0x00ffffffu;
+    tbase = w1.y;
+    if (!(ng.y & 0xff000000u)) {
+        if (r.sp == 0) return false;
+        --r.sp;
+        ng = (r.sp < STACK_SMEM) ? stack[r.sp * TR_THREADS] : lstack[r.sp - STACK_SMEM];
     }
+    r.ng = ng;
+    return true;
 }
 
+int g_tiled = -1;                      // walk dense frames in 8x4 tiles (DP_TILED)
+
+// index in the work order -> output slot.  Dense frames are walked in 8x4-pixel tiles so that the 32
+// rays of a warp share most of their path; results are still written at the row-major slot.
+__device__ __forceinline__ long long work_to_slot(long long i, bool tiled, int W)
+{
+    if (!tiled) return i;
+    const long long tile = i >> 5;
+    const int l = (int)(i & 31);
+    const int tpr = W >> 3;
+    const long long trow = tile / tpr;
+    const int tcol = (int)(tile - trow * tpr);
+    return (trow * 4 + (l >> 3)) * W + tcol * 8 + (l & 7);
+}
+
+constexpr int TQ_CAP = 64;                      // triangle queue entries per warp (power of two)
+constexpr unsigned TQ_TRI_MASK = (1u << 27) - 1u;
+constexpr unsigned long long KEY_MISS = (0x7f800000ull << 32) | 0xffffffffull;   // t = +inf, face = -1
+
+// Triangle tests of one warp, compacted: the (ray, triangle) pairs the node steps produce are queued
+// in shared memory and tested 32 at a time by all lanes, whichever lane owns the ray; the ray's
+// constants come by shuffle from the owner and the result goes to the owner's 64-bit key
+// (t bits << 32 | face id) with a shared-memory atomicMin: minimum t, ties to the smaller face id.
 template <bool STATS>
+__device__ __forceinline__ void tri_batch(const RayState &r, const TriRec *__restrict__ tris, const unsigned *queue,
+                                          unsigned long long *best, int qhead, int cnt, int lane, unsigned &n_tris)
+{
+    const unsigned e = queue[(qhead + lane) & (TQ_CAP - 1)];
+    const bool live = lane < cnt;
+    const int owner = live ? (int)(e >> 27) : lane;
+    RayCtx w;
+    w.ox = __shfl_sync(0xffffffffu, r.w.ox, owner);
+    w.oy = __shfl_sync(0xffffffffu, r.w.oy, owner);
+    w.oz = __shfl_sync(0xffffffffu, r.w.oz, owner);
+    w.Sx = __shfl_sync(0xffffffffu, r.w.Sx, owner);
+    w.Sy = __shfl_sync(0xffffffffu, r.w.Sy, owner);
+    w.Sz = __shfl_sync(0xffffffffu, r.w.Sz, owner);
+    const int kpack = __shfl_sync(0xffffffffu, r.w.kx | (r.w.ky << 2) | (r.w.kz << 4), owner);
+    w.kx = kpack & 3; w.ky = (kpack >> 2) & 3; w.kz = kpack >> 4;
+    if (live) {
+        const float4 *tp = reinterpret_cast<const float4 *>(tris + (e & TQ_TRI_MASK));
+        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        if (STATS) ++n_tris;
+        float t;
+        if (tri_test(w, p0, p1, p2, t)) {
+            t += 0.0f;      // -0 -> +0 so that the bit pattern orders like the value
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)__float_as_int(p0.w);
+            atomicMin(&best[owner], key);
+        }
+    }
+    __syncwarp();
+}
+
+// SRC = 0: rays come from (pixel -> dir4[]) of the compaction + ray generation kernels, origins per frame
+// SRC = 1: explicit float32 rays [n][6]
+template <bool STATS, int SRC>
 __global__ void __launch_bounds__(TR_THREADS)
-k_trace_pixels(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
-               const uint32_t *__restrict__ pixel, const float *__restrict__ intensity,
-               const long long *__restrict__ d_n, long long n_max, int H, int W, const FrameXf *__restrict__ xf,
-               long long n_xf, float *__restrict__ t_hit, int32_t *__restrict__ face, float *__restrict__ point,
-               double *__restrict__ point64, Accum acc, int has_acc, long long *d_hits, TraceStats *stats)
+k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
+        const float4 *__restrict__ dir4, const float *__restrict__ rays6, const float *__restrict__ intensity,
+        const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
+        const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
+        unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled)
 {
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
+    __shared__ unsigned s_queue[(TR_THREADS / 32) * TQ_CAP];
+    __shared__ unsigned long long s_best[TR_THREADS];
+    uint2 lstack[STACK_LOCAL];
+    uint2 *stack = s_stack + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *queue = s_queue + warp * TQ_CAP;
+    unsigned long long *best = s_best + warp * 32;
+    const unsigned lt = (1u << lane) - 1u;
+    long long n = d_n ? *d_n : n_max;
+    if (n > n_max) n = n_max;
+    const bool tiled = SRC == 0 && allow_tiled && n == total_px && (W & 7) == 0 && (H & 3) == 0 && W > 0;
+    const float scale = __ldg(d_scale);
+    unsigned nn = 0, nt = 0, n_hit_local = 0, n_ray_local = 0;
+
+    // lane 0 keeps the next packet's base one fetch ahead, so the atomic's latency hides behind a packet
+    unsigned long long pf = 0;
+    if (lane == 0) pf = atomicAdd(work_counter, 32ull);
+    for (;;) {
+        const long long base = (long long)__shfl_sync(0xffffffffu, pf, 0);
+        if (base >= n) break;
+        if (lane == 0) pf = atomicAdd(work_counter, 32ull);
+        const long long i = base + lane;
+        bool alive = i < n;
+        const bool valid = alive;
+        long long slot = 0;
+        RayState r;
+        {
+            float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
+            if (valid) {
+                slot = work_to_slot(i, tiled, W);
+                if (SRC == 0) {
+                    const float4 d = __ldg(dir4 + slot);
+                    const double *c = xf[__float_as_uint(d.w)].v;
+                    ox = (float)c[13]; oy = (float)c[14]; oz = (float)c[15];
+                    dx = d.x; dy = d.y; dz = d.z;
+                } else {
+                    const float *q = rays6 + 6 * slot;
+                    ox = q[0]; oy = q[1]; oz = q[2]; dx = q[3]; dy = q[4]; dz = q[5];
+                }
+                if (STATS) ++n_ray_local;
+            }
+            ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
+        }
+        best[lane] = KEY_MISS;
+        __syncwarp();
+        int qhead = 0, qcount = 0;              // warp-uniform
+        const unsigned nn_start = nn;
+
+        while (__any_sync(0xffffffffu, alive)) {
+            unsigned tmask = 0, tbase = 0;
+            if (alive) {
+                const float tlimit = __uint_as_float((unsigned)(best[lane] >> 32)) * T_SLACK;
+                alive = node_step<STATS>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn);
+            }
+            // queue this step's triangles, one per lane and round; test whenever 32 are waiting
+            for (;;) {
+                const unsigned contrib = __ballot_sync(0xffffffffu, tmask != 0u);
+                if (!contrib) break;
+                if (tmask) {
+                    const int b = __ffs(tmask) - 1;
+                    tmask &= tmask - 1u;
+                    queue[(qhead + qcount + __popc(contrib & lt)) & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
+                }
+                qcount += __popc(contrib);
+                __syncwarp();
+                if (qcount >= 32) {
+                    tri_batch<STATS>(r, tris, queue, best, qhead, 32, lane, nt);
+                    qhead = (qhead + 32) & (TQ_CAP - 1);
+                    qcount -= 32;
+                }
+            }
+        }
+        if (qcount) tri_batch<STATS>(r, tris, queue, best, qhead, qcount, lane, nt);
+
+        // ---- results of the packet
+        const unsigned long long key = best[lane];
+        const float tb = __uint_as_float((unsigned)(key >> 32));
+        const int bf = (int)(unsigned)key;
+        if (valid) {
+            if (t_hit) t_hit[slot] = tb;
+            if (face) face[slot] = bf;
+            if (STATS && stats->ray_nodes) stats->ray_nodes[slot] = nn - nn_start;
+        }
+        const bool hit = valid && bf >= 0;
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            ++n_hit_local;
+            if (has_acc) {
+                // warp-aggregated: one atomic per distinct face in the packet
+                const unsigned peers = __match_any_sync(hm, bf);
+                float I = intensity ? intensity[slot] : 0.0f;
+                I = I > 0.0f ? I : 0.0f;
+                const unsigned mx = __reduce_max_sync(peers, __float_as_uint(I));
+                if (lane == __ffs(peers) - 1) {
+                    atomicAdd(&acc.hist[bf], __popc(peers));
+                    atomicMax(&acc.fmax[bf], mx);
+                    const int32_t *f3 = acc.F + 3ll * bf;
+                    atomicMax(&acc.vmax[f3[0]], mx);
+                    atomicMax(&acc.vmax[f3[1]], mx);
+                    atomicMax(&acc.vmax[f3[2]], mx);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // ---- per-warp totals
+    unsigned h = n_hit_local;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    if (d_hits && lane == 0 && h) atomicAdd(reinterpret_cast<unsigned long long *>(d_hits), (unsigned long long)h);
+    if (STATS) {
+        unsigned long long a = nn, b = nt, c = n_ray_local;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, d);
+            b += __shfl_xor_sync(0xffffffffu, b, d);
+            c += __shfl_xor_sync(0xffffffffu, c, d);
+        }
+        if (lane == 0) {
+            atomicAdd(&stats->rays, c);
+            atomicAdd(&stats->hits, (unsigned long long)h);
+            atomicAdd(&stats->nodes, a);
+            atomicAdd(&stats->tris, b);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Subsystem (2): pixel -> ray, float64 exactly as compute_rays (:216-221), then the object-frame
+// rotation in float64 and the float32 cast of :251.  One thread per compacted pixel; dir4.w carries
+// the frame index.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
+                                              uint32_t &fr, double &dcx, double &dcy, double &dcz)
+{
+    const uint32_t hw = (uint32_t)H * (uint32_t)W;
+    fr = pix / hw;
+    const uint32_t rem = pix - fr * hw;
+    const uint32_t y = rem / (uint32_t)W;
+    const uint32_t x = rem - y * (uint32_t)W;
+    if ((long long)fr >= n_xf) fr = 0;
+    const double *c = xf[fr].v;
+    const double xn = __ddiv_rn(__dsub_rn((double)x, c[2]), c[0]);
+    const double yn = __ddiv_rn(__dsub_rn((double)y, c[3]), c[1]);
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xn, xn), __dmul_rn(yn, yn)), 1.0));
+    dcx = __ddiv_rn(xn, nrm);
+    dcy = __ddiv_rn(yn, nrm);
+    dcz = __ddiv_rn(1.0, nrm);
+}
+
+__global__ void __launch_bounds__(256)
+k_raygen(const uint32_t *__restrict__ pixel, const long long *__restrict__ d_n, long long n_max, int H, int W,
+         const FrameXf *__restrict__ xf, long long n_xf, float4 *__restrict__ dir4)
+{
     long long n = *d_n;
     if (n > n_max) n = n_max;
-    const long long i = blockIdx.x * (long long)TR_THREADS + threadIdx.x;
-    if ((long long)blockIdx.x * TR_THREADS >= n) return;      // whole block idle
-    const bool valid = i < n;
-
-    float best = __int_as_float(0x7f800000);
-    int bf = -1;
-    unsigned nn = 0, nt = 0;
-    double dcx = 0.0, dcy = 0.0, dcz = 0.0;
-    if (valid) {
-        const uint32_t pix = pixel[i];
-        const uint32_t hw = (uint32_t)H * (uint32_t)W;
-        const uint32_t fr = pix / hw;
-        const uint32_t rem = pix - fr * hw;
-        const uint32_t y = rem / (uint32_t)W;
-        const uint32_t x = rem - y * (uint32_t)W;
-        const double *c = xf[(long long)fr < n_xf ? fr : 0].v;
-        // compute_rays (:216-221) in float64, operation by operation
-        const double xn = __ddiv_rn(__dsub_rn((double)x, c[2]), c[0]);
-        const double yn = __ddiv_rn(__dsub_rn((double)y, c[3]), c[1]);
-        const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xn, xn), __dmul_rn(yn, yn)), 1.0));
-        dcx = __ddiv_rn(xn, nrm);
-        dcy = __ddiv_rn(yn, nrm);
-        dcz = __ddiv_rn(1.0, nrm);
-        const double *Ri = c + 4;
-        const float dx = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[0], dcx), __dmul_rn(Ri[1], dcy)), __dmul_rn(Ri[2], dcz));
-        const float dy = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[3], dcx), __dmul_rn(Ri[4], dcy)), __dmul_rn(Ri[5], dcz));
-        const float dz = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[6], dcx), __dmul_rn(Ri[7], dcy)), __dmul_rn(Ri[8], dcz));
-        const float ox = (float)c[13], oy = (float)c[14], oz = (float)c[15];
-        const float pad_abs = 1.9073486e-6f * (__ldg(d_scale) + fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))));
-        traverse<STATS>(nodes, tris, pad_abs, ox, oy, oz, dx, dy, dz, s_stack + threadIdx.x, best, bf, nn, nt);
-        if (t_hit) t_hit[i] = best;
-        if (face) face[i] = bf;
-        if (point64) {
-            const double t = (double)best;
-            const double qn = __longlong_as_double(0x7ff8000000000000ll);
-            point64[3 * i + 0] = bf >= 0 ? __dmul_rn(dcx, t) : qn;
-            point64[3 * i + 1] = bf >= 0 ? __dmul_rn(dcy, t) : qn;
-            point64[3 * i + 2] = bf >= 0 ? __dmul_rn(dcz, t) : qn;
-        }
-        if (point) {
-            if (bf >= 0) {
-                // :261-263 with origin 0: p = d (float64) * t (float32), stored as float32
-                const double t = (double)best;
-                point[3 * i + 0] = (float)__dmul_rn(dcx, t);
-                point[3 * i + 1] = (float)__dmul_rn(dcy, t);
-                point[3 * i + 2] = (float)__dmul_rn(dcz, t);
-            } else {
-                const float qnan = __int_as_float(0x7fc00000);
-                point[3 * i + 0] = qnan; point[3 * i + 1] = qnan; point[3 * i + 2] = qnan;
-            }
-        }
-    }
-    const bool hit = valid && bf >= 0;
-    const unsigned hm = __ballot_sync(0xffffffffu, hit);
-    const int lane = threadIdx.x & 31;
-    if (d_hits && lane == 0 && hm) atomicAdd(reinterpret_cast<unsigned long long *>(d_hits), (unsigned long long)__popc(hm));
-    if (has_acc && hit) {
-        // warp-aggregated: one atomic per distinct face in the warp
-        const unsigned peers = __match_any_sync(hm, bf);
-        float I = intensity ? intensity[i] : 0.0f;
-        I = I > 0.0f ? I : 0.0f;
-        const unsigned mx = __reduce_max_sync(peers, __float_as_uint(I));
-        if (lane == __ffs(peers) - 1) {
-            atomicAdd(&acc.hist[bf], __popc(peers));
-            atomicMax(&acc.fmax[bf], mx);
-            const int32_t *f3 = acc.F + 3ll * bf;
-            atomicMax(&acc.vmax[f3[0]], mx);
-            atomicMax(&acc.vmax[f3[1]], mx);
-            atomicMax(&acc.vmax[f3[2]], mx);
-        }
-    }
-    if (STATS) warp_stats(stats, valid, hit, nn, nt);
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t fr;
+    double dcx, dcy, dcz;
+    pixel_ray_f64(pixel[i], H, W, xf, n_xf, fr, dcx, dcy, dcz);
+    const double *Ri = xf[fr].v + 4;
+    float4 d;
+    d.x = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[0], dcx), __dmul_rn(Ri[1], dcy)), __dmul_rn(Ri[2], dcz));
+    d.y = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[3], dcx), __dmul_rn(Ri[4], dcy)), __dmul_rn(Ri[5], dcz));
+    d.z = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[6], dcx), __dmul_rn(Ri[7], dcy)), __dmul_rn(Ri[8], dcz));
+    d.w = __uint_as_float(fr);
+    dir4[i] = d;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(TR_THREADS)
-k_trace_rays6(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
-              const float *__restrict__ rays6, long long n, float *__restrict__ t_hit, int32_t *__restrict__ face,
-              TraceStats *stats)
+// hit point in the camera frame: p = d_cam (float64) * t (float32)   (:261-263 with origin 0)
+__global__ void __launch_bounds__(256)
+k_points(const uint32_t *__restrict__ pixel, const float *__restrict__ t_hit, const long long *__restrict__ d_n,
+         long long n_max, int H, int W, const FrameXf *__restrict__ xf, long long n_xf, float *__restrict__ point,
+         double *__restrict__ point64)
 {
-    __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
-    const long long i = blockIdx.x * (long long)TR_THREADS + threadIdx.x;
-    const bool valid = i < n;
-    float best = __int_as_float(0x7f800000);
-    int bf = -1;
-    unsigned nn = 0, nt = 0;
-    if (valid) {
-        const float *r = rays6 + 6 * i;
-        const float ox = r[0], oy = r[1], oz = r[2], dx = r[3], dy = r[4], dz = r[5];
-        const float pad_abs = 1.9073486e-6f * (__ldg(d_scale) + fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))));
-        traverse<STATS>(nodes, tris, pad_abs, ox, oy, oz, dx, dy, dz, s_stack + threadIdx.x, best, bf, nn, nt);
-        if (t_hit) t_hit[i] = best;
-        if (face) face[i] = bf;
+    long long n = *d_n;
+    if (n > n_max) n = n_max;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float tf = t_hit[i];
+    const bool hit = tf < __int_as_float(0x7f800000);
+    double px, py, pz;
+    if (hit) {
+        uint32_t fr;
+        double dcx, dcy, dcz;
+        pixel_ray_f64(pixel[i], H, W, xf, n_xf, fr, dcx, dcy, dcz);
+        const double t = (double)tf;
+        px = __dmul_rn(dcx, t); py = __dmul_rn(dcy, t); pz = __dmul_rn(dcz, t);
+    } else {
+        px = py = pz = __longlong_as_double(0x7ff8000000000000ll);
     }
-    if (STATS) warp_stats(stats, valid, valid && bf >= 0, nn, nt);
+    if (point64) { point64[3 * i] = px; point64[3 * i + 1] = py; point64[3 * i + 2] = pz; }
+    if (point) { point[3 * i] = (float)px; point[3 * i + 1] = (float)py; point[3 * i + 2] = (float)pz; }
 }
 
 // compute_rays (:196-223) on its own: float64 unit directions in the camera frame
@@ -358,6 +512,29 @@ __global__ void k_compute_rays(const int32_t *__restrict__ xs, const int32_t *__
     rays3[3 * i + 2] = __ddiv_rn(1.0, nrm);
 }
 
+int knob_tiled()
+{
+    if (g_tiled < 0) { const char *e = getenv("DP_TILED"); g_tiled = e ? atoi(e) : 1; }
+    return g_tiled;
+}
+
+int g_trace_grid = 0;     // persistent grid: CTAs resident on the device at once
+
+cudaError_t trace_grid(int *grid)
+{
+    if (g_trace_grid == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0>, TR_THREADS, 0)) != cudaSuccess)
+            return e;
+        g_trace_grid = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    *grid = g_trace_grid;
+    return cudaSuccess;
+}
+
 }  // namespace
 
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
@@ -368,34 +545,63 @@ cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n,
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_pixels(const BvhView &bvh, const uint32_t *pixel, const float *intensity,
-                                const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
-                                int64_t n_xf, float *t_hit, int32_t *face, float *point, double *point64,
-                                const Accum *acc, long long *d_hits, TraceStats *stats, cudaStream_t s)
+cudaError_t launch_raygen(const uint32_t *pixel, const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
+                          int64_t n_xf, float4 *dir4, cudaStream_t s)
 {
     if (n_max <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n_max + TR_THREADS - 1) / TR_THREADS);
+    k_raygen<<<(unsigned)((n_max + 255) / 256), 256, 0, s>>>(pixel, d_n, n_max, H, W, xf, n_xf, dir4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long long *d_n, int64_t n_max, int H, int W,
+                          const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s)
+{
+    if (n_max <= 0 || (!point && !point64)) return cudaSuccess;
+    k_points<<<(unsigned)((n_max + 255) / 256), 256, 0, s>>>(pixel, t_hit, d_n, n_max, H, W, xf, n_xf, point, point64);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
+                                int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
+                                int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
+                                TraceStats *stats, cudaStream_t s)
+{
+    if (n_max <= 0) return cudaSuccess;
+    cudaError_t e;
+    int grid = 0;
+    if ((e = trace_grid(&grid)) != cudaSuccess) return e;
+    const long long want = (n_max + TR_THREADS - 1) / TR_THREADS;
+    if (want < grid) grid = (int)want;
+    if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
     if (stats)
-        k_trace_pixels<true><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, pixel, intensity, d_n, n_max,
-                                                         H, W, xf, n_xf, t_hit, face, point, point64, a,
-                                                         acc != nullptr, d_hits, stats);
+        k_trace<true, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,
+                                                     total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter,
+                                                     d_hits, stats, knob_tiled());
     else
-        k_trace_pixels<false><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, pixel, intensity, d_n,
-                                                          n_max, H, W, xf, n_xf, t_hit, face, point, point64, a,
-                                                          acc != nullptr, d_hits, stats);
+        k_trace<false, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n,
+                                                      n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr,
+                                                      work_counter, d_hits, stats, knob_tiled());
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,
-                               TraceStats *stats, cudaStream_t s)
+                               unsigned long long *work_counter, TraceStats *stats, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n + TR_THREADS - 1) / TR_THREADS);
+    cudaError_t e;
+    int grid = 0;
+    if ((e = trace_grid(&grid)) != cudaSuccess) return e;
+    const long long want = (n + TR_THREADS - 1) / TR_THREADS;
+    if (want < grid) grid = (int)want;
+    if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
+    Accum a{nullptr, nullptr, nullptr, nullptr};
     if (stats)
-        k_trace_rays6<true><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, rays6, n, t_hit, face, stats);
+        k_trace<true, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0,
+                                                     0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0);
     else
-        k_trace_rays6<false><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, rays6, n, t_hit, face, stats);
+        k_trace<false, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n,
+                                                      0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0);
     return cudaGetLastError();
 }
 

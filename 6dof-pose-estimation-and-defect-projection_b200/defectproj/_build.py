@@ -27,13 +27,14 @@ def is_stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, extra=(), out=None) -> str:
+    out = out or SO_PATH
+    if not force and not is_stale() and out == SO_PATH:
         return SO_PATH
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra)
     if verbose:
         flags = flags + ["-Xptxas", "-v"]
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build" + ("_" + os.path.basename(out) if out != SO_PATH else ""))
     os.makedirs(objdir, exist_ok=True)
 
     def one(src):
@@ -48,12 +49,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH, *objs, "-Xcompiler", "-fPIC",
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC",
            "-cudart", "shared"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return SO_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdefectproj.so")
+SO_PATH = os.environ.get("DEFECTPROJ_LIB") or os.path.join(_HERE, "libdefectproj.so")
 
 DP_OK, DP_E_ARG, DP_E_CUDA, DP_E_NOMEM, DP_E_STATE = 0, -1, -2, -3, -4
 DP_HOST, DP_DEVICE = 0, 1
@@ -55,6 +55,7 @@ SYMBOLS = {
     "dp_get_stats": (i32, [vp, C.POINTER(Stats)]),
     "dp_last_timings": (i32, [vp, vp]),
     "dp_debug_dump_bvh": (i32, [vp, i32, vp, C.POINTER(i64), vp, C.POINTER(i64)]),
+    "dp_debug_ray_nodes": (i32, [vp, vp, i64]),
     "dp_debug_radix_sort": (i32, [vp, vp, vp, i64]),
     "dp_debug_morton": (i32, [vp, vp]),
 }

@@ -312,9 +312,9 @@ class Context:
         return {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
 
     def last_timings(self):
-        ms = (C.c_float * 3)()
+        ms = (C.c_float * 4)()
         self._check(self._L.dp_last_timings(self._h, ms))
-        return {"compact_ms": ms[0], "trace_ms": ms[1], "total_ms": ms[2]}
+        return {"compact_ms": ms[0], "raygen_ms": ms[1], "trace_ms": ms[2], "total_ms": ms[3]}
 
     def dump_bvh(self, frame="object"):
         fr = _frame(frame)
@@ -324,6 +324,11 @@ class Context:
         tris = np.empty((nt.value, 12), np.float32)
         self._check(self._L.dp_debug_dump_bvh(self._h, fr, _ptr(nodes), C.byref(nn), _ptr(tris), C.byref(nt)))
         return nodes, tris
+
+    def ray_node_counts(self, n):
+        out = np.empty(int(n), np.uint32)
+        self._check(self._L.dp_debug_ray_nodes(self._h, _ptr(out), int(n)))
+        return out
 
     def radix_sort(self, keys, vals):
         keys = np.array(keys, dtype=np.uint32, copy=True)

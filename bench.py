@@ -323,7 +323,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_frame": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "wall_ms_per_frame": 1e3 * e2e_wall / e2e_steps,
                     "outputs": "pixel u32, t_hit f32, face i32 per ray + ray/hit counts; heatmap f32 in; pinned host memory"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 4 * args.steps,   # k_compact, k_raygen, k_trace, k_points per frame
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
                          "kernel": "k_trace_pixels<false>", "kernel_ms": k_ms, "bytes_per_ray": b_ray,

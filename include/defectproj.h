@@ -155,12 +155,15 @@ DP_API int dp_accum_device_ptrs(dp_ctx *ctx, int32_t **hist, float **fmax, float
 DP_API int dp_set_stats(dp_ctx *ctx, int enable);
 DP_API int dp_get_stats(dp_ctx *ctx, dp_stats *out);
 /* device time (ms, CUDA events on the caller's stream) of the stages of the last dp_project:
- * [0] compaction, [1] traversal+accumulation, [2] whole call on the device */
-DP_API int dp_last_timings(dp_ctx *ctx, float *ms3);
+ * [0] H2D (if any) + compaction, [1] ray generation, [2] traversal + accumulation kernel,
+ * [3] the whole call on the device (including the hit-point kernel) */
+DP_API int dp_last_timings(dp_ctx *ctx, float *ms4);
 /* structural dump of the wide BVH for the tests: nodes [n*80 bytes], triangle records
  * [nt*48 bytes] (v0.xyz, face id bits, v1.xyz, 0, v2.xyz, 0).  Pass NULL to query sizes. */
 DP_API int dp_debug_dump_bvh(dp_ctx *ctx, int frame, void *nodes, int64_t *n_nodes, void *tris,
                              int64_t *n_tris);
+/* nodes fetched by each ray of the last dp_project launched with stats enabled: counts [n] HOST */
+DP_API int dp_debug_ray_nodes(dp_ctx *ctx, uint32_t *counts, int64_t n);
 /* the in-house radix sort on its own, for the structural tests: sorts (key,value) pairs
  * of HOST arrays in place, stable, ascending by key. */
 DP_API int dp_debug_radix_sort(dp_ctx *ctx, uint32_t *keys, uint32_t *vals, int64_t n);
