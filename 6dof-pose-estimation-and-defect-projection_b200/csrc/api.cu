@@ -4,6 +4,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <new>
@@ -64,9 +65,11 @@ struct dp_ctx {
     DevBuf hist, fmax, vmax;
 
     // per-call scratch
-    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, cscratch, counts, fcounts, xf, stats;
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, cscratch, counts, fcounts, xf, stats;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
     bool stats_on = false;
+    int order_parity = 0;
+    size_t order_np = 0;
     int64_t ray_nodes_n = 0;
     dp_stats last_stats{};
     cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -164,6 +167,7 @@ int dp_create(int device, dp_ctx **out)
         return fail(nullptr, DP_E_CUDA, "dp_create: alloc", e);
     }
     cudaMemset(ctx->scales.p, 0, 64);
+    cudaMemset(ctx->counts.p, 0xff, 64);      // counts[3] = -1: no learnt packet order yet
     *out = ctx;
     return DP_OK;
 }
@@ -176,7 +180,7 @@ void dp_destroy(dp_ctx *ctx)
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face,
                       &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
-                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
+                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats};
     for (DevBuf *b : bufs) b->release();
     if (ctx->build_scratch) cudaFree(ctx->build_scratch);
@@ -522,12 +526,42 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     // t_hit is needed by the hit-point kernel even when the caller does not want it
     if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
     CK(ctx->dir4.ensure((size_t)cap * 16 + 16), "dp_project: rays");
+    // packet schedule: read the state the previous call wrote, write the other one (double buffer)
+    const OrderState *ord_prev = nullptr;
+    OrderState *ord_next = nullptr;
+    {
+        const size_t np = (size_t)(cap / 32 + 2);
+        const size_t per = np * 4 * 2 + ((np + 15) & ~size_t(15));
+        const void *before = ctx->order.p;
+        CK(ctx->order.ensure(2 * per + 256), "dp_project: schedule");
+        char *basep = ctx->order.as<char>();
+        OrderState h[2];
+        for (int k = 0; k < 2; ++k) {
+            char *p = basep + 256 + k * per;
+            h[k].n_valid = -1; h[k].cost_sum = 0; h[k].cnt[0] = h[k].cnt[1] = 0;
+            h[k].list0 = reinterpret_cast<uint32_t *>(p);
+            h[k].list1 = reinterpret_cast<uint32_t *>(p + np * 4);
+            h[k].flags = reinterpret_cast<unsigned char *>(p + np * 8);
+        }
+        OrderState *dstate = reinterpret_cast<OrderState *>(basep);
+        if (ctx->order.p != before || np != ctx->order_np) {
+            CK(cudaMemcpyAsync(dstate, h, sizeof(h), cudaMemcpyHostToDevice, s), "dp_project: schedule");
+            ctx->order_parity = 0;
+            ctx->order_np = np;
+        }
+        const int cur = ctx->order_parity, nxt = cur ^ 1;
+        // reset the state this launch will write (n_valid, cost_sum, cnt), keep its pointers
+        CK(cudaMemcpyAsync(dstate + nxt, &h[nxt], offsetof(OrderState, list0), cudaMemcpyHostToDevice, s), "dp_project: schedule");
+        ord_prev = dstate + cur;
+        ord_next = dstate + nxt;
+        ctx->order_parity = nxt;
+    }
     CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s),
        "dp_project: ray generation");
     CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
     CK(launch_trace_pixels(view_of(b), ctx->dir4.as<float4>(), d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
-                           d_counts + 1, st, s),
+                           d_counts + 1, st, ord_prev, ord_next, s),
        "dp_project: traversal");
     CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
     CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s),

@@ -51,6 +51,15 @@ struct Accum {
     const int32_t *F;  // [nF*3]
 };
 
+// Packet schedule learnt by one traversal launch for the next one over the same rays (device memory).
+struct OrderState {
+    long long n_valid;               // ray count the lists were built for (-1 = none)
+    unsigned long long cost_sum;     // sum over packets of the longest ray (node steps)
+    unsigned cnt[2];                 // entries in list0 / list1
+    uint32_t *list0, *list1;         // packets above 2.5x / 1.5x the mean cost
+    unsigned char *flags;            // [packets] 1 = the packet is in one of the lists
+};
+
 struct TraceStats {
     unsigned long long rays, hits, nodes, tris;
     unsigned *ray_nodes;   // optional [n]: nodes fetched by each ray (debug)
@@ -74,7 +83,7 @@ cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long 
 cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
-                                TraceStats *stats, cudaStream_t s);
+                                TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s);
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
                                 cudaStream_t s);
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,

@@ -142,20 +142,39 @@ __device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float
 #ifndef DP_PLANE_MODE
 #define DP_PLANE_MODE 0
 #endif
-#if DP_PLANE_MODE == 0
+#if DP_PLANE_MODE == 0 || DP_PLANE_MODE == 3
 __device__ __forceinline__ float qf(unsigned w, int i)
 {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (unsigned)i)) - 8388608.0f;
+    // selector as the immediate, the magic constant in a register: one PRMT, no extra move
+    const unsigned magic = 0x4B000000u;
+    unsigned f;
+    switch (i) {
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7440;" : "=r"(f) : "r"(w), "r"(magic)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7441;" : "=r"(f) : "r"(w), "r"(magic)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7442;" : "=r"(f) : "r"(w), "r"(magic)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7443;" : "=r"(f) : "r"(w), "r"(magic)); break;
+    }
+    return __uint_as_float(f) - 8388608.0f;
+}
+__device__ __forceinline__ float qf_xu(unsigned w, int i)
+{
+#if DP_PLANE_MODE == 3
+    return (float)((w >> (8 * i)) & 0xffu);       // I2F.U8 on the XU pipe: spreads the conversions over two pipes
+#else
+    return qf(w, i);
+#endif
 }
 #define DP_QBIAS 0.0f
 #elif DP_PLANE_MODE == 1
 __device__ __forceinline__ float qf(unsigned w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+__device__ __forceinline__ float qf_xu(unsigned w, int i) { return qf(w, i); }
 #define DP_QBIAS 0.0f
 #else
 __device__ __forceinline__ float qf(unsigned w, int i)
 {
     return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (unsigned)(i << 4)));
 }
+__device__ __forceinline__ float qf_xu(unsigned w, int i) { return qf(w, i); }
 #define DP_QBIAS 32768.0f
 #endif
 
@@ -214,9 +233,9 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
         const unsigned cbits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tnx = fmaf(qf(nxw, j), adjx, nox);
-            const float tny = fmaf(qf(nyw, j), adjy, noy);
-            const float tnz = fmaf(qf(nzw, j), adjz, noz);
+            const float tnx = fmaf(qf_xu(nxw, j), adjx, nox);
+            const float tny = fmaf(qf_xu(nyw, j), adjy, noy);
+            const float tnz = fmaf(qf_xu(nzw, j), adjz, noz);
             const float tfx = fmaf(qf(fxw, j), adjx, fox);
             const float tfy = fmaf(qf(fyw, j), adjy, foy);
             const float tfz = fmaf(qf(fzw, j), adjz, foz);
@@ -298,7 +317,8 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
         const float4 *__restrict__ dir4, const float *__restrict__ rays6, const float *__restrict__ intensity,
         const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
         const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
-        unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled)
+        unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
+        const OrderState *__restrict__ ord_prev, OrderState *ord_next)
 {
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
     __shared__ unsigned s_queue[(TR_THREADS / 32) * TQ_CAP];
@@ -314,15 +334,35 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
     const bool tiled = SRC == 0 && allow_tiled && n == total_px && (W & 7) == 0 && (H & 3) == 0 && W > 0;
     const float scale = __ldg(d_scale);
     unsigned nn = 0, nt = 0, n_hit_local = 0, n_ray_local = 0;
+    // Packets the previous launch over the same rays found expensive (longest ray, in node steps,
+    // above 2.5x / 1.5x the mean) are walked first, so that their long dependent chains overlap with
+    // the bulk of the work instead of forming the tail of the kernel; the rest follows in natural order.
+    const long long np = (n + 31) >> 5;
+    const bool use_order = ord_prev != nullptr && ord_prev->n_valid == n;
+    const long long c0 = use_order ? (long long)ord_prev->cnt[0] : 0, c1 = use_order ? (long long)ord_prev->cnt[1] : 0;
+    float thr0 = __int_as_float(0x7f800000), thr1 = thr0;
+    if (ord_prev != nullptr && ord_prev->n_valid == n && np > 0) {
+        const float mean = (float)ord_prev->cost_sum / (float)np;
+        thr0 = 2.5f * mean; thr1 = 1.5f * mean;
+    }
+    if (ord_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ord_next->n_valid = n;
+    unsigned long long cost_local = 0;
 
     // lane 0 keeps the next packet's base one fetch ahead, so the atomic's latency hides behind a packet
     unsigned long long pf = 0;
-    if (lane == 0) pf = atomicAdd(work_counter, 32ull);
+    if (lane == 0) pf = atomicAdd(work_counter, 1ull);
     for (;;) {
-        const long long base = (long long)__shfl_sync(0xffffffffu, pf, 0);
-        if (base >= n) break;
-        if (lane == 0) pf = atomicAdd(work_counter, 32ull);
-        const long long i = base + lane;
+        const long long w = (long long)__shfl_sync(0xffffffffu, pf, 0);
+        if (w >= np + c0 + c1) break;
+        if (lane == 0) pf = atomicAdd(work_counter, 1ull);
+        long long packet;
+        if (w < c0) packet = ord_prev->list0[w];
+        else if (w < c0 + c1) packet = ord_prev->list1[w - c0];
+        else {
+            packet = w - c0 - c1;
+            if (use_order && ord_prev->flags[packet]) continue;      // already done from a list
+        }
+        const long long i = packet * 32 + lane;
         bool alive = i < n;
         const bool valid = alive;
         long long slot = 0;
@@ -348,12 +388,14 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
         __syncwarp();
         int qhead = 0, qcount = 0;              // warp-uniform
         const unsigned nn_start = nn;
+        unsigned steps = 0;
 
         while (__any_sync(0xffffffffu, alive)) {
             unsigned tmask = 0, tbase = 0;
             if (alive) {
                 const float tlimit = __uint_as_float((unsigned)(best[lane] >> 32)) * T_SLACK;
                 alive = node_step<STATS>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn);
+                ++steps;
             }
             // queue this step's triangles, one per lane and round; test whenever 32 are waiting
             for (;;) {
@@ -375,6 +417,19 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
         }
         if (qcount) tri_batch<STATS>(r, tris, queue, best, qhead, qcount, lane, nt);
 
+        if (ord_next != nullptr) {
+            const unsigned c = __reduce_max_sync(0xffffffffu, steps);
+            if (lane == 0) {
+                cost_local += c;
+                const float cf = (float)c;
+                const int cls = cf > thr0 ? 0 : (cf > thr1 ? 1 : 2);
+                ord_next->flags[packet] = cls < 2;
+                if (cls < 2) {
+                    const unsigned pos = atomicAdd(&ord_next->cnt[cls], 1u);
+                    (cls == 0 ? ord_next->list0 : ord_next->list1)[pos] = (uint32_t)packet;
+                }
+            }
+        }
         // ---- results of the packet
         const unsigned long long key = best[lane];
         const float tb = __uint_as_float((unsigned)(key >> 32));
@@ -407,6 +462,7 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
         __syncwarp();
     }
     // ---- per-warp totals
+    if (ord_next != nullptr && lane == 0 && cost_local) atomicAdd(&ord_next->cost_sum, cost_local);
     unsigned h = n_hit_local;
 #pragma unroll
     for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
@@ -512,6 +568,12 @@ __global__ void k_compute_rays(const int32_t *__restrict__ xs, const int32_t *__
     rays3[3 * i + 2] = __ddiv_rn(1.0, nrm);
 }
 
+int g_order = -1;
+int knob_order()
+{
+    if (g_order < 0) { const char *e = getenv("DP_ORDER"); g_order = e ? atoi(e) : 1; }
+    return g_order;
+}
 int knob_tiled()
 {
     if (g_tiled < 0) { const char *e = getenv("DP_TILED"); g_tiled = e ? atoi(e) : 1; }
@@ -564,7 +626,7 @@ cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long 
 cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
-                                TraceStats *stats, cudaStream_t s)
+                                TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s)
 {
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
@@ -574,14 +636,15 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     if (want < grid) grid = (int)want;
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
+    if (knob_order() == 0) { ord_prev = nullptr; ord_next = nullptr; }
     if (stats)
         k_trace<true, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,
                                                      total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter,
-                                                     d_hits, stats, knob_tiled());
+                                                     d_hits, stats, knob_tiled(), ord_prev, ord_next);
     else
         k_trace<false, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n,
                                                       n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr,
-                                                      work_counter, d_hits, stats, knob_tiled());
+                                                      work_counter, d_hits, stats, knob_tiled(), ord_prev, ord_next);
     return cudaGetLastError();
 }
 
@@ -598,10 +661,10 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
     Accum a{nullptr, nullptr, nullptr, nullptr};
     if (stats)
         k_trace<true, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0,
-                                                     0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0);
+                                                     0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr);
     else
         k_trace<false, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n,
-                                                      0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0);
+                                                      0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr);
     return cudaGetLastError();
 }
 
