@@ -470,7 +470,7 @@ __global__ void k_widefit(long long begin, long long end, const WideNode *__rest
             unsigned a = 255u, b = 0u;
             if (valid[s]) {
                 const double base = (double)nlo[k];
-                // 1/128 of a step of slack: the traversal's plane arithmetic is exact to 1/512 step
+                // 1/128 of a quantisation step of slack on top of the exact containment below
                 double x = floor(((double)clo[s][k] - base) / sc[k] - 0.0078125);
                 x = x < 0.0 ? 0.0 : (x > 255.0 ? 255.0 : x);
                 while (x > 0.0 && base + x * sc[k] > (double)clo[s][k]) x -= 1.0;

@@ -88,8 +88,6 @@ __device__ __forceinline__ float safe_inv(float d)
     return fabsf(d) > 1e-18f ? __fdiv_rn(1.0f, d) : copysignf(1e18f, d);
 }
 
-__device__ __forceinline__ float byte_f(unsigned w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
-
 // ------------------------------------------------------------------------------------------
 // Per-lane traversal state.  A warp traces packets of 32 rays in lock step (coherent rays share
 // node fetches); packets are handed out by a global counter to persistent warps so that no SM
@@ -135,15 +133,16 @@ __device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float
     r.sp = 0;
 }
 
-// 8-bit plane index -> float without the conversion (XU) pipe: PRMT drops the byte into the low
-// mantissa bits of 2^23, giving 8388608 + q exactly, and one FADD removes the 2^23 again (exact).
-// DP_PLANE_MODE 1 = plain I2F.U8; 2 = byte in mantissa bits 8..15 of 2^15 with the bias folded into
-// the FMA addend (one instruction less per plane, but 2^-9 of a quantisation step of rounding).
+// 8-bit plane index -> float.  Measured on B200 (configs[1], 500k triangles, traversal kernel):
+//   mode 1  I2F.U8 (XU pipe, 48 per node step)                                   0.311 ms   <- default
+//   mode 0  PRMT into the mantissa of 2^23 + FADD (ALU + FMA pipes, exact)       0.328 ms
+//   mode 3  near planes by I2F, far planes by PRMT + FADD                         0.318 ms
+// A fourth variant (byte into mantissa bits 8..15 of 2^15 with the bias folded into the FMA addend,
+// 0.309 ms) was dropped: it lost a hit on a ray with |1/d| ~ 7e13 in tests/test_gpu_parity.py.
 #ifndef DP_PLANE_MODE
-#define DP_PLANE_MODE 0
+#define DP_PLANE_MODE 1
 #endif
-#if DP_PLANE_MODE == 0 || DP_PLANE_MODE == 3
-__device__ __forceinline__ float qf(unsigned w, int i)
+__device__ __forceinline__ float qf_magic(unsigned w, int i)
 {
     // selector as the immediate, the magic constant in a register: one PRMT, no extra move
     const unsigned magic = 0x4B000000u;
@@ -156,26 +155,16 @@ __device__ __forceinline__ float qf(unsigned w, int i)
     }
     return __uint_as_float(f) - 8388608.0f;
 }
-__device__ __forceinline__ float qf_xu(unsigned w, int i)
-{
-#if DP_PLANE_MODE == 3
-    return (float)((w >> (8 * i)) & 0xffu);       // I2F.U8 on the XU pipe: spreads the conversions over two pipes
-#else
-    return qf(w, i);
-#endif
-}
-#define DP_QBIAS 0.0f
+__device__ __forceinline__ float qf_i2f(unsigned w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+#if DP_PLANE_MODE == 0
+#define qf qf_magic
+#define qf_xu qf_magic
 #elif DP_PLANE_MODE == 1
-__device__ __forceinline__ float qf(unsigned w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
-__device__ __forceinline__ float qf_xu(unsigned w, int i) { return qf(w, i); }
-#define DP_QBIAS 0.0f
+#define qf qf_i2f
+#define qf_xu qf_i2f
 #else
-__device__ __forceinline__ float qf(unsigned w, int i)
-{
-    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (unsigned)(i << 4)));
-}
-__device__ __forceinline__ float qf_xu(unsigned w, int i) { return qf(w, i); }
-#define DP_QBIAS 32768.0f
+#define qf qf_magic
+#define qf_xu qf_i2f
 #endif
 
 // One node step: visit the nearest pending inner child (fetch its 80-byte node, test the 8 child
@@ -202,9 +191,9 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
     const float adjx = __uint_as_float((w0.w & 0xffu) << 23) * r.ix;
     const float adjy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23) * r.iy;
     const float adjz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23) * r.iz;
-    const float orgx = fmaf(-DP_QBIAS, adjx, (__uint_as_float(w0.x) - r.ox) * r.ix);
-    const float orgy = fmaf(-DP_QBIAS, adjy, (__uint_as_float(w0.y) - r.oy) * r.iy);
-    const float orgz = fmaf(-DP_QBIAS, adjz, (__uint_as_float(w0.z) - r.oz) * r.iz);
+    const float orgx = (__uint_as_float(w0.x) - r.ox) * r.ix;
+    const float orgy = (__uint_as_float(w0.y) - r.oy) * r.iy;
+    const float orgz = (__uint_as_float(w0.z) - r.oz) * r.iz;
     const float nox = orgx - r.px, fox = orgx + r.px;
     const float noy = orgy - r.py, foy = orgy + r.py;
     const float noz = orgz - r.pz, foz = orgz + r.pz;

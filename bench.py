@@ -11,7 +11,7 @@ threshold+compaction -> pixel rays (object frame) -> 8-wide BVH traversal -> his
              launching stream, L2 flushed between steps (256 MiB memset, outside the events).
 * e2e        the same frame through the host-buffer C-ABI call (dp_project, DP_HOST): pinned host heatmap
              in, (pixel, t_hit, face) + counts out, copies inside the timed region.
-* roofline   traversal kernel: algorithmic bytes/ray (80 B x nodes fetched + 48 B x triangles tested + 32 B
+* roofline   traversal kernel (k_trace): algorithmic bytes/ray (80 B x nodes fetched + 48 B x triangles tested + 32 B
              of ray I/O + 32 B of accumulator RMW per hit; counts measured live by the counting kernel
              variant) / the kernel's mean duration (CUDA events), against MEASURED_PEAKS.json's HBM copy rate.
 * cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/, OpenMP, all host
@@ -326,7 +326,7 @@ def run_ours(args):
             "gpu_launches": 4 * args.steps,   # k_compact, k_raygen, k_trace, k_points per frame
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
-                         "kernel": "k_trace_pixels<false>", "kernel_ms": k_ms, "bytes_per_ray": b_ray,
+                         "kernel": "k_trace<false,0>", "kernel_ms": k_ms, "bytes_per_ray": b_ray,
                          "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "hit_frac": hit_frac,
                          "note": "BVH (nodes+records) is smaller than L2, so most fetched bytes are L2 hits: frac is "
                                  "algorithmic bytes over the HBM copy rate, not DRAM traffic"},

@@ -566,3 +566,51 @@ def test_shards_of_a_batch_combine_to_the_whole(ctx):
         assert np.array_equal(np.max(fs, axis=0), fw) and np.array_equal(np.max(vs, axis=0), vw)
         assert np.array_equal(np.concatenate(faces), whole["face"])
         assert np.array_equal(np.concatenate(pix), whole["pixel"].astype(np.int64))
+
+
+def test_repeated_calls_are_identical_and_schedule_state_is_safe(ctx, orc):
+    """The traversal learns a packet schedule from the previous launch over the same rays (heavy packets
+    first).  It must never change results, and must be dropped when the ray count changes."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0, scale=6.0)
+    K, H, W = synth.camera_wfov()
+    pose = synth.fill_frame_pose()
+    ctx.set_mesh(V, F).build_bvh()
+    dense = np.ones((256, 512), np.float32)
+    Ks = synth.K_matrix(126.0, 126.0, 256.0, 128.0)
+    ref = None
+    for it in range(4):                                              # 1st: natural order, 2nd: thresholds, 3rd+: lists
+        ctx.accum_reset()
+        res = ctx.project(dense, Ks, pose[None], 0.5, "object", True, want=("pixel", "t_hit", "face"))
+        hist = ctx.accum_get()[0]
+        if ref is None:
+            xs, ys, I = orc.heatmap_to_points(dense, 0.5)
+            t, f = orc.Bvh(V, F).cast_f32(orc.rays_object_frame(xs, ys, orc.frame_xform(Ks, pose)))
+            assert np.array_equal(res["face"], f) and np.array_equal(_bits(res["t_hit"]), _bits(t))
+            ref = (res["face"].copy(), res["t_hit"].copy(), hist.copy())
+        assert np.array_equal(res["face"], ref[0]) and np.array_equal(_bits(res["t_hit"]), _bits(ref[1]))
+        assert np.array_equal(hist, ref[2]) and hist.sum() == res["hits"]
+    # a different ray count right after: the learnt lists must be ignored, not indexed out of range
+    for shape, thr in (((100, 300), 0.5), ((256, 512), 0.5), ((31, 33), 0.5)):
+        heat = np.random.default_rng(shape[0]).random(shape).astype(np.float32)
+        Kx = synth.K_matrix(126.0, 126.0, shape[1] / 2, shape[0] / 2)
+        res = ctx.project(heat, Kx, pose[None], thr, "object", False, want=("pixel", "t_hit", "face"))
+        xs, ys, I = orc.heatmap_to_points(heat, thr)
+        t, f = orc.Bvh(V, F).cast_f32(orc.rays_object_frame(xs, ys, orc.frame_xform(Kx, pose)))
+        assert np.array_equal(res["face"], f) and np.array_equal(_bits(res["t_hit"]), _bits(t))
+
+
+def test_statistics_counters(ctx):
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["small"], seed=0)
+    K, H, W = synth.camera_720p()
+    ctx.set_mesh(V, F).build_bvh()
+    ctx.set_stats(True)
+    try:
+        res = ctx.project(synth.gaussian_heatmap((H, W), dtype=np.float32), K, synth.fixed_pose()[None], 0.5)
+        st = ctx.stats()
+        assert st["rays"] == res["n"] == 10885 and st["hits"] == res["hits"]
+        assert st["nodes_fetched"] >= st["rays"] and st["tris_tested"] >= st["hits"]
+        counts = ctx.ray_node_counts(res["n"])
+        assert counts.sum() == st["nodes_fetched"] and counts.min() >= 1
+        assert st["n_tris"] == len(F) and 1 <= st["wide_depth"] <= 16
+    finally:
+        ctx.set_stats(False)
