@@ -566,6 +566,8 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
     CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s),
        "dp_project: hit points");
+    if (out && out->counts)
+        CK(cudaMemcpyAsync(out->counts, d_counts, 16, cudaMemcpyDefault, s), "dp_project: counts");
     CK(cudaEventRecord(ctx->ev[2], s), "dp_project");
     ctx->timings_valid = true;
 

@@ -9,6 +9,6 @@ include/defectproj.h).  There is no CPU fallback.
 """
 from . import synth  # noqa: F401
 from .core import Context, DefectProjError  # noqa: F401
-from .projector import Projector  # noqa: F401
+from .projector import FrameStream, Projector  # noqa: F401
 
-__all__ = ["Context", "Projector", "DefectProjError", "synth"]
+__all__ = ["Context", "Projector", "FrameStream", "DefectProjError", "synth"]

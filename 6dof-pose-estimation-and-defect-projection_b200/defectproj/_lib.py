@@ -22,7 +22,7 @@ i64, i32, f64, vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
 
 class RaysOut(C.Structure):
     _fields_ = [("pixel", vp), ("intensity", vp), ("t_hit", vp), ("face", vp), ("point", vp), ("point64", vp),
-                ("cap", i64)]
+                ("cap", i64), ("counts", vp)]
 
 
 class Stats(C.Structure):

@@ -276,8 +276,9 @@ class Context:
             caps = []
             for k, tsr in out.items():
                 setattr(ro, k, _ptr(tsr))
-                caps.append(tsr.shape[0])
-            ro.cap = min(caps)
+                if k != "counts":
+                    caps.append(tsr.shape[0])
+            ro.cap = min(caps) if caps else 0
         n, nh = C.c_int64(0), C.c_int64(0)
         st = self._stream(stream if stream is not None else torch.cuda.current_stream())
         self._check(self._L.dp_project(self._h, fr, _ptr(heat), DP_F64 if heat.dtype == torch.float64 else DP_F32, B, H,

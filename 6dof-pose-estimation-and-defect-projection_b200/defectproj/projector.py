@@ -13,7 +13,7 @@ import numpy as np
 
 from .core import Context
 
-__all__ = ["Projector", "shard_range", "combine_accumulators", "gather_hits"]
+__all__ = ["Projector", "FrameStream", "shard_range", "combine_accumulators", "gather_hits"]
 
 
 def shard_range(n_items: int, world: int, rank: int):
@@ -112,3 +112,112 @@ class Projector:
         if reduce and self.world > 1:
             combine_accumulators(*self.accumulators(), group=self.group)
         return n, h
+
+
+class FrameStream:
+    """Host-buffer streaming of frames through one context with copies and kernels overlapped.
+
+    Three CUDA streams: H2D of frame i+1, kernels of frame i and D2H of frame i-1 run concurrently on
+    double-buffered device memory; the host only waits for the 16-byte ray/hit counts of a frame before it
+    queues that frame's (exact-size) result copy.  Inputs and outputs are pinned host tensors, so
+    every copy is a real DMA.  Results are identical to Context.project on the same frame.
+    """
+
+    _DT = {"pixel": "int32", "intensity": "float32", "t_hit": "float32", "face": "int32", "point": "float32"}
+
+    def __init__(self, ctx: Context, H: int, W: int, want=("pixel", "t_hit", "face"), cap=None, ring: int = 3,
+                 heat_dtype="float32"):
+        import torch
+        self.ctx, self.H, self.W, self.want = ctx, int(H), int(W), tuple(want)
+        self.cap = int(cap) if cap is not None else self.H * self.W
+        self.ring = max(3, int(ring))
+        dev = f"cuda:{ctx.device}"
+        self.dev = dev
+        hd = getattr(torch, heat_dtype)
+        self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.heat_d = [torch.empty((1, self.H, self.W), dtype=hd, device=dev) for _ in range(2)]
+
+        def outs(device, pin):
+            d = {}
+            for k in self.want:
+                shp = (self.cap, 3) if k == "point" else (self.cap,)
+                t = torch.empty(shp, dtype=getattr(torch, self._DT[k]), device=device)
+                d[k] = t.pin_memory() if pin else t
+            return d
+        self.out_d = [outs(dev, False) for _ in range(2)]
+        self.out_h = [outs("cpu", True) for _ in range(self.ring)]
+        self.counts_h = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+
+    def run(self, heats, K, poses, thr=0.5, frame="object", accumulate=True, before_kernels=None):
+        """heats: sequence of pinned host tensors [H,W]; K [3,3] or per frame; poses [B,4,4].
+        Yields (index, dict) per frame in order; the dict's arrays are views of a pinned ring buffer that is
+        reused `ring` frames later.  `before_kernels(stream)` is called on the kernel stream ahead of every
+        frame (bench.py uses it to flush L2).  After the generator is exhausted `last_elapsed_ms` holds the
+        device time from the first H2D to the last D2H (CUDA events)."""
+        import torch
+        ctx = self.ctx
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record(self.s_in)
+        B = len(heats)
+        K = np.asarray(K, np.float64).reshape(-1, 9)
+        poses = None if poses is None else np.asarray(poses, np.float64).reshape(-1, 4, 4)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_k = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(self.ring)]
+        done_k = [False, False]
+        pending = []                                   # frames whose D2H has been queued, not yet yielded
+
+        def queue_d2h(i):
+            b = i % 2
+            ev_k[b].synchronize()                      # the 16-byte counts of frame i are on the host now
+            n, nh = int(self.counts_h[b][0]), int(self.counts_h[b][1])
+            m = min(n, self.cap)
+            r = i % self.ring
+            with torch.cuda.stream(self.s_out):
+                for k in self.want:
+                    self.out_h[r][k][:m].copy_(self.out_d[b][k][:m], non_blocking=True)
+                ev_out[r].record(self.s_out)
+            pending.append((i, r, n, nh, m))
+
+        def pop_result():
+            i, r, n, nh, m = pending.pop(0)
+            ev_out[r].synchronize()
+            res = {k: self.out_h[r][k][:m].numpy() for k in self.want}
+            if "pixel" in res:
+                res["pixel"] = res["pixel"].view(np.uint32)
+            res["n"], res["hits"] = n, nh
+            if n > self.cap:
+                raise MemoryError(f"frame {i}: {n} selected pixels exceed the stream capacity {self.cap}")
+            return i, res
+
+        for i in range(B):
+            b = i % 2
+            with torch.cuda.stream(self.s_in):
+                if done_k[b]:
+                    self.s_in.wait_event(ev_k[b])      # kernels of frame i-2 have consumed this heat buffer
+                self.heat_d[b].copy_(heats[i].reshape(1, self.H, self.W), non_blocking=True)
+                ev_in[b].record(self.s_in)
+            if i >= 2:
+                # the device result buffer b is free once frame i-2's D2H is done
+                self.s_k.wait_event(ev_out[(i - 2) % self.ring])
+            self.s_k.wait_event(ev_in[b])
+            if before_kernels is not None:
+                with torch.cuda.stream(self.s_k):
+                    before_kernels(self.s_k)
+            out = dict(self.out_d[b])
+            out["counts"] = self.counts_h[b]
+            ctx.project_device(self.heat_d[b], K[i if len(K) > 1 else 0], None if poses is None else poses[i:i + 1], thr,
+                               frame, accumulate, out=out, sync=False, stream=self.s_k)
+            ev_k[b].record(self.s_k)
+            done_k[b] = True
+            if i >= 1:
+                queue_d2h(i - 1)
+            while len(pending) > 1:
+                yield pop_result()
+        if B:
+            queue_d2h(B - 1)
+        t_end.record(self.s_out)
+        while pending:
+            yield pop_result()
+        t_end.synchronize()
+        self.last_elapsed_ms = t_start.elapsed_time(t_end)

@@ -68,6 +68,8 @@ typedef struct dp_rays_out {
     float *point;      /* [cap*3] hit point, camera frame     (:261-263); NaN on miss        */
     double *point64;   /* [cap*3] the same in float64: d (float64) * t (float32), as :261-263 */
     int64_t cap;       /* capacity in rays of every non-NULL array above                     */
+    int64_t *counts;   /* optional [2], device or PINNED host memory: receives (n_rays, n_hits) by
+                          an asynchronous copy on the call's stream (for pipelined callers)       */
 } dp_rays_out;
 
 typedef struct dp_stats {

@@ -614,3 +614,31 @@ def test_statistics_counters(ctx):
         assert st["n_tris"] == len(F) and 1 <= st["wide_depth"] <= 16
     finally:
         ctx.set_stats(False)
+
+
+def test_frame_stream_equals_blocking_calls(ctx, orc):
+    """The pipelined host-buffer API (H2D | kernels | D2H on three streams) returns what Context.project returns."""
+    import torch
+    from defectproj import FrameStream
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
+    K, H, W = synth.K_matrix(305.0, 305.0, 320.0, 180.0), 360, 640
+    B = 7
+    poses = synth.helix_poses(B, turns=1)
+    heats = [torch.from_numpy(synth.blob_heatmap((H, W), seed=40 + i)).pin_memory() for i in range(B)]
+    heats[3] = torch.zeros((H, W)).pin_memory()                                   # an empty frame in the middle
+    ctx.set_mesh(V, F).build_bvh()
+    ctx.accum_reset()
+    fs = FrameStream(ctx, H, W, want=("pixel", "t_hit", "face", "point"))
+    got = {}
+    for i, res in fs.run(heats, K, poses, 0.5, "object", True):
+        got[i] = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in res.items()}
+    hist_stream = ctx.accum_get()[0]
+    assert sorted(got) == list(range(B))
+    ctx.accum_reset()
+    for i in range(B):
+        ref = ctx.project(heats[i].numpy(), K, poses[i][None], 0.5, "object", True, want=("pixel", "t_hit", "face", "point"))
+        assert got[i]["n"] == ref["n"] and got[i]["hits"] == ref["hits"]
+        for k in ("pixel", "t_hit", "face", "point"):
+            assert np.array_equal(got[i][k], ref[k], equal_nan=(k in ("t_hit", "point"))), (i, k)
+    assert got[3]["n"] == 0
+    assert np.array_equal(hist_stream, ctx.accum_get()[0]) and hist_stream.sum() == sum(g["hits"] for g in got.values())
