@@ -65,7 +65,7 @@ struct dp_ctx {
     DevBuf hist, fmax, vmax;
 
     // per-call scratch
-    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, cscratch, counts, fcounts, xf, stats;
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[6], cscratch, counts, fcounts, xf, stats;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
     bool stats_on = false;
     int order_parity = 0;
@@ -183,6 +183,7 @@ void dp_destroy(dp_ctx *ctx)
                       &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats};
     for (DevBuf *b : bufs) b->release();
+    for (DevBuf &b : ctx->tmp) b.release();
     if (ctx->build_scratch) cudaFree(ctx->build_scratch);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     for (int i = 0; i < 10; ++i)
@@ -588,6 +589,127 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
             CK(cudaStreamSynchronize(s), "dp_project: D2H");
         }
         if (total > cap) return fail(ctx, DP_E_NOMEM, "dp_project: output capacity too small for the selected pixels");
+    }
+    return DP_OK;
+}
+
+int dp_depth_backproject(dp_ctx *ctx, const void *heat, int dtype, int H, int W, const uint16_t *depth, int Hd, int Wd,
+                         const double *K, double thr, double *points4, int64_t cap, int64_t *n, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (H < 0 || W < 0 || Hd < 0 || Wd < 0 || cap < 0 || !K || !n || (dtype != DP_F32 && dtype != DP_F64))
+        return fail(ctx, DP_E_ARG, "dp_depth_backproject: bad arguments");
+    const int64_t ne = (int64_t)H * W, nd = (int64_t)Hd * Wd;
+    if ((ne > 0 && !heat) || (nd > 0 && !depth) || (cap > 0 && !points4)) return fail(ctx, DP_E_ARG, "dp_depth_backproject: NULL buffer");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == DP_F64 ? 8 : 4;
+    const void *d_heat = heat;
+    const uint16_t *d_depth = depth;
+    double *d_out = points4;
+    if (mem == DP_HOST) {
+        CK(ctx->heat.ensure((size_t)ne * esz + 16), "dp_depth_backproject: heat");
+        CK(ctx->tmp[0].ensure((size_t)nd * 2 + 16), "dp_depth_backproject: depth");
+        CK(ctx->tmp[1].ensure((size_t)cap * 32 + 16), "dp_depth_backproject: out");
+        if (ne) CK(cudaMemcpyAsync(ctx->heat.p, heat, (size_t)ne * esz, cudaMemcpyHostToDevice, s), "dp_depth_backproject: H2D");
+        if (nd) CK(cudaMemcpyAsync(ctx->tmp[0].p, depth, (size_t)nd * 2, cudaMemcpyHostToDevice, s), "dp_depth_backproject: H2D");
+        d_heat = ctx->heat.p;
+        d_depth = ctx->tmp[0].as<uint16_t>();
+        d_out = ctx->tmp[1].as<double>();
+    }
+    CK(ctx->cscratch.ensure(depth_select_scratch_bytes(ne) + 64), "dp_depth_backproject: scratch");
+    CK(ctx->tmp[2].ensure(64), "dp_depth_backproject: scalars");
+    long long *d_counts = ctx->counts.as<long long>();
+    CK(launch_depth_select(d_heat, dtype, H, W, d_depth, Hd, Wd, thr, K, d_out, cap, ctx->cscratch.as<unsigned long long>(),
+                           d_counts, ctx->tmp[2].as<double>(), reinterpret_cast<int *>(ctx->tmp[2].as<char>() + 16), s),
+       "dp_depth_backproject: launch");
+    CK(cudaMemcpyAsync(ctx->h_counts, d_counts, 8, cudaMemcpyDeviceToHost, s), "dp_depth_backproject: count");
+    CK(cudaStreamSynchronize(s), "dp_depth_backproject: kernels");
+    const int64_t total = ctx->h_counts[0];
+    *n = total;
+    const int64_t nc = total < cap ? total : cap;
+    if (mem == DP_HOST && nc > 0) {
+        CK(cudaMemcpyAsync(points4, d_out, (size_t)nc * 32, cudaMemcpyDeviceToHost, s), "dp_depth_backproject: D2H");
+        CK(cudaStreamSynchronize(s), "dp_depth_backproject: D2H");
+    }
+    if (total > cap) return fail(ctx, DP_E_NOMEM, "dp_depth_backproject: capacity too small for the selected pixels");
+    return DP_OK;
+}
+
+int dp_calc_coordinates(dp_ctx *ctx, const int32_t *xs, const int32_t *ys, int64_t n, const uint16_t *depth, int Hd, int Wd,
+                        const double *K, double *out3, unsigned char *valid, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || Hd < 0 || Wd < 0 || !K || (n > 0 && (!xs || !ys || !out3 || !valid)) || ((int64_t)Hd * Wd > 0 && !depth))
+        return fail(ctx, DP_E_ARG, "dp_calc_coordinates: bad arguments");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t nd = (int64_t)Hd * Wd;
+    const int32_t *dx = xs, *dy = ys;
+    const uint16_t *dd = depth;
+    double *dout = out3;
+    unsigned char *dv = valid;
+    if (mem == DP_HOST) {
+        CK(ctx->tmp[0].ensure((size_t)nd * 2 + 16), "dp_calc_coordinates: depth");
+        CK(ctx->tmp[1].ensure((size_t)n * 24 + 16), "dp_calc_coordinates: out");
+        CK(ctx->tmp[3].ensure((size_t)n * 8 + 16), "dp_calc_coordinates: xy");
+        CK(ctx->tmp[4].ensure((size_t)n + 16), "dp_calc_coordinates: valid");
+        if (nd) CK(cudaMemcpyAsync(ctx->tmp[0].p, depth, (size_t)nd * 2, cudaMemcpyHostToDevice, s), "dp_calc_coordinates: H2D");
+        CK(cudaMemcpyAsync(ctx->tmp[3].p, xs, (size_t)n * 4, cudaMemcpyHostToDevice, s), "dp_calc_coordinates: H2D");
+        CK(cudaMemcpyAsync(ctx->tmp[3].as<int32_t>() + n, ys, (size_t)n * 4, cudaMemcpyHostToDevice, s), "dp_calc_coordinates: H2D");
+        dd = ctx->tmp[0].as<uint16_t>();
+        dx = ctx->tmp[3].as<int32_t>();
+        dy = dx + n;
+        dout = ctx->tmp[1].as<double>();
+        dv = ctx->tmp[4].as<unsigned char>();
+    }
+    CK(launch_calc_coordinates(dx, dy, n, dd, Hd, Wd, K, dout, dv, s), "dp_calc_coordinates: launch");
+    if (mem == DP_HOST) {
+        CK(cudaMemcpyAsync(out3, dout, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_calc_coordinates: D2H");
+        CK(cudaMemcpyAsync(valid, dv, (size_t)n, cudaMemcpyDeviceToHost, s), "dp_calc_coordinates: D2H");
+        CK(cudaStreamSynchronize(s), "dp_calc_coordinates: kernels");
+    }
+    return DP_OK;
+}
+
+int dp_align_to_surface(dp_ctx *ctx, const double *query, int stride, int64_t n, const double *target, const double *normals,
+                        int64_t m, double offset, double *offset_points, double *aligned_points, int32_t *idx, int mem,
+                        void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || m < 0 || stride < 3 || (n > 0 && !query) || (m > 0 && !target) || (offset_points && !normals))
+        return fail(ctx, DP_E_ARG, "dp_align_to_surface: bad arguments");
+    if (n > 0 && m == 0) return fail(ctx, DP_E_ARG, "dp_align_to_surface: empty target cloud");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double *dq = query, *dt = target, *dn = normals;
+    double *doff = offset_points, *dal = aligned_points;
+    int32_t *di = idx;
+    if (mem == DP_HOST) {
+        CK(ctx->tmp[0].ensure((size_t)n * stride * 8 + 16), "dp_align_to_surface: query");
+        CK(ctx->tmp[1].ensure((size_t)m * 24 + 16), "dp_align_to_surface: target");
+        CK(ctx->tmp[2].ensure((size_t)m * 24 + 64), "dp_align_to_surface: normals");
+        CK(ctx->tmp[3].ensure((size_t)n * 24 + 16), "dp_align_to_surface: out");
+        CK(ctx->tmp[4].ensure((size_t)n * 24 + 16), "dp_align_to_surface: out");
+        CK(ctx->tmp[5].ensure((size_t)n * 4 + 16), "dp_align_to_surface: idx");
+        CK(cudaMemcpyAsync(ctx->tmp[0].p, query, (size_t)n * stride * 8, cudaMemcpyHostToDevice, s), "dp_align_to_surface: H2D");
+        CK(cudaMemcpyAsync(ctx->tmp[1].p, target, (size_t)m * 24, cudaMemcpyHostToDevice, s), "dp_align_to_surface: H2D");
+        if (normals) CK(cudaMemcpyAsync(ctx->tmp[2].p, normals, (size_t)m * 24, cudaMemcpyHostToDevice, s), "dp_align_to_surface: H2D");
+        dq = ctx->tmp[0].as<double>();
+        dt = ctx->tmp[1].as<double>();
+        dn = normals ? ctx->tmp[2].as<double>() : nullptr;
+        doff = offset_points ? ctx->tmp[3].as<double>() : nullptr;
+        dal = aligned_points ? ctx->tmp[4].as<double>() : nullptr;
+        di = idx ? ctx->tmp[5].as<int32_t>() : nullptr;
+    }
+    CK(launch_nearest(dq, stride, n, dt, m, dn, offset, di, dal, doff, s), "dp_align_to_surface: launch");
+    if (mem == DP_HOST) {
+        if (offset_points) CK(cudaMemcpyAsync(offset_points, doff, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_align_to_surface: D2H");
+        if (aligned_points) CK(cudaMemcpyAsync(aligned_points, dal, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_align_to_surface: D2H");
+        if (idx) CK(cudaMemcpyAsync(idx, di, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_align_to_surface: D2H");
+        CK(cudaStreamSynchronize(s), "dp_align_to_surface: kernels");
     }
     return DP_OK;
 }

@@ -89,6 +89,16 @@ cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n,
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,
                                unsigned long long *work_counter, TraceStats *stats, cudaStream_t s);
 
+// ---- depth.cu ------------------------------------------------------------------------------
+size_t depth_select_scratch_bytes(int64_t n_elems);
+cudaError_t launch_depth_select(const void *heat, int dtype, int H, int W, const uint16_t *depth, int Hd, int Wd,
+                                double thr, const double *K, double *out4, int64_t cap, unsigned long long *scratch,
+                                long long *d_count, double *d_max, int *d_nan, cudaStream_t s);
+cudaError_t launch_calc_coordinates(const int32_t *xs, const int32_t *ys, int64_t n, const uint16_t *depth, int Hd, int Wd,
+                                    const double *K, double *out3, unsigned char *valid, cudaStream_t s);
+cudaError_t launch_nearest(const double *q, int stride, int64_t n, const double *target, int64_t m, const double *normals,
+                           double offset, int32_t *idx, double *aligned, double *offset_pts, cudaStream_t s);
+
 // ---- build.cu ------------------------------------------------------------------------------
 struct BuildScratch;   // opaque, owned by the context
 

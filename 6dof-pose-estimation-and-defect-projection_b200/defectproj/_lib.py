@@ -48,6 +48,9 @@ SYMBOLS = {
     "dp_cast_rays": (i32, [vp, i32, vp, i64, vp, vp, i32, vp]),
     "dp_project": (i32, [vp, i32, vp, i32, i64, i32, i32, f64, vp, i64, vp, i32, C.POINTER(RaysOut),
                          C.POINTER(i64), C.POINTER(i64), i32, vp]),
+    "dp_depth_backproject": (i32, [vp, vp, i32, i32, i32, vp, i32, i32, vp, f64, vp, i64, C.POINTER(i64), i32, vp]),
+    "dp_calc_coordinates": (i32, [vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, i32, vp]),
+    "dp_align_to_surface": (i32, [vp, vp, i32, i64, vp, vp, i64, f64, vp, vp, vp, i32, vp]),
     "dp_accum_reset": (i32, [vp, vp]),
     "dp_accum_get": (i32, [vp, vp, vp, vp, i32, vp]),
     "dp_accum_device_ptrs": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),

@@ -287,6 +287,63 @@ class Context:
                                        C.byref(nh) if sync else None, DP_DEVICE, st))
         return (n.value, nh.value) if sync else None
 
+    # ------------------------------------------------------------------ depth-image projection path
+    @staticmethod
+    def _depth_u16(depth):
+        depth = np.asarray(depth)
+        if depth.dtype != np.uint16:
+            raise ValueError("depth image must be uint16 (cv2.IMREAD_UNCHANGED of a Kinect depth PNG)")
+        if depth.ndim != 2:
+            raise ValueError("depth image must be 2-D")
+        return np.ascontiguousarray(depth)
+
+    def depth_backproject(self, heat, depth, K, thr=0.1, stream=None):
+        """heatmap_to_point3d on the GPU -> float64 [n,4] rows (x3d, y3d, z3d, intensity), row-major pixel order."""
+        heat = np.asarray(heat)
+        if heat.dtype not in (np.float32, np.float64):
+            heat = heat.astype(np.float64)
+        heat = np.ascontiguousarray(heat)
+        if heat.ndim != 2:
+            raise ValueError("heatmap must be 2-D")
+        depth = self._depth_u16(depth)
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        cap = heat.size
+        out = np.empty((cap, 4), np.float64)
+        n = C.c_int64(0)
+        self._check(self._L.dp_depth_backproject(self._h, _ptr(heat), DP_F64 if heat.dtype == np.float64 else DP_F32,
+                                                 heat.shape[0], heat.shape[1], _ptr(depth), depth.shape[0], depth.shape[1],
+                                                 _ptr(K), float(thr), _ptr(out), cap, C.byref(n), DP_HOST, self._stream(stream)))
+        return out[:n.value]
+
+    def calc_coordinates(self, xs, ys, depth, K, stream=None):
+        xs = np.ascontiguousarray(xs, dtype=np.int32)
+        ys = np.ascontiguousarray(ys, dtype=np.int32)
+        depth = self._depth_u16(depth)
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        out = np.empty((len(xs), 3), np.float64)
+        valid = np.empty(len(xs), np.uint8)
+        self._check(self._L.dp_calc_coordinates(self._h, _ptr(xs), _ptr(ys), len(xs), _ptr(depth), depth.shape[0], depth.shape[1],
+                                                _ptr(K), _ptr(out), _ptr(valid), DP_HOST, self._stream(stream)))
+        return out, valid.astype(bool)
+
+    def align_to_surface(self, query, target, normals=None, offset=0.1, stream=None):
+        """Exact nearest target point of every query point (first three columns), float64.
+        Returns (offset_points | None, aligned_points, idx)."""
+        q = np.ascontiguousarray(query, dtype=np.float64)
+        if q.ndim != 2 or q.shape[1] < 3:
+            raise ValueError("query must be [n, >=3]")
+        t = np.ascontiguousarray(target, dtype=np.float64).reshape(-1, 3)
+        nr = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64).reshape(-1, 3)
+        if nr is not None and len(nr) != len(t):
+            raise ValueError("normals and target points differ in length")
+        n = len(q)
+        offs = np.empty((n, 3), np.float64) if nr is not None else None
+        ali = np.empty((n, 3), np.float64)
+        idx = np.empty(n, np.int32)
+        self._check(self._L.dp_align_to_surface(self._h, _ptr(q), q.shape[1], n, _ptr(t), _ptr(nr), len(t), float(offset),
+                                                _ptr(offs), _ptr(ali), _ptr(idx), DP_HOST, self._stream(stream)))
+        return offs, ali, idx
+
     # ------------------------------------------------------------------ H6 / H7
     def accum_reset(self, stream=None):
         self._check(self._L.dp_accum_reset(self._h, self._stream(stream)))

@@ -35,7 +35,8 @@ from .core import Context
 
 __all__ = ["heatmap_to_points", "compute_rays", "intersect_rays_with_mesh", "create_intersection_pcd",
            "project_debug_rays", "ray_tracing", "load_extrinsics", "PointCloud", "LineSet", "TriangleMesh",
-           "last_result", "get_context", "face_intensities"]
+           "last_result", "get_context", "face_intensities",
+           "heatmap_to_point3d", "pcd_from_point3d", "align_to_surface", "calc_coordinates", "depth_projection_heatmap"]
 
 _CTX = None
 _SCENE = {"V": None, "F": None}
@@ -59,12 +60,16 @@ def last_result():
 # light geometry containers (the attributes src/web_vis.py:203-217 reads)
 # ------------------------------------------------------------------------------------------
 class PointCloud:
-    def __init__(self, points=None, colors=None):
+    def __init__(self, points=None, colors=None, normals=None):
         self.points = np.zeros((0, 3)) if points is None else np.asarray(points, dtype=np.float64)
         self.colors = np.zeros((0, 3)) if colors is None else np.asarray(colors, dtype=np.float64)
+        self.normals = np.zeros((0, 3)) if normals is None else np.asarray(normals, dtype=np.float64)
         self.face_ids = None
         self.t_hit = None
         self.pixels = None
+
+    def has_normals(self):
+        return len(self.normals) == len(self.points) and len(self.points) > 0
 
     def transform(self, T):
         """In place, like o3d.geometry.PointCloud.transform (used at run.py:118)."""
@@ -332,3 +337,52 @@ def face_intensities():
     """(hist int32 [nF], fmax float32 [nF], vmax float32 [nV]) accumulated by the last ray_tracing() call:
     what a go.Mesh3d(intensity=..., intensitymode='cell' | 'vertex') needs."""
     return _LAST.get("hist"), _LAST.get("fmax"), _LAST.get("vmax")
+
+
+# ------------------------------------------------------------------------------------------
+# depth-image projection path (:359-492, :613-630) -- SURVEY.md 8f #1
+# ------------------------------------------------------------------------------------------
+def heatmap_to_point3d(heatmap, depth_image, intrinsic, threshold=0.1):
+    """[n,4] float64 rows (x3d, y3d, z3d, intensity) of the pixels with heat/max(heat) > threshold and
+    depth > 0, in the reference's row-major loop order (:376-393); one GPU pass instead of the H x W Python loop.
+    An empty selection gives ``np.array([])`` like the reference."""
+    pts = get_context().depth_backproject(heatmap, depth_image, _K(intrinsic), threshold)
+    return pts if len(pts) else np.array([])
+
+
+def pcd_from_point3d(points_3D):
+    if len(points_3D) == 0:
+        raise ValueError("No valid 3D points found.")
+    return PointCloud(np.asarray(points_3D)[:, :3])
+
+
+def align_to_surface(defect_points, target_pcd, offset=0.1):
+    """(offset_points, aligned_points): nearest target point of every defect point and that point moved along its
+    normal (:441-459).  The target must carry normals (estimating them is Open3D's job, :431-436)."""
+    tp = np.asarray(target_pcd.points, dtype=np.float64)
+    tn = np.asarray(getattr(target_pcd, "normals", np.zeros((0, 3))), dtype=np.float64)
+    if len(tn) != len(tp):
+        raise ValueError("target point cloud has no normals; estimate them before align_to_surface")
+    dp = np.asarray(defect_points, dtype=np.float64)
+    if dp.size == 0:
+        return np.array([]), np.array([])
+    offs, ali, _ = get_context().align_to_surface(dp.reshape(len(dp), -1), tp, tn, offset)
+    return offs, ali
+
+
+def calc_coordinates(depth_image, points, intrinsic):
+    """3-D coordinates of picked pixels (:462-492); pixels with depth 0 are skipped like the reference."""
+    pts = np.asarray(list(points), dtype=np.int64).reshape(-1, 2)
+    if len(pts) == 0:
+        return np.zeros((0,), np.float64)
+    out, valid = get_context().calc_coordinates(pts[:, 0], pts[:, 1], depth_image, _K(intrinsic))
+    for (x, y) in pts[~valid]:
+        logging.info(f"Depth is zero at coordinates x = {x}, y = {y}. Skipping this point.")
+    return np.array(out[valid], dtype=np.float64)
+
+
+def depth_projection_heatmap(depth_image, intrinsic, target, defects):
+    """heatmap -> 3-D points by depth -> snapped to the target surface (:613-630)."""
+    point3d = heatmap_to_point3d(defects, depth_image, intrinsic)
+    offset_points, aligned_points = align_to_surface(point3d, target, offset=0.5)
+    return offset_points, aligned_points, point3d

@@ -145,6 +145,25 @@ DP_API int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64
                       double thr, const double *K, int64_t nK, const double *pose, int accumulate,
                       dp_rays_out *out, int64_t *n_rays, int64_t *n_hits, int mem, void *stream);
 
+/* ---- depth-image projection path (src/defect_projection.py:359-492, :613-649) ---------- */
+/* heatmap_to_point3d (:359-395): intensity = heat/max(heat); pixels with intensity > thr and depth > 0, in
+ * row-major order, back-projected with their depth: points4[i] = ((x-cx)*d/fx, (y-cy)*d/fy, d*0.98, intensity),
+ * all float64.  heat: [H*W] of `dtype`; depth: [Hd*Wd] uint16 (pixels outside the depth image are skipped);
+ * K: 9 HOST doubles; points4: [cap*4]; *n (HOST) = number of selected pixels (the call synchronises). */
+DP_API int dp_depth_backproject(dp_ctx *ctx, const void *heat, int dtype, int H, int W, const uint16_t *depth, int Hd,
+                                int Wd, const double *K, double thr, double *points4, int64_t cap, int64_t *n, int mem,
+                                void *stream);
+/* calc_coordinates (:462-492): picked pixels -> ((x-cx)*d/fx, (y-cy)*d/fy, d); valid[i] = depth > 0 (the
+ * reference skips the others).  xs, ys: [n] int32; out3: [n*3] float64; valid: [n] bytes. */
+DP_API int dp_calc_coordinates(dp_ctx *ctx, const int32_t *xs, const int32_t *ys, int64_t n, const uint16_t *depth, int Hd,
+                               int Wd, const double *K, double *out3, unsigned char *valid, int mem, void *stream);
+/* align_to_surface (:417-460): for every query point (first 3 of `stride` doubles) the nearest target point
+ * (exact, float64, ties to the smaller index; replaces KDTreeFlann.search_knn_vector_3d(p, 1)):
+ * aligned = target[idx], offset_points = target[idx] + normals[idx]*offset.  Any output may be NULL. */
+DP_API int dp_align_to_surface(dp_ctx *ctx, const double *query, int stride, int64_t n, const double *target,
+                               const double *normals, int64_t m, double offset, double *offset_points,
+                               double *aligned_points, int32_t *idx, int mem, void *stream);
+
 /* ---- H6/H7: accumulators (extensions named by north_star) ------------------ */
 DP_API int dp_accum_reset(dp_ctx *ctx, void *stream);
 /* hist: [nF] int32, fmax: [nF] float32, vmax: [nV] float32; any may be NULL */

@@ -285,3 +285,42 @@ def brute_f64_numpy(V, F, rays6, chunk=256):
         tout[s:s + chunk] = tt
         fout[s:s + chunk] = np.where(np.isfinite(tt), j, -1)
     return tout, fout
+
+
+# ------------------------------------------------------------------ depth-image projection path (numpy, float64)
+def heatmap_to_point3d(heat, depth, K, thr=0.1):
+    """Vectorised restatement of src/defect_projection.py:359-395 (same selection, order and arithmetic)."""
+    heat = np.asarray(heat)
+    depth = np.asarray(depth)
+    K = np.asarray(K, np.float64)
+    H, W = heat.shape
+    Hd, Wd = depth.shape
+    maxv = np.max(heat).astype(np.float64) if heat.size else np.float64(1.0)
+    h = min(H, Hd)
+    w = min(W, Wd)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inten = heat[:h, :w].astype(np.float64) / maxv
+    d = depth[:h, :w]
+    ys, xs = np.nonzero((inten > thr) & (d > 0))
+    dd = d[ys, xs].astype(np.float64)
+    x3 = (xs - K[0, 2]) * dd / K[0, 0]
+    y3 = (ys - K[1, 2]) * dd / K[1, 1]
+    return np.stack([x3, y3, dd * 0.98, inten[ys, xs]], axis=1)
+
+
+def nearest_points(query, target):
+    """Exact float64 nearest neighbour, first minimum (smaller index) on ties: stands in for KDTreeFlann (k = 1)."""
+    q = np.asarray(query, np.float64)[:, :3]
+    t = np.asarray(target, np.float64)
+    idx = np.empty(len(q), np.int32)
+    for s in range(0, len(q), 512):
+        d = q[s:s + 512, None, :] - t[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        idx[s:s + 512] = np.argmin(d2, axis=1)
+    return idx
+
+
+def align_to_surface(query, target, normals, offset):
+    idx = nearest_points(query, target)
+    t = np.asarray(target, np.float64)
+    return t[idx] + np.asarray(normals, np.float64)[idx] * offset, t[idx], idx

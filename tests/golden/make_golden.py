@@ -115,6 +115,40 @@ def main():
 
     path = os.path.join(HERE, "reference_path.npz")
     np.savez_compressed(path, **out)
+
+    # ---- D: the depth-image projection path (:359-492, :613-630), file depth_path.npz
+    dep = {}
+    rng = np.random.default_rng(7)
+    Hh, Ww = 60, 80
+    heat = (synth.gaussian_heatmap((Hh, Ww), sigma=11.0) + 0.3 * synth.blob_heatmap((Hh, Ww), seed=5, dtype=np.float64)
+            * (rng.random((Hh, Ww)) < 0.5)) * 3.7                                # max != 1: the /max matters
+    depth = rng.integers(300, 900, (Hh, Ww)).astype(np.uint16)
+    depth[rng.random((Hh, Ww)) < 0.2] = 0                                       # invalid depth pixels
+    Kd = synth.K_matrix(75.3, 76.1, 39.5, 30.25)
+    intr_d = o3d.camera.PinholeCameraIntrinsic(Ww, Hh, Kd[0, 0], Kd[1, 1], Kd[0, 2], Kd[1, 2])
+    dep["d_heat"], dep["d_depth"], dep["d_K"] = heat, depth, Kd
+    for thr, tag in ((0.1, "010"), (0.5, "050")):
+        dep[f"d_point3d_{tag}"] = ref["heatmap_to_point3d"](heat, depth, intr_d, threshold=thr)
+    small_depth = depth[:50, :70]                                               # depth image smaller than the heatmap
+    dep["d_point3d_small"] = ref["heatmap_to_point3d"](heat, small_depth, intr_d, threshold=0.3)
+    picks = [(int(x), int(y)) for x, y in zip(rng.integers(0, Ww, 40), rng.integers(0, Hh, 40))]
+    dep["d_picks"] = np.array(picks, np.int32)
+    dep["d_calc"] = ref["calc_coordinates"](depth, picks, intr_d)
+    # target cloud with normals: the vertices of a small synthetic mesh, normals = normalised radial direction
+    Vt, Ft = synth.param_mesh(30, 20, seed=9)
+    tp = Vt.astype(np.float64) * 2.0 + np.array([0.0, 0.0, 600.0])
+    tn = tp - tp.mean(0)
+    tn /= np.linalg.norm(tn, axis=1, keepdims=True)
+    target = o3d.geometry.PointCloud()
+    target.points = o3d.utility.Vector3dVector(tp)
+    target.normals = o3d.utility.Vector3dVector(tn)
+    dep["d_target_points"], dep["d_target_normals"] = tp, tn
+    offs, ali, p3 = ref["depth_projection_heatmap"](depth, intr_d, target, heat)
+    dep["d_proj_offset"], dep["d_proj_aligned"], dep["d_proj_point3d"] = offs, ali, p3
+    o2, a2 = ref["align_to_surface"](dep["d_point3d_050"], target, offset=0.1)
+    dep["d_align_offset_01"], dep["d_align_aligned_01"] = o2, a2
+    np.savez_compressed(os.path.join(HERE, "depth_path.npz"), **dep)
+    print("wrote depth_path.npz", {k: v.shape for k, v in dep.items()})
     print("wrote", path, {k: v.shape for k, v in out.items()})
     print("g3 counts (720p sigma=50, thr .5/.75):", out["g3_counts"])
 

@@ -138,6 +138,24 @@ class PointCloud:
     def __init__(self):
         self.points = _Vec(np.zeros((0, 3)), np.float64)
         self.colors = _Vec(np.zeros((0, 3)), np.float64)
+        self.normals = _Vec(np.zeros((0, 3)), np.float64)
+
+    def has_normals(self):
+        return len(self.normals) > 0
+
+
+class KDTreeFlann:
+    """search_knn_vector_3d(p, 1) answered by an exact float64 scan (first minimum = smaller index)."""
+
+    def __init__(self, pcd):
+        self._p = np.asarray(pcd.points, dtype=np.float64)
+
+    def search_knn_vector_3d(self, query, knn):
+        assert knn == 1
+        d = self._p - np.asarray(query, dtype=np.float64)[None, :]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        i = int(np.argmin(d2))
+        return 1, [i], [float(d2[i])]
 
 
 class LineSet:
@@ -198,6 +216,8 @@ def _make_open3d():
     geometry.TriangleMesh = TriangleMesh
     geometry.PointCloud = PointCloud
     geometry.LineSet = LineSet
+    geometry.KDTreeFlann = KDTreeFlann
+    geometry.KDTreeSearchParamHybrid = lambda radius=0.0, max_nn=0: None
     utility = types.ModuleType("open3d.utility")
     utility.Vector3dVector = lambda a: _Vec(a, np.float64)
     utility.Vector2iVector = lambda a: _Vec(a, np.int32)

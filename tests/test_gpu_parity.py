@@ -642,3 +642,49 @@ def test_frame_stream_equals_blocking_calls(ctx, orc):
             assert np.array_equal(got[i][k], ref[k], equal_nan=(k in ("t_hit", "point"))), (i, k)
     assert got[3]["n"] == 0
     assert np.array_equal(hist_stream, ctx.accum_get()[0]) and hist_stream.sum() == sum(g["hits"] for g in got.values())
+
+
+# ------------------------------------------------------------------------------------------ depth path (8f #1)
+def test_depth_projection_path_matches_reference(built_lib, orc):
+    """heatmap_to_point3d / calc_coordinates / align_to_surface / depth_projection_heatmap through the drop-in
+    against the outputs of the reference's own functions (tests/golden/depth_path.npz), bit for bit (float64)."""
+    import os
+    from defectproj import defect_projection as dpj
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "depth_path.npz"))
+    K, heat, depth = g["d_K"], g["d_heat"], g["d_depth"]
+    for thr, key in ((0.1, "d_point3d_010"), (0.5, "d_point3d_050")):
+        assert np.array_equal(dpj.heatmap_to_point3d(heat, depth, K, threshold=thr), g[key])
+    assert np.array_equal(dpj.heatmap_to_point3d(heat, depth[:50, :70], K, threshold=0.3), g["d_point3d_small"])
+    assert np.array_equal(dpj.heatmap_to_point3d(heat.astype(np.float32), depth, K, threshold=0.5),
+                          orc.heatmap_to_point3d(heat.astype(np.float32), depth, K, 0.5))
+    assert dpj.heatmap_to_point3d(np.zeros((8, 8)) + 1e-3, np.zeros((8, 8), np.uint16), K).shape == (0,)
+    got = dpj.calc_coordinates(depth, [tuple(p) for p in g["d_picks"]], K)
+    assert np.array_equal(got, g["d_calc"])
+    target = dpj.PointCloud(g["d_target_points"], normals=g["d_target_normals"])
+    offs, ali, p3 = dpj.depth_projection_heatmap(depth, K, target, heat)
+    assert np.array_equal(p3, g["d_proj_point3d"])
+    assert np.array_equal(ali, g["d_proj_aligned"]) and np.array_equal(offs, g["d_proj_offset"])
+    o2, a2 = dpj.align_to_surface(g["d_point3d_050"], target, offset=0.1)
+    assert np.array_equal(o2, g["d_align_offset_01"]) and np.array_equal(a2, g["d_align_aligned_01"])
+    with pytest.raises(ValueError, match="normals"):
+        dpj.align_to_surface(g["d_point3d_050"], dpj.PointCloud(g["d_target_points"]))
+    with pytest.raises(ValueError, match="uint16"):
+        dpj.heatmap_to_point3d(heat, depth.astype(np.float32), K)
+
+
+def test_depth_path_full_size_properties(ctx, orc):
+    """720p heatmap + depth image, 200k-point target cloud: selection == numpy, every nearest neighbour exact."""
+    rng = np.random.default_rng(11)
+    K, H, W = synth.camera_720p()
+    heat = synth.blob_heatmap((H, W), seed=2, dtype=np.float64)
+    depth = rng.integers(400, 900, (H, W)).astype(np.uint16)
+    depth[rng.random((H, W)) < 0.1] = 0
+    pts = ctx.depth_backproject(heat, depth, K, 0.4)
+    ref = orc.heatmap_to_point3d(heat, depth, K, 0.4)
+    assert len(pts) > 50000 and np.array_equal(pts, ref)
+    V, _ = synth.param_mesh(500, 400, seed=1)
+    tp = V.astype(np.float64) * 3.0 + np.array([0.0, 0.0, 650.0])
+    q = pts[:: max(1, len(pts) // 4000)]
+    _, ali, idx = ctx.align_to_surface(q, tp, None, 0.0)
+    ridx = orc.nearest_points(q, tp)
+    assert np.array_equal(idx, ridx) and np.array_equal(ali, tp[ridx])

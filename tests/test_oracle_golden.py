@@ -108,3 +108,21 @@ def test_accumulate_conservation(orc):
         sel = face == f
         assert hist[f] == sel.sum()
         assert fmax[f] == (I[sel].max() if sel.any() else 0.0)
+
+
+# ------------------------------------------------------------------ depth-image projection path (8f #1)
+@pytest.fixture(scope="module")
+def depth_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "depth_path.npz"))
+
+
+def test_depth_path_oracle_vs_reference(orc, depth_golden):
+    g = depth_golden
+    for thr, key in ((0.1, "d_point3d_010"), (0.5, "d_point3d_050")):
+        assert np.array_equal(orc.heatmap_to_point3d(g["d_heat"], g["d_depth"], g["d_K"], thr), g[key])
+    assert np.array_equal(orc.heatmap_to_point3d(g["d_heat"], g["d_depth"][:50, :70], g["d_K"], 0.3), g["d_point3d_small"])
+    offs, ali, idx = orc.align_to_surface(g["d_proj_point3d"], g["d_target_points"], g["d_target_normals"], 0.5)
+    assert np.array_equal(offs, g["d_proj_offset"]) and np.array_equal(ali, g["d_proj_aligned"])
+    offs, ali, _ = orc.align_to_surface(g["d_point3d_050"], g["d_target_points"], g["d_target_normals"], 0.1)
+    assert np.array_equal(offs, g["d_align_offset_01"]) and np.array_equal(ali, g["d_align_aligned_01"])
