@@ -65,7 +65,7 @@ struct dp_ctx {
     DevBuf hist, fmax, vmax;
 
     // per-call scratch
-    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[6], cscratch, counts, fcounts, xf, stats;
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, counts, fcounts, xf, stats, jet;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
     bool stats_on = false;
     int order_parity = 0;
@@ -181,7 +181,7 @@ void dp_destroy(dp_ctx *ctx)
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face,
                       &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
                       &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
-                      &ctx->stats};
+                      &ctx->stats, &ctx->jet};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : ctx->tmp) b.release();
     if (ctx->build_scratch) cudaFree(ctx->build_scratch);
@@ -711,6 +711,137 @@ int dp_align_to_surface(dp_ctx *ctx, const double *query, int stride, int64_t n,
         if (idx) CK(cudaMemcpyAsync(idx, di, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_align_to_surface: D2H");
         CK(cudaStreamSynchronize(s), "dp_align_to_surface: kernels");
     }
+    return DP_OK;
+}
+
+int dp_prepare_heatmap(dp_ctx *ctx, const void *data, int dtype, int src_h, int src_w, int H, int W, void *out, int out_dtype,
+                       int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (src_h <= 0 || src_w <= 0 || H < 0 || W < 0 || !data || (dtype != DP_F32 && dtype != DP_F64) ||
+        (out_dtype != DP_F32 && out_dtype != DP_F64) || ((int64_t)H * W > 0 && !out))
+        return fail(ctx, DP_E_ARG, "dp_prepare_heatmap: bad arguments");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t isz = dtype == DP_F64 ? 8 : 4, osz = out_dtype == DP_F64 ? 8 : 4;
+    const int64_t ns = (int64_t)src_h * src_w, no = (int64_t)H * W;
+    const void *d_in = data;
+    void *d_out = out;
+    if (mem == DP_HOST) {
+        CK(ctx->tmp[0].ensure((size_t)ns * isz + 16), "dp_prepare_heatmap: in");
+        CK(ctx->tmp[1].ensure((size_t)no * osz + 16), "dp_prepare_heatmap: out");
+        CK(cudaMemcpyAsync(ctx->tmp[0].p, data, (size_t)ns * isz, cudaMemcpyHostToDevice, s), "dp_prepare_heatmap: H2D");
+        d_in = ctx->tmp[0].p;
+        d_out = ctx->tmp[1].p;
+    }
+    CK(ctx->tmp[2].ensure(64), "dp_prepare_heatmap: scalars");
+    CK(launch_prepare_heatmap(d_in, dtype, src_h, src_w, H, W, d_out, out_dtype, ctx->tmp[2].as<long long>(), s),
+       "dp_prepare_heatmap: launch");
+    if (mem == DP_HOST) {
+        if (no) CK(cudaMemcpyAsync(out, d_out, (size_t)no * osz, cudaMemcpyDeviceToHost, s), "dp_prepare_heatmap: D2H");
+        CK(cudaStreamSynchronize(s), "dp_prepare_heatmap: kernels");
+    }
+    return DP_OK;
+}
+
+int dp_transform_points(dp_ctx *ctx, double *points3, int64_t n, const double *T, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || !T || (n > 0 && !points3)) return fail(ctx, DP_E_ARG, "dp_transform_points: bad arguments");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double *d = points3;
+    if (mem == DP_HOST) {
+        CK(ctx->tmp[0].ensure((size_t)n * 24 + 16), "dp_transform_points: buffer");
+        CK(cudaMemcpyAsync(ctx->tmp[0].p, points3, (size_t)n * 24, cudaMemcpyHostToDevice, s), "dp_transform_points: H2D");
+        d = ctx->tmp[0].as<double>();
+    }
+    CK(launch_transform_points(d, n, T, s), "dp_transform_points: launch");
+    if (mem == DP_HOST) {
+        CK(cudaMemcpyAsync(points3, d, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_transform_points: D2H");
+        CK(cudaStreamSynchronize(s), "dp_transform_points: kernels");
+    }
+    return DP_OK;
+}
+
+void dp_jet_lut(double *lut)
+{
+    if (lut) jet_lut_host(lut);
+}
+
+int dp_pack_hits(dp_ctx *ctx, const void *intensity, int dtype, const int32_t *face, const uint32_t *pixel, const double *point64,
+                 int64_t n, const double *T, double *points, double *colors, int32_t *face_out, uint32_t *pixel_out,
+                 double *intensity_out, int64_t cap, int64_t *m, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || cap < 0 || !m || (dtype != DP_F32 && dtype != DP_F64) || (n > 0 && !intensity) || (points && !point64))
+        return fail(ctx, DP_E_ARG, "dp_pack_hits: bad arguments");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!ctx->jet.p) {
+        double lut[768];
+        jet_lut_host(lut);
+        CK(ctx->jet.ensure(sizeof(lut)), "dp_pack_hits: colour table");
+        CK(cudaMemcpy(ctx->jet.p, lut, sizeof(lut), cudaMemcpyHostToDevice), "dp_pack_hits: colour table");
+    }
+    const size_t isz = dtype == DP_F64 ? 8 : 4;
+    const void *d_in = intensity;
+    const int32_t *d_face = face;
+    const uint32_t *d_pix = pixel;
+    const double *d_p64 = point64;
+    double *d_pts = points, *d_col = colors, *d_io = intensity_out;
+    int32_t *d_fo = face_out;
+    uint32_t *d_po = pixel_out;
+    if (mem == DP_HOST) {
+        // inputs: tmp[0] intensity | tmp[1] face + pixel | tmp[3] point64 ; outputs: tmp[4] points | tmp[5] colours |
+        // tmp[6] face_out + pixel_out | tmp[7] intensity_out
+        CK(ctx->tmp[0].ensure((size_t)n * isz + 16), "dp_pack_hits: in");
+        CK(ctx->tmp[1].ensure((size_t)n * 8 + 16), "dp_pack_hits: in");
+        if (n) CK(cudaMemcpyAsync(ctx->tmp[0].p, intensity, (size_t)n * isz, cudaMemcpyHostToDevice, s), "dp_pack_hits: H2D");
+        d_in = ctx->tmp[0].p;
+        if (face) {
+            if (n) CK(cudaMemcpyAsync(ctx->tmp[1].p, face, (size_t)n * 4, cudaMemcpyHostToDevice, s), "dp_pack_hits: H2D");
+            d_face = ctx->tmp[1].as<int32_t>();
+        }
+        if (pixel) {
+            if (n) CK(cudaMemcpyAsync(ctx->tmp[1].as<int32_t>() + n, pixel, (size_t)n * 4, cudaMemcpyHostToDevice, s), "dp_pack_hits: H2D");
+            d_pix = ctx->tmp[1].as<uint32_t>() + n;
+        }
+        if (point64) {
+            CK(ctx->tmp[3].ensure((size_t)n * 24 + 16), "dp_pack_hits: in");
+            if (n) CK(cudaMemcpyAsync(ctx->tmp[3].p, point64, (size_t)n * 24, cudaMemcpyHostToDevice, s), "dp_pack_hits: H2D");
+            d_p64 = ctx->tmp[3].as<double>();
+        }
+        if (points) { CK(ctx->tmp[4].ensure((size_t)cap * 24 + 16), "dp_pack_hits: out"); d_pts = ctx->tmp[4].as<double>(); }
+        if (colors) { CK(ctx->tmp[5].ensure((size_t)cap * 24 + 16), "dp_pack_hits: out"); d_col = ctx->tmp[5].as<double>(); }
+        if (face_out || pixel_out) {
+            CK(ctx->tmp[6].ensure((size_t)cap * 8 + 16), "dp_pack_hits: out");
+            if (face_out) d_fo = ctx->tmp[6].as<int32_t>();
+            if (pixel_out) d_po = ctx->tmp[6].as<uint32_t>() + cap;
+        }
+        if (intensity_out) { CK(ctx->tmp[7].ensure((size_t)cap * 8 + 16), "dp_pack_hits: out"); d_io = ctx->tmp[7].as<double>(); }
+    }
+    CK(ctx->cscratch.ensure(pack_scratch_bytes(n) + 64), "dp_pack_hits: scratch");
+    CK(ctx->tmp[2].ensure(64), "dp_pack_hits: scalars");
+    long long *d_counts = ctx->counts.as<long long>();
+    CK(launch_pack_hits(d_in, dtype, d_face, d_pix, d_p64, n, T, ctx->jet.as<double>(), ctx->tmp[2].as<long long>(), d_pts, d_col,
+                        d_fo, d_po, d_io, cap, ctx->cscratch.as<unsigned long long>(), d_counts, s),
+       "dp_pack_hits: launch");
+    CK(cudaMemcpyAsync(ctx->h_counts, d_counts, 8, cudaMemcpyDeviceToHost, s), "dp_pack_hits: count");
+    CK(cudaStreamSynchronize(s), "dp_pack_hits: kernels");
+    const int64_t total = ctx->h_counts[0];
+    *m = total;
+    const int64_t nc = total < cap ? total : cap;
+    if (mem == DP_HOST && nc > 0) {
+        if (points) CK(cudaMemcpyAsync(points, d_pts, (size_t)nc * 24, cudaMemcpyDeviceToHost, s), "dp_pack_hits: D2H");
+        if (colors) CK(cudaMemcpyAsync(colors, d_col, (size_t)nc * 24, cudaMemcpyDeviceToHost, s), "dp_pack_hits: D2H");
+        if (face_out) CK(cudaMemcpyAsync(face_out, d_fo, (size_t)nc * 4, cudaMemcpyDeviceToHost, s), "dp_pack_hits: D2H");
+        if (pixel_out) CK(cudaMemcpyAsync(pixel_out, d_po, (size_t)nc * 4, cudaMemcpyDeviceToHost, s), "dp_pack_hits: D2H");
+        if (intensity_out) CK(cudaMemcpyAsync(intensity_out, d_io, (size_t)nc * 8, cudaMemcpyDeviceToHost, s), "dp_pack_hits: D2H");
+        CK(cudaStreamSynchronize(s), "dp_pack_hits: D2H");
+    }
+    if (total > cap) return fail(ctx, DP_E_NOMEM, "dp_pack_hits: capacity too small for the selected rays");
     return DP_OK;
 }
 

@@ -99,6 +99,18 @@ cudaError_t launch_calc_coordinates(const int32_t *xs, const int32_t *ys, int64_
 cudaError_t launch_nearest(const double *q, int stride, int64_t n, const double *target, int64_t m, const double *normals,
                            double offset, int32_t *idx, double *aligned, double *offset_pts, cudaStream_t s);
 
+// ---- prep.cu -------------------------------------------------------------------------------
+// mm: 4 device long longs (ordered max, ordered min, NaN flag, count)
+void jet_lut_host(double *lut768);
+cudaError_t launch_prepare_heatmap(const void *data, int dtype, int sh, int sw, int H, int W, void *out, int out_dtype,
+                                   long long *mm, cudaStream_t s);
+cudaError_t launch_transform_points(double *p, int64_t n, const double *T_host, cudaStream_t s);
+size_t pack_scratch_bytes(int64_t n);
+cudaError_t launch_pack_hits(const void *inten, int dtype, const int32_t *face, const uint32_t *pixel, const double *point64,
+                             int64_t n, const double *T_host, const double *lut, long long *mm, double *points, double *colors,
+                             int32_t *face_out, uint32_t *pixel_out, double *inten_out, int64_t cap,
+                             unsigned long long *scratch, long long *d_count, cudaStream_t s);
+
 // ---- build.cu ------------------------------------------------------------------------------
 struct BuildScratch;   // opaque, owned by the context
 

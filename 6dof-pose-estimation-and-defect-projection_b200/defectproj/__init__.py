@@ -3,6 +3,8 @@ ziadabohalawa/6DoF-Pose-Estimation-and-Defect-Projection, src/defect_projection.
 
     from defectproj import defect_projection as dp      # the reference's call surface
     from defectproj import Context, Projector            # the batched / multi-GPU surface
+    from defectproj import datareader, web_vis, tracking # the steps either side of the path (get_heatmap,
+                                                         # update_dash_data, the run.py detection loop)
 
 All computation runs in libdefectproj.so (hand-written sm_100a CUDA behind a C ABI,
 include/defectproj.h).  There is no CPU fallback.

@@ -344,6 +344,96 @@ class Context:
                                                 _ptr(offs), _ptr(ali), _ptr(idx), DP_HOST, self._stream(stream)))
         return offs, ali, idx
 
+    # ------------------------------------------------------------------ before / after the path (8f #3, #2)
+    def prepare_heatmap(self, data, H, W, out_dtype=np.float64, stream=None):
+        """DataReader.get_heatmap's array work (datareader.py:658-674) on the GPU: min-max normalise, cv2-exact
+        INTER_LINEAR resize to min(H, W)^2, centred in a zero [H, W] frame.  `data` may be a CUDA tensor, in which
+        case a CUDA tensor is returned (ready for project_device)."""
+        if _is_torch(data):
+            import torch
+            if data.dtype not in (torch.float32, torch.float64) or data.dim() != 2 or not data.is_contiguous():
+                raise ValueError("device heatmap data must be a contiguous 2-D float32/float64 tensor")
+            odt = torch.float64 if np.dtype(out_dtype) == np.float64 else torch.float32
+            out = torch.empty((int(H), int(W)), dtype=odt, device=data.device)
+            if stream is None:
+                stream = torch.cuda.current_stream(data.device)
+            self._check(self._L.dp_prepare_heatmap(self._h, _ptr(data), DP_F64 if data.dtype == torch.float64 else DP_F32,
+                                                   data.shape[0], data.shape[1], int(H), int(W), _ptr(out),
+                                                   DP_F64 if odt == torch.float64 else DP_F32, DP_DEVICE, self._stream(stream)))
+            return out
+        data = np.asarray(data)
+        if data.ndim != 2 or data.size == 0:
+            raise ValueError("heatmap data must be a non-empty 2-D array")
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        data = np.ascontiguousarray(data)
+        out_dtype = np.dtype(out_dtype)
+        if out_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("out_dtype must be float32 or float64")
+        out = np.empty((int(H), int(W)), out_dtype)
+        self._check(self._L.dp_prepare_heatmap(self._h, _ptr(data), DP_F64 if data.dtype == np.float64 else DP_F32,
+                                               data.shape[0], data.shape[1], int(H), int(W), _ptr(out),
+                                               DP_F64 if out_dtype == np.float64 else DP_F32, DP_HOST, self._stream(stream)))
+        return out
+
+    def transform_points(self, points, T, stream=None):
+        """PointCloud.transform on the GPU (float64); returns a new [n,3] array (a CUDA tensor is transformed in place)."""
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        if _is_torch(points):
+            import torch
+            if points.dtype != torch.float64 or not points.is_contiguous():
+                raise ValueError("device points must be a contiguous float64 tensor")
+            if stream is None:
+                stream = torch.cuda.current_stream(points.device)
+            self._check(self._L.dp_transform_points(self._h, _ptr(points), points.numel() // 3, _ptr(T), DP_DEVICE,
+                                                    self._stream(stream)))
+            return points
+        p = np.array(points, dtype=np.float64, order="C").reshape(-1, 3)
+        self._check(self._L.dp_transform_points(self._h, _ptr(p), len(p), _ptr(T), DP_HOST, self._stream(stream)))
+        return p
+
+    def jet_lut(self):
+        lut = np.empty((256, 3), np.float64)
+        self._L.dp_jet_lut(_ptr(lut))
+        return lut
+
+    def pack_hits(self, intensity, face=None, pixel=None, point64=None, T=None,
+                  want=("points", "colors", "face", "pixel", "intensity"), stream=None):
+        """The viewer payload of one projection: the rays that hit (face >= 0; all when face is None) in ray order,
+        their jet colours (create_intersection_pcd, :286-291) and their points moved by T (run.py:118)."""
+        I = np.asarray(intensity)
+        if I.dtype not in (np.float32, np.float64):
+            I = I.astype(np.float64)
+        I = np.ascontiguousarray(I).reshape(-1)
+        n = len(I)
+        face = None if face is None else np.ascontiguousarray(face, dtype=np.int32).reshape(-1)
+        pixel = None if pixel is None else np.ascontiguousarray(pixel, dtype=np.uint32).reshape(-1)
+        p64 = None if point64 is None else np.ascontiguousarray(point64, dtype=np.float64).reshape(-1, 3)
+        for a in (face, pixel, p64):
+            if a is not None and len(a) != n:
+                raise ValueError("per-ray arrays differ in length")
+        Tm = None if T is None else np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        cap = n
+        out = {}
+        if "points" in want and p64 is not None:
+            out["points"] = np.empty((cap, 3), np.float64)
+        if "colors" in want:
+            out["colors"] = np.empty((cap, 3), np.float64)
+        if "face" in want and face is not None:
+            out["face"] = np.empty(cap, np.int32)
+        if "pixel" in want:
+            out["pixel"] = np.empty(cap, np.uint32)
+        if "intensity" in want:
+            out["intensity"] = np.empty(cap, np.float64)
+        m = C.c_int64(0)
+        self._check(self._L.dp_pack_hits(self._h, _ptr(I), DP_F64 if I.dtype == np.float64 else DP_F32, _ptr(face), _ptr(pixel),
+                                         _ptr(p64), n, _ptr(Tm), _ptr(out.get("points")), _ptr(out.get("colors")),
+                                         _ptr(out.get("face")), _ptr(out.get("pixel")), _ptr(out.get("intensity")), cap,
+                                         C.byref(m), DP_HOST, self._stream(stream)))
+        out = {k: v[:m.value] for k, v in out.items()}
+        out["m"] = m.value
+        return out
+
     # ------------------------------------------------------------------ H6 / H7
     def accum_reset(self, stream=None):
         self._check(self._L.dp_accum_reset(self._h, self._stream(stream)))

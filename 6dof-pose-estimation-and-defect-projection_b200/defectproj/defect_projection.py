@@ -73,8 +73,8 @@ class PointCloud:
 
     def transform(self, T):
         """In place, like o3d.geometry.PointCloud.transform (used at run.py:118)."""
-        T = np.asarray(T, dtype=np.float64)
-        self.points = self.points @ T[:3, :3].T + T[:3, 3]
+        if len(self.points):
+            self.points = get_context().transform_points(self.points, T)
         return self
 
     def __len__(self):
@@ -204,62 +204,17 @@ def intersect_rays_with_mesh(mesh, rays, origin, intensities, _return_ids=False)
 
 
 # ------------------------------------------------------------------------------------------
-# H5  colour packaging (matplotlib's 'jet', 256 entries, restated without matplotlib)
+# H5  colour packaging: matplotlib's 256-entry 'jet' looked up on the GPU (csrc/prep.cu k_pack_hits)
 # ------------------------------------------------------------------------------------------
-_JET_SEGMENTS = {
-    0: ((0.00, 0.0), (0.35, 0.0), (0.66, 1.0), (0.89, 1.0), (1.00, 0.5)),                       # red
-    1: ((0.000, 0.0), (0.125, 0.0), (0.375, 1.0), (0.640, 1.0), (0.910, 0.0), (1.000, 0.0)),   # green
-    2: ((0.00, 0.5), (0.11, 1.0), (0.34, 1.0), (0.65, 0.0), (1.00, 0.0)),                       # blue
-}
-_JET_N = 256
-_JET_LUT = None
-
-
-def _jet_lut():
-    global _JET_LUT
-    if _JET_LUT is None:
-        lut = np.empty((_JET_N, 3), np.float64)
-        grid = np.linspace(0, _JET_N - 1, _JET_N)
-        for ch, seg in _JET_SEGMENTS.items():
-            xk = np.array([p[0] for p in seg]) * (_JET_N - 1)
-            yk = np.array([p[1] for p in seg])
-            col = np.empty(_JET_N)
-            col[0], col[-1] = yk[0], yk[-1]
-            j = np.searchsorted(xk, grid[1:-1])
-            w = (grid[1:-1] - xk[j - 1]) / (xk[j] - xk[j - 1])
-            col[1:-1] = w * (yk[j] - yk[j - 1]) + yk[j - 1]
-            lut[:, ch] = np.clip(col, 0.0, 1.0)
-        _JET_LUT = lut
-    return _JET_LUT
-
-
-def _jet(x):
-    """RGB of matplotlib.cm.get_cmap('jet')(x) for x in [0, 1]; NaN -> (0, 0, 0) ('bad' colour)."""
-    x = np.asarray(x, dtype=np.float64)
-    bad = np.isnan(x)
-    with np.errstate(invalid="ignore"):
-        k = x * _JET_N
-        k = np.where(k == _JET_N, _JET_N - 1, k)
-        k = np.clip(np.where(bad, 0, k), 0, _JET_N - 1).astype(np.int64)   # below 0 / above N map to the end colours
-    rgb = _jet_lut()[k]
-    rgb[bad] = 0.0
-    return rgb
-
-
 def create_intersection_pcd(intersections, intensities):
     """Coloured hit cloud: jet((I - min) / (max - min)) (:286-291).  All-equal intensities give the
     colour-map's 'bad' colour (0,0,0), which is what the reference's 0/0 produces, without the warning."""
     intersections = np.asarray(intersections, dtype=np.float64).reshape(-1, 3)
-    intensities = np.asarray(intensities, dtype=np.float64)
+    intensities = np.asarray(intensities)
     pcd = PointCloud(intersections)
     if len(intensities) == 0:
         return pcd
-    lo, hi = np.min(intensities), np.max(intensities)
-    if hi > lo:
-        normalized = (intensities - lo) / (hi - lo)
-    else:
-        normalized = np.full(intensities.shape, np.nan)
-    pcd.colors = _jet(normalized)
+    pcd.colors = get_context().pack_hits(intensities, want=("colors",))["colors"]
     return pcd
 
 
@@ -321,10 +276,12 @@ def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_thresh
     _LAST.update(pixel=pix, intensity=inten, t_hit=res["t_hit"], face=res["face"], hist=hist, fmax=fmax, vmax=vmax,
                  n_rays=res["n"], n_hits=res["hits"])
     if res["hits"] > 0:
-        pcd = create_intersection_pcd(res["point64"][valid], inten[valid])
-        pcd.face_ids = res["face"][valid]
+        # selection of the hits + colours in one GPU pass (replaces the boolean indexing of :259-264 and :286-291)
+        pk = ctx.pack_hits(inten, res["face"], res["pixel"], res["point64"], want=("points", "colors", "face", "pixel"))
+        pcd = PointCloud(pk["points"], pk["colors"])
+        pcd.face_ids = pk["face"]
         pcd.t_hit = res["t_hit"][valid]
-        pcd.pixels = pix[valid]
+        pcd.pixels = pk["pixel"].astype(np.int64)
         return pcd, mesh_copy
     # miss-all: the reference draws the rays (:561-563)
     W = heat.shape[1]

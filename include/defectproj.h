@@ -164,6 +164,31 @@ DP_API int dp_align_to_surface(dp_ctx *ctx, const double *query, int stride, int
                                const double *normals, int64_t m, double offset, double *offset_points,
                                double *aligned_points, int32_t *idx, int mem, void *stream);
 
+/* ---- before the path: heatmap preparation (datareader.py:639-675) ---------------------- */
+/* DataReader.get_heatmap: data [src_h*src_w] of `dtype` is min-max normalised ((d - min) / max(d - min), in the
+ * array's own type), resized to o x o with o = min(H, W) exactly as cv2.resize(..., INTER_LINEAR) of the
+ * opencv-python wheel computes it for CV_32F / CV_64F, and centred in a zero H x W frame (`heatmap_full`).
+ * out: [H*W] of `out_dtype` (the reference returns float64; DP_F32 stores the float32 rounding for dp_project). */
+DP_API int dp_prepare_heatmap(dp_ctx *ctx, const void *data, int dtype, int src_h, int src_w, int H, int W, void *out,
+                              int out_dtype, int mem, void *stream);
+
+/* ---- after the path: viewer payload (src/defect_projection.py:259-294, src/web_vis.py:203-217) */
+/* PointCloud.transform (run.py:118, :196-200) in place: p' = (T*[p,1])[:3] / w, float64,
+ * ((T0*x + T1*y) + T2*z) + T3 per row.  points3: [n*3]; T: 16 HOST doubles, row-major. */
+DP_API int dp_transform_points(dp_ctx *ctx, double *points3, int64_t n, const double *T, int mem, void *stream);
+/* Selection of the rays that hit (face[i] >= 0; face == NULL selects all), in ray order, with the colours of
+ * create_intersection_pcd (:286-291): jet((I - min) / (max - min))[:, :3] over the SELECTED intensities
+ * (matplotlib's 256-entry 'jet' table; max == min gives (0,0,0), the table's NaN colour) and, when T != NULL,
+ * the rigid transform above applied to the hit points.  intensity: [n] of `dtype`; pixel, point64: per-ray
+ * arrays as dp_rays_out (may be NULL).  Outputs [cap] / [cap*3], any may be NULL.  *m (HOST) = number selected
+ * (the call synchronises). */
+DP_API int dp_pack_hits(dp_ctx *ctx, const void *intensity, int dtype, const int32_t *face, const uint32_t *pixel,
+                        const double *point64, int64_t n, const double *T, double *points, double *colors,
+                        int32_t *face_out, uint32_t *pixel_out, double *intensity_out, int64_t cap, int64_t *m, int mem,
+                        void *stream);
+/* the colour table used above: lut [256*3] float64 RGB (host helper, no device work) */
+DP_API void dp_jet_lut(double *lut);
+
 /* ---- H6/H7: accumulators (extensions named by north_star) ------------------ */
 DP_API int dp_accum_reset(dp_ctx *ctx, void *stream);
 /* hist: [nF] int32, fmax: [nF] float32, vmax: [nV] float32; any may be NULL */

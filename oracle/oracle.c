@@ -709,3 +709,68 @@ ORC_API int orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* DataReader.get_heatmap  (datareader.py:639-675)  -- SURVEY.md 8f #3         */
+/*   heatmap = data - np.min(data); heatmap = heatmap / np.max(heatmap)  :658   */
+/*   vis = cv2.resize(heatmap, (o, o), INTER_LINEAR), o = min(H, W)       :664  */
+/*   full = zeros(H, W); full[y0:y0+o, x0:x0+o] = vis                     :669  */
+/* cv2 (opencv-python 4.13 wheel, IPP) is a third-party dependency; its         */
+/* CV_32F / CV_64F linear resize was pinned against the real cv2 in the build   */
+/* container (tests/golden/make_golden.py section E):                           */
+/*   v = fma(j + .5, src/dst, -.5) [double]; s = floor(v); f = v - s;           */
+/*   s < 0 -> s = 0, f = 0;  s >= src-1 -> s = src-1, f = 0;  f cast to T       */
+/*   row = fma(n[s+1] - n[s], fx, n[s]);  out = fma(row1 - row0, fy, row0)      */
+/* ------------------------------------------------------------------------- */
+static void lin_coef(int64_t j, int64_t src, int64_t dst, int64_t *s0, int64_t *s1, double *f)
+{
+    double scale = (double)src / (double)dst;
+    double v = fma((double)j + 0.5, scale, -0.5);
+    double fl = floor(v);
+    double fr = v - fl;
+    int64_t s = (int64_t)fl;
+    if (s < 0) { s = 0; fr = 0.0; }
+    if (s >= src - 1) { s = src - 1; fr = 0.0; }
+    *s0 = s;
+    *s1 = s + 1 < src ? s + 1 : src - 1;
+    *f = fr;
+}
+
+#define ORC_PREPARE(NAME, T, FMA)                                                                          \
+    ORC_API void NAME(const T *data, int64_t sh, int64_t sw, int64_t H, int64_t W, double *out)            \
+    {                                                                                                      \
+        T mn = data[0], mx = data[0];                                                                      \
+        int nan = 0;                                                                                       \
+        for (int64_t i = 0; i < sh * sw; ++i) {                                                            \
+            T v = data[i];                                                                                 \
+            if (v != v) nan = 1;                                                                           \
+            if (v < mn) mn = v;                                                                            \
+            if (v > mx) mx = v;                                                                            \
+        }                                                                                                  \
+        if (nan) { mn = (T)NAN; mx = (T)NAN; }                                                             \
+        T range = (T)(mx - mn);                                                                            \
+        int64_t o = H < W ? H : W, y0 = (H - o) / 2, x0 = (W - o) / 2;                                      \
+        for (int64_t e = 0; e < H * W; ++e) out[e] = 0.0;                                                  \
+        T *row = (T *)malloc(sizeof(T) * (size_t)(sh * (o > 0 ? o : 1)));                                  \
+        for (int64_t y = 0; y < sh; ++y)                                                                   \
+            for (int64_t j = 0; j < o; ++j) {                                                              \
+                int64_t s0, s1; double fd;                                                                 \
+                lin_coef(j, sw, o, &s0, &s1, &fd);                                                         \
+                T f = (T)fd;                                                                               \
+                T a = (T)((T)(data[y * sw + s0] - mn) / range), b = (T)((T)(data[y * sw + s1] - mn) / range); \
+                row[y * o + j] = FMA((T)(b - a), f, a);                                                    \
+            }                                                                                              \
+        for (int64_t i = 0; i < o; ++i) {                                                                  \
+            int64_t s0, s1; double fd;                                                                     \
+            lin_coef(i, sh, o, &s0, &s1, &fd);                                                             \
+            T f = (T)fd;                                                                                   \
+            for (int64_t j = 0; j < o; ++j) {                                                              \
+                T r0 = row[s0 * o + j], r1 = row[s1 * o + j];                                              \
+                out[(y0 + i) * W + x0 + j] = (double)FMA((T)(r1 - r0), f, r0);                             \
+            }                                                                                              \
+        }                                                                                                  \
+        free(row);                                                                                         \
+    }
+
+ORC_PREPARE(orc_prepare_heatmap_f64, double, fma)
+ORC_PREPARE(orc_prepare_heatmap_f32, float, fmaf)

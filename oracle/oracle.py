@@ -75,6 +75,10 @@ def lib():
         L.orc_project_frame_f32.restype = i64
         L.orc_project_frame_f32.argtypes = [vp, vp, i64, i64, f32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_num_threads.restype = C.c_int
+        L.orc_prepare_heatmap_f64.argtypes = [vp, i64, i64, i64, i64, vp]
+        L.orc_prepare_heatmap_f64.restype = None
+        L.orc_prepare_heatmap_f32.argtypes = [vp, i64, i64, i64, i64, vp]
+        L.orc_prepare_heatmap_f32.restype = None
         L.orc_num_threads.argtypes = []
         _lib = L
     return _lib
@@ -324,3 +328,77 @@ def align_to_surface(query, target, normals, offset):
     idx = nearest_points(query, target)
     t = np.asarray(target, np.float64)
     return t[idx] + np.asarray(normals, np.float64)[idx] * offset, t[idx], idx
+
+
+# ------------------------------------------------------------------ before / after the path
+def prepare_heatmap(data, H, W):
+    """DataReader.get_heatmap (datareader.py:639-675): min-max normalise, cv2 INTER_LINEAR resize to min(H, W)^2,
+    centre in a zero H x W float64 frame.  The resize is the C restatement pinned against the real cv2."""
+    data = np.asarray(data)
+    dt = np.float32 if data.dtype == np.float32 else np.float64
+    d = np.ascontiguousarray(data, dtype=dt)
+    out = np.empty((H, W), np.float64)
+    fn = lib().orc_prepare_heatmap_f32 if dt == np.float32 else lib().orc_prepare_heatmap_f64
+    fn(_p(d), d.shape[0], d.shape[1], H, W, _p(out))
+    return out
+
+
+_JET_SEG = {
+    0: ((0.00, 0, 0), (0.35, 0, 0), (0.66, 1, 1), (0.89, 1, 1), (1.00, 0.5, 0.5)),
+    1: ((0.000, 0, 0), (0.125, 0, 0), (0.375, 1, 1), (0.640, 1, 1), (0.910, 0, 0), (1.000, 0, 0)),
+    2: ((0.00, 0.5, 0.5), (0.11, 1, 1), (0.34, 1, 1), (0.65, 0, 0), (1.00, 0, 0)),
+}
+
+
+def jet_lut(N=256):
+    """matplotlib.colors._create_lookup_table for the 'jet' segment data (public algorithm; matplotlib is absent)."""
+    lut = np.empty((N, 3), np.float64)
+    for c, data in _JET_SEG.items():
+        a = np.array(data, dtype=np.float64)
+        x, y0, y1 = a[:, 0] * (N - 1), a[:, 1], a[:, 2]
+        xind = np.linspace(0, N - 1, N)
+        ind = np.searchsorted(x, xind)[1:-1]
+        dist = (xind[1:-1] - x[ind - 1]) / (x[ind] - x[ind - 1])
+        lut[:, c] = np.clip(np.concatenate([[y1[0]], dist * (y0[ind] - y1[ind - 1]) + y1[ind - 1], [y0[-1]]]), 0.0, 1.0)
+    return lut
+
+
+def jet(x):
+    """RGB of plt.get_cmap('jet')(x)[:, :3] (Colormap.__call__: x*N, truncation, x == 1 -> N-1, NaN -> (0,0,0))."""
+    x = np.array(x, dtype=np.float64)
+    bad = np.isnan(x)
+    with np.errstate(invalid="ignore"):
+        xa = x * 256
+        xa[xa < 0] = -1
+        xa[xa == 256] = 255
+        xi = np.clip(np.where(bad, 0, xa), -1, 256).astype(int)
+    xi[xi > 255] = 255          # "over" colour = lut[N-1]
+    xi[xi < 0] = 0              # "under" colour = lut[0]
+    rgb = jet_lut()[xi]
+    rgb[bad] = 0.0
+    return rgb
+
+
+def transform_points(p, T):
+    """Open3D PointCloud.transform: (T @ [p, 1])[:3] / w, evaluated left to right in float64."""
+    p = np.asarray(p, np.float64).reshape(-1, 3)
+    T = np.asarray(T, np.float64)
+    h = [((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3] for r in range(4)]
+    return np.stack([h[0] / h[3], h[1] / h[3], h[2] / h[3]], axis=1)
+
+
+def pack_hits(intensity, face=None, point64=None, T=None):
+    """Selection of the hits (:259-264), colours of create_intersection_pcd (:286-291), optional transform (run.py:118)."""
+    I = np.asarray(intensity).astype(np.float64)
+    sel = np.ones(len(I), bool) if face is None else np.asarray(face) >= 0
+    Is = I[sel]
+    out = {"index": np.nonzero(sel)[0], "intensity": Is}
+    if len(Is):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out["colors"] = jet((Is - np.min(Is)) / (np.max(Is) - np.min(Is)))
+    else:
+        out["colors"] = np.zeros((0, 3))
+    if point64 is not None:
+        pts = np.asarray(point64, np.float64).reshape(-1, 3)[sel]
+        out["points"] = transform_points(pts, T) if T is not None else pts
+    return out

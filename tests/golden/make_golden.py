@@ -147,6 +147,34 @@ def main():
     dep["d_proj_offset"], dep["d_proj_aligned"], dep["d_proj_point3d"] = offs, ali, p3
     o2, a2 = ref["align_to_surface"](dep["d_point3d_050"], target, offset=0.1)
     dep["d_align_offset_01"], dep["d_align_aligned_01"] = o2, a2
+    # ---- E: DataReader.get_heatmap (datareader.py:639-675) executed verbatim with the real cv2
+    import ast
+    import textwrap
+    import types as _types
+    import cv2
+    src_dr = open("/root/reference/datareader.py").read()
+    tree = ast.parse(src_dr)
+    fn_src = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "DataReader":
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == "get_heatmap":
+                    fn_src = ast.get_source_segment(src_dr, item)
+    ns2 = {"np": np, "cv2": cv2}
+    exec(textwrap.dedent(fn_src), ns2)
+    for tag, (hs, cH, cW, ds) in {"a": (64, 180, 320, 1), "b": (100, 90, 76, 1), "c": (224, 360, 640, 2),
+                                  "d": (96, 200, 150, 1)}.items():
+        data = (rng.random((hs, hs)) * 5.0 - 1.0) * synth.gaussian_heatmap((hs, hs), sigma=hs / 5.0)
+        if tag == "d":
+            data = data.astype(np.float32)      # a float32 .npy stays float32 through :658-665 (CV_32F resize)
+        with tempfile.TemporaryDirectory() as d:
+            os.makedirs(os.path.join(d, "heatmap"))
+            np.save(os.path.join(d, "heatmap", "0002.npy"), data)
+            fake = _types.SimpleNamespace(base_dir=d, color_H=cH, color_W=cW, downscale=ds)
+            color = (rng.random((cH, cW, 3)) * 255).astype(np.uint8)
+            full, _, vis, _ = ns2["get_heatmap"](fake, color)
+        dep[f"h_data_{tag}"], dep[f"h_full_{tag}"] = data, full
+        dep[f"h_cfg_{tag}"] = np.array([cH, cW, ds], np.int64)
     np.savez_compressed(os.path.join(HERE, "depth_path.npz"), **dep)
     print("wrote depth_path.npz", {k: v.shape for k, v in dep.items()})
     print("wrote", path, {k: v.shape for k, v in out.items()})

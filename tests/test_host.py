@@ -104,12 +104,16 @@ def test_gaussian_heatmap_counts_match_reference_generator(golden):
     assert [(h > 0.5).sum(), (h > 0.75).sum()] == golden["g3_counts"].tolist()
 
 
-def test_jet_packaging_matches_reference(golden):
-    from defectproj import defect_projection as dpj
-    pcd = dpj.create_intersection_pcd(np.zeros((33, 3)), golden["g7_ramp"])
-    assert np.allclose(pcd.colors, golden["g7_colors"], rtol=0, atol=1e-12)
-    const = dpj.create_intersection_pcd(np.zeros((4, 3)), np.full(4, 0.7))
-    assert np.array_equal(const.colors, np.zeros((4, 3)))       # matplotlib's 'bad' colour for 0/0
+def test_jet_table_of_the_library_matches_matplotlibs_construction(built_lib, orc, golden):
+    # dp_jet_lut is a host helper (no device work): the table k_pack_hits looks colours up in
+    import ctypes as C
+    lut = np.empty((256, 3), np.float64)
+    built_lib.dp_jet_lut(lut.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(lut, orc.jet_lut())
+    # ... and the oracle's lookup reproduces what the reference's create_intersection_pcd produced (golden g7)
+    ramp = golden["g7_ramp"]
+    assert np.array_equal(orc.jet((ramp - ramp.min()) / (ramp.max() - ramp.min())), golden["g7_colors"])
+    assert np.array_equal(orc.pack_hits(np.full(4, 0.7))["colors"], np.zeros((4, 3)))   # 0/0 -> 'bad' colour
 
 
 def test_debug_lineset_matches_reference(golden):

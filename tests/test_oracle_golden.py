@@ -126,3 +126,42 @@ def test_depth_path_oracle_vs_reference(orc, depth_golden):
     assert np.array_equal(offs, g["d_proj_offset"]) and np.array_equal(ali, g["d_proj_aligned"])
     offs, ali, _ = orc.align_to_surface(g["d_point3d_050"], g["d_target_points"], g["d_target_normals"], 0.1)
     assert np.array_equal(offs, g["d_align_offset_01"]) and np.array_equal(ali, g["d_align_aligned_01"])
+
+
+# ------------------------------------------------------------------ heatmap preparation (8f #3)
+def test_prepare_heatmap_oracle_vs_reference_get_heatmap(orc, depth_golden):
+    """h_full_* were produced by the reference's DataReader.get_heatmap run verbatim with the real cv2."""
+    g = depth_golden
+    for tag in "abcd":
+        cH, cW, ds = (int(v) for v in g[f"h_cfg_{tag}"])
+        out = orc.prepare_heatmap(g[f"h_data_{tag}"], int(cH / ds), int(cW / ds))
+        assert out.dtype == np.float64 and np.array_equal(out, g[f"h_full_{tag}"]), tag
+    assert g["h_data_d"].dtype == np.float32          # the CV_32F path is covered
+
+
+def test_prepare_heatmap_oracle_vs_live_cv2(orc):
+    """Where cv2 is importable the restatement is also checked live (the wheel's IPP path may differ per CPU)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    for dt in (np.float32, np.float64):
+        for sh, sw, H, W in ((50, 70, 120, 200), (224, 224, 720, 1280), (33, 21, 64, 48), (300, 300, 77, 91), (7, 7, 1, 5)):
+            data = (rng.random((sh, sw)) * 3 - 1).astype(dt)
+            h = data - np.min(data)
+            h = h / np.max(h)
+            o = min(H, W)
+            full = np.zeros((H, W))
+            y0, x0 = (H - o) // 2, (W - o) // 2
+            full[y0:y0 + o, x0:x0 + o] = cv2.resize(h, (o, o), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(orc.prepare_heatmap(data, H, W), full), (dt, sh, sw, H, W)
+
+
+def test_transform_points_oracle_is_a_rigid_map(orc):
+    from defectproj import synth
+    rng = np.random.default_rng(2)
+    p = rng.normal(size=(100, 3)) * 50
+    T = np.eye(4)
+    T[:3, :3] = synth.rot_y(0.7) @ synth.rot_x(-0.3)
+    T[:3, 3] = [10.0, -4.0, 500.0]
+    q = orc.transform_points(p, T)
+    assert np.allclose(q, p @ T[:3, :3].T + T[:3, 3], rtol=0, atol=1e-10)
+    assert np.allclose(orc.transform_points(q, np.linalg.inv(T)), p, rtol=0, atol=1e-9)
