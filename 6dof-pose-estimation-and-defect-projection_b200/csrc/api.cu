@@ -253,25 +253,30 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t nf = (size_t)(ctx->nF > 0 ? ctx->nF : 1);
-    // a wide node is rooted at a binary node with > LEAF_MAX triangles; <= nF/2 + 1 of them
-    // can exist in the worst case of a degenerate chain, typically ~nF/5
-    const size_t cap_nodes = nf / 2 + 64;
-    CK(ctx->obj_nodes.ensure(cap_nodes * sizeof(WideNode)), "dp_build_bvh: nodes");
-    CK(ctx->obj_tris.ensure(nf * sizeof(TriRec)), "dp_build_bvh: tris");
-    CK(ctx->obj_wlo.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
-    CK(ctx->obj_whi.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
-    CK(ctx->tri_face.ensure(nf * 4), "dp_build_bvh: tri_face");
-    ctx->obj.nodes = ctx->obj_nodes.as<WideNode>();
-    ctx->obj.tris = ctx->obj_tris.as<TriRec>();
-    ctx->obj.wlo = ctx->obj_wlo.as<float>();
-    ctx->obj.whi = ctx->obj_whi.as<float>();
-    ctx->obj.cap_nodes = (int64_t)cap_nodes;
-    ctx->obj.d_scale = ctx->scales.as<float>();
-    ctx->topo.tri_face = ctx->tri_face.as<int32_t>();
-    ctx->has_bvh = ctx->has_cam = false;
-    CK(cudaEventRecord(ctx->ev[8], s), "dp_build_bvh");
-    cudaError_t e = build_lbvh(ctx->V.as<float>(), ctx->nV, ctx->F.as<int32_t>(), ctx->nF, ctx->obj, ctx->topo,
-                               &ctx->build_scratch, &ctx->build_scratch_bytes, nullptr, s);
+    // a wide node is rooted at an internal binary node: typically ~nF/7 of them, nF/2 when every one is rooted at a
+    // subtree of > LEAF_MAX triangles, never more than nF - 1 (second attempt)
+    cudaError_t e = cudaSuccess;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const size_t cap_nodes = attempt == 0 ? nf / 2 + 64 : nf + 64;
+        CK(ctx->obj_nodes.ensure(cap_nodes * sizeof(WideNode)), "dp_build_bvh: nodes");
+        CK(ctx->obj_tris.ensure(nf * sizeof(TriRec)), "dp_build_bvh: tris");
+        CK(ctx->obj_wlo.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
+        CK(ctx->obj_whi.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
+        CK(ctx->tri_face.ensure(nf * 4), "dp_build_bvh: tri_face");
+        ctx->obj.nodes = ctx->obj_nodes.as<WideNode>();
+        ctx->obj.tris = ctx->obj_tris.as<TriRec>();
+        ctx->obj.wlo = ctx->obj_wlo.as<float>();
+        ctx->obj.whi = ctx->obj_whi.as<float>();
+        ctx->obj.cap_nodes = (int64_t)cap_nodes;
+        ctx->obj.d_scale = ctx->scales.as<float>();
+        ctx->topo.tri_face = ctx->tri_face.as<int32_t>();
+        ctx->has_bvh = ctx->has_cam = false;
+        CK(cudaEventRecord(ctx->ev[8], s), "dp_build_bvh");
+        e = build_lbvh(ctx->V.as<float>(), ctx->nV, ctx->F.as<int32_t>(), ctx->nF, ctx->obj, ctx->topo,
+                       &ctx->build_scratch, &ctx->build_scratch_bytes, nullptr, s);
+        if (e != cudaErrorMemoryAllocation) break;
+        cudaGetLastError();
+    }
     if (e == cudaErrorInvalidValue) return fail(ctx, DP_E_STATE, "dp_build_bvh: hierarchy deeper than 126 levels");
     CK(e, "dp_build_bvh");
     CK(cudaEventRecord(ctx->ev[9], s), "dp_build_bvh");

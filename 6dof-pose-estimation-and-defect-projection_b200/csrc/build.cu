@@ -16,6 +16,7 @@
 #include "dp_internal.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace dp {
 
@@ -262,9 +263,37 @@ __global__ void k_karras(const uint32_t *__restrict__ keys, long long n, int32_t
     last[i] = (int32_t)hi;
 }
 
+// Surface-area cost model of the collapse (Ylitie, Karras, Laine 2017, section 3.1, restated for this node
+// layout): C(n, i) = cheapest way to represent the binary subtree n as at most i children of one wide node.
+//   C(n, 1) = min(C_leaf, C_distribute(n, 8) + A_n * c_node),   C_leaf = A_n * P_n * c_prim  (P_n <= LEAF_MAX)
+//   C(n, i) = min(C_distribute(n, i), C(n, i - 1)),              i = 2..7
+//   C_distribute(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// ctab[n][i-1] holds C(n, i) for the internal nodes; a single triangle costs A * c_prim for every i.
+constexpr float C_NODE = 1.0f;
+
+__device__ __forceinline__ float half_area(const float lo[3], const float hi[3])
+{
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ float distribute_cost(const float cl[7], const float cr[7], int j, int *split)
+{
+    float best = INFINITY;
+    int bk = 1;
+    const int k0 = j - 7 > 1 ? j - 7 : 1, k1 = j - 1 < 7 ? j - 1 : 7;
+    for (int k = k0; k <= k1; ++k) {
+        const float c = cl[k - 1] + cr[j - k - 1];
+        if (c < best) { best = c; bk = k; }
+    }
+    if (split) *split = bk;
+    return best;
+}
+
 __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict__ F, const uint32_t *__restrict__ sorted_tri,
                          long long n, const int32_t *__restrict__ parent, const int32_t *__restrict__ left,
-                         const int32_t *__restrict__ right, float *blo, float *bhi, int *flags)
+                         const int32_t *__restrict__ right, const int32_t *__restrict__ first,
+                         const int32_t *__restrict__ last, float *blo, float *bhi, int *flags, float *ctab, float c_prim)
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -274,17 +303,48 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
 #pragma unroll
     for (int k = 0; k < 3; ++k) { blo[3 * id + k] = lo[k]; bhi[3 * id + k] = hi[k]; }
     if (n == 1) return;
+    float mine[7];                                        // C(id, 1..7) of the subtree this thread carries upwards
+    {
+        const float c = half_area(lo, hi) * c_prim;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) mine[i] = c;
+    }
     long long cur = parent[id];
     for (;;) {
         __threadfence();
         if (atomicAdd(&flags[cur], 1) == 0) return;       // the sibling subtree is not done yet
-        const long long sib = (left[cur] == id) ? right[cur] : left[cur];
+        const bool id_is_left = left[cur] == id;
+        const long long sib = id_is_left ? right[cur] : left[cur];
+        float slo[3], shi[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            lo[k] = fminf(lo[k], __ldcg(&blo[3 * sib + k]));
-            hi[k] = fmaxf(hi[k], __ldcg(&bhi[3 * sib + k]));
+            slo[k] = __ldcg(&blo[3 * sib + k]);
+            shi[k] = __ldcg(&bhi[3 * sib + k]);
+            lo[k] = fminf(lo[k], slo[k]);
+            hi[k] = fmaxf(hi[k], shi[k]);
             blo[3 * cur + k] = lo[k];
             bhi[3 * cur + k] = hi[k];
+        }
+        if (ctab) {
+            float other[7];
+            if (sib >= n - 1) {
+                const float c = half_area(slo, shi) * c_prim;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) other[i] = c;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 7; ++i) other[i] = __ldcg(&ctab[8 * sib + i]);
+            }
+            const float *cl = id_is_left ? mine : other, *cr = id_is_left ? other : mine;
+            const float A = half_area(lo, hi);
+            const int P = last[cur] - first[cur] + 1;
+            float C[7];
+            const float c_leaf = P <= LEAF_MAX ? A * (float)P * c_prim : INFINITY;
+            C[0] = fminf(c_leaf, distribute_cost(cl, cr, 8, nullptr) + A * C_NODE);
+#pragma unroll
+            for (int i = 2; i <= 7; ++i) C[i - 1] = fminf(distribute_cost(cl, cr, i, nullptr), C[i - 2]);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { mine[i] = C[i]; ctab[8 * cur + i] = C[i]; }
         }
         if (cur == 0) return;
         id = cur;
@@ -299,11 +359,13 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
                            const int32_t *__restrict__ right, const int32_t *__restrict__ first,
                            const int32_t *__restrict__ last, const float *__restrict__ blo,
                            const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
-                           WideNode *nodes, int32_t *tri_face, unsigned *counters)
+                           WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
+                           float c_prim, int greedy_mode)
 {
     const long long w = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (w >= end) return;
     const int32_t r = wroot[w];
+    unsigned inner_mask = 0;
     auto count = [&](int32_t id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
     auto expandable = [&](int32_t id) -> bool { return id < n - 1 && (last[id] - first[id] + 1) > LEAF_MAX; };
     auto area = [&](int32_t id) -> float {
@@ -311,15 +373,68 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
                     dz = bhi[3ll * id + 2] - blo[3ll * id + 2];
         return dx * dy + dy * dz + dz * dx;
     };
+    auto prio = [&](int32_t id) -> float {
+        if (greedy_mode == 2) return (float)count(id);
+        if (greedy_mode == 3) return area(id) * (float)count(id);
+        if (greedy_mode == 4) return area(id) * sqrtf((float)count(id));
+        return area(id);
+    };
     int32_t cand[8];
     float carea[8];
     int nc;
-    if (!expandable(r)) {
+    if (ctab) {
+        // cost-optimal cut of the binary subtree (tables from k_binfit); `inner` marks the children that become
+        // wide nodes themselves
+        auto cost = [&](int32_t id, int i) -> float {
+            return id < n - 1 ? ctab[8ll * id + (i - 1)] : area(id) * c_prim;
+        };
+        auto load7 = [&](int32_t id, float *c) {
+            for (int i = 1; i <= 7; ++i) c[i - 1] = cost(id, i);
+        };
+        auto is_inner = [&](int32_t id) -> bool {
+            if (id >= n - 1) return false;
+            const int P = last[id] - first[id] + 1;
+            if (P > LEAF_MAX) return true;
+            return !(area(id) * (float)P * c_prim == ctab[8ll * id]);      // C(id,1) came from the internal option
+        };
+        nc = 0;
+        inner_mask = 0;
+        if (r >= n - 1 || (w == 0 && !is_inner(r))) {
+            cand[0] = r; nc = 1;                                            // a whole mesh of <= LEAF_MAX triangles
+        } else {
+            int32_t st_id[16];
+            int st_b[16], sp = 0;
+            st_id[0] = r; st_b[0] = 8; sp = 1;
+            bool force = true;                                              // the root of a wide node always distributes
+            while (sp > 0) {
+                --sp;
+                const int32_t id = st_id[sp];
+                int b = st_b[sp];
+                if (id >= n - 1) { cand[nc++] = id; continue; }
+                float cl[7], cr[7];
+                load7(left[id], cl);
+                load7(right[id], cr);
+                if (!force) {
+                    while (b > 1 && !(distribute_cost(cl, cr, b, nullptr) < cost(id, b - 1))) --b;
+                    if (b == 1) {
+                        if (is_inner(id)) inner_mask |= 1u << nc;
+                        cand[nc++] = id;
+                        continue;
+                    }
+                }
+                force = false;
+                int k;
+                distribute_cost(cl, cr, b, &k);
+                st_id[sp] = right[id]; st_b[sp] = b - k; ++sp;
+                st_id[sp] = left[id]; st_b[sp] = k; ++sp;
+            }
+        }
+    } else if (!expandable(r)) {
         cand[0] = r; carea[0] = -1.0f; nc = 1;
     } else {
         cand[0] = left[r]; cand[1] = right[r];
-        carea[0] = expandable(cand[0]) ? area(cand[0]) : -1.0f;
-        carea[1] = expandable(cand[1]) ? area(cand[1]) : -1.0f;
+        carea[0] = expandable(cand[0]) ? prio(cand[0]) : -1.0f;
+        carea[1] = expandable(cand[1]) ? prio(cand[1]) : -1.0f;
         nc = 2;
         while (nc < 8) {
             int b = -1;
@@ -329,8 +444,8 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
             if (b < 0) break;
             const int32_t id = cand[b];
             const int32_t l = left[id], rr = right[id];
-            cand[b] = l; carea[b] = expandable(l) ? area(l) : -1.0f;
-            cand[nc] = rr; carea[nc] = expandable(rr) ? area(rr) : -1.0f;
+            cand[b] = l; carea[b] = expandable(l) ? prio(l) : -1.0f;
+            cand[nc] = rr; carea[nc] = expandable(rr) ? prio(rr) : -1.0f;
             ++nc;
         }
     }
@@ -364,9 +479,12 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
         slot_of[bci] = bs;
         cand_at[bs] = bci;
     }
+    if (!ctab)
+        for (int c = 0; c < nc; ++c)
+            if (expandable(cand[c])) inner_mask |= 1u << c;
     int n_inner = 0, n_leaf_tris = 0;
     for (int c = 0; c < nc; ++c) {
-        if (expandable(cand[c])) ++n_inner; else n_leaf_tris += count(cand[c]);
+        if ((inner_mask >> c) & 1u) ++n_inner; else n_leaf_tris += count(cand[c]);
     }
     const unsigned cbase = n_inner ? atomicAdd(&counters[0], (unsigned)n_inner) : 0u;
     const unsigned tbase = n_leaf_tris ? atomicAdd(&counters[1], (unsigned)n_leaf_tris) : 0u;
@@ -377,7 +495,7 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
         if (c < 0) continue;
         const int32_t id = cand[c];
         unsigned meta;
-        if (expandable(id)) {
+        if ((inner_mask >> c) & 1u) {
             imask |= 1u << s;
             meta = 0x20u | (24u + (unsigned)s);
             wroot[cbase + k_inner++] = id;
@@ -581,6 +699,21 @@ cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp,
     return cudaGetLastError();   // 4 passes: the result is back in keys / vals
 }
 
+// DP_COLLAPSE=0 selects the greedy largest-area expansion (kept for A/B measurements); DP_CPRIM overrides the
+// triangle/node cost ratio of the surface-area model.
+static int knob_sah_collapse()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DP_COLLAPSE"); v = e ? atoi(e) : 1; }
+    return v;
+}
+static float knob_c_prim()
+{
+    static float v = -1.0f;
+    if (v < 0.0f) { const char *e = getenv("DP_CPRIM"); v = e ? (float)atof(e) : 0.5f; }
+    return v;
+}
+
 cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF, BvhStorage &out, Topology &topo,
                        void **scratch, size_t *scratch_bytes, uint32_t *morton_out_host, cudaStream_t s)
 {
@@ -588,7 +721,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     const long long n = nF;
     const size_t N = (size_t)(n > 0 ? n : 1);
     size_t need = 4096 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
-                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + 1024;
+                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + 1024;
     if ((e = ensure_scratch(scratch, scratch_bytes, need)) != cudaSuccess) return e;
     Bump b{static_cast<char *>(*scratch)};
     unsigned *bounds_u = b.take<unsigned>(8);
@@ -603,6 +736,8 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     float *blo = b.take<float>(2 * N * 3), *bhi = b.take<float>(2 * N * 3);
     int *flags = b.take<int>(N);
     int32_t *wroot = b.take<int32_t>(N);
+    float *ctab = knob_sah_collapse() == 1 ? b.take<float>(8 * N) : nullptr;
+    const float c_prim = knob_c_prim();
 
     out.n_tris = n;
     topo.n_levels = 0;
@@ -641,7 +776,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     if ((e = cudaMemsetAsync(parent, 0xff, 2 * N * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
     if (n > 1) k_karras<<<blocks_for(n - 1, 256), 256, 0, s>>>(keys, n, left, right, parent, first, last);
-    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, blo, bhi, flags);
+    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab, c_prim);
 
     // top-down collapse, one launch per level of the wide tree
     {
@@ -655,7 +790,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     while (begin < end) {
         if (L + 1 >= 127) return cudaErrorInvalidValue;
         k_collapse<<<blocks_for(end - begin, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
-                                                                wroot, out.nodes, topo.tri_face, counters);
+                                                                wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse());
         unsigned cnt[2];
         if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;

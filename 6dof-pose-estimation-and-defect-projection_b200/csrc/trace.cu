@@ -261,6 +261,10 @@ __device__ __forceinline__ long long work_to_slot(long long i, bool tiled, int W
 }
 
 constexpr int TQ_CAP = 64;                      // triangle queue entries per warp (power of two)
+#ifndef DP_TQ_FLUSH
+#define DP_TQ_FLUSH 32
+#endif
+constexpr int TQ_FLUSH = DP_TQ_FLUSH;           // pending (ray, triangle) pairs that trigger a test round
 constexpr unsigned TQ_TRI_MASK = (1u << 27) - 1u;
 constexpr unsigned long long KEY_MISS = (0x7f800000ull << 32) | 0xffffffffull;   // t = +inf, face = -1
 
@@ -400,10 +404,11 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
                 }
                 qcount += __popc(contrib);
                 __syncwarp();
-                if (qcount >= 32) {
-                    tri_batch<STATS>(r, tris, queue, best, qhead, 32, lane, nt);
-                    qhead = (qhead + 32) & (TQ_CAP - 1);
-                    qcount -= 32;
+                if (qcount >= TQ_FLUSH) {
+                    const int c = qcount < 32 ? qcount : 32;
+                    tri_batch<STATS>(r, tris, queue, best, qhead, c, lane, nt);
+                    qhead = (qhead + c) & (TQ_CAP - 1);
+                    qcount -= c;
                 }
             }
         }
