@@ -995,3 +995,149 @@ int dp_debug_morton(dp_ctx *ctx, uint32_t *codes)
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ point-to-plane ICP
+namespace {
+// x = A^-1 b for the symmetric 6 x 6 normal equations (Gaussian elimination, partial pivoting); returns det(A)
+double solve6(double A[6][6], double b[6], double x[6])
+{
+    double det = 1.0;
+    int perm_sign = 1;
+    for (int c = 0; c < 6; ++c) {
+        int p = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+        if (A[p][c] == 0.0) return 0.0;
+        if (p != c) {
+            for (int k = 0; k < 6; ++k) { const double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
+            const double t = b[c]; b[c] = b[p]; b[p] = t;
+            perm_sign = -perm_sign;
+        }
+        det *= A[c][c];
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[r][c] / A[c][c];
+            for (int k = c; k < 6; ++k) A[r][k] -= f * A[c][k];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int r = 5; r >= 0; --r) {
+        double acc = b[r];
+        for (int k = r + 1; k < 6; ++k) acc -= A[r][k] * x[k];
+        x[r] = acc / A[r][r];
+    }
+    return det * perm_sign;
+}
+
+void mat4_mul(const double *A, const double *B, double *C)
+{
+    double T[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += A[4 * r + k] * B[4 * k + c];
+            T[4 * r + c] = acc;
+        }
+    memcpy(C, T, sizeof(T));
+}
+
+// Open3D TransformVector6dToMatrix4d: R = Rz(x2) * Ry(x1) * Rx(x0), t = x3..5
+void se3_from_vector6(const double x[6], double *M)
+{
+    const double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+    const double Rx[16] = {1, 0, 0, 0, 0, ca, -sa, 0, 0, sa, ca, 0, 0, 0, 0, 1};
+    const double Ry[16] = {cb, 0, sb, 0, 0, 1, 0, 0, -sb, 0, cb, 0, 0, 0, 0, 1};
+    const double Rz[16] = {cg, -sg, 0, 0, sg, cg, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double T[16];
+    mat4_mul(Ry, Rx, T);
+    mat4_mul(Rz, T, M);
+    M[3] = x[3]; M[7] = x[4]; M[11] = x[5];
+}
+}  // namespace
+
+extern "C" int dp_icp_point_to_plane(dp_ctx *ctx, const double *source, int64_t n, const double *target,
+                                     const double *target_normals, int64_t m, double max_correspondence_distance,
+                                     const double *init, int max_iteration, double relative_fitness, double relative_rmse,
+                                     double *T_out, double *fitness, double *inlier_rmse, int *iterations,
+                                     int32_t *correspondence, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || m < 0 || max_iteration < 0 || !T_out || !(max_correspondence_distance > 0.0) || (n > 0 && !source) ||
+        (m > 0 && (!target || !target_normals)))
+        return fail(ctx, DP_E_ARG, "dp_icp_point_to_plane: bad arguments");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double T[16];
+    memcpy(T, init ? init : ident, sizeof(T));
+    // working copy of the source cloud (Open3D transforms a copy in place, iteration after iteration)
+    CK(ctx->tmp[0].ensure((size_t)n * 24 + 16), "dp_icp_point_to_plane: cloud");
+    double *d_src = ctx->tmp[0].as<double>();
+    const double *d_tp = target, *d_tn = target_normals;
+    int32_t *d_corr = correspondence;
+    if (n) CK(cudaMemcpyAsync(d_src, source, (size_t)n * 24, mem == DP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s),
+              "dp_icp_point_to_plane: source");
+    if (mem == DP_HOST) {
+        CK(ctx->tmp[1].ensure((size_t)m * 24 + 16), "dp_icp_point_to_plane: target");
+        CK(ctx->tmp[2].ensure((size_t)m * 24 + 16), "dp_icp_point_to_plane: normals");
+        if (m) {
+            CK(cudaMemcpyAsync(ctx->tmp[1].p, target, (size_t)m * 24, cudaMemcpyHostToDevice, s), "dp_icp_point_to_plane: H2D");
+            CK(cudaMemcpyAsync(ctx->tmp[2].p, target_normals, (size_t)m * 24, cudaMemcpyHostToDevice, s), "dp_icp_point_to_plane: H2D");
+        }
+        d_tp = ctx->tmp[1].as<double>();
+        d_tn = ctx->tmp[2].as<double>();
+        if (correspondence) {
+            CK(ctx->tmp[5].ensure((size_t)n * 4 + 16), "dp_icp_point_to_plane: corr");
+            d_corr = ctx->tmp[5].as<int32_t>();
+        }
+    }
+    CK(ctx->tmp[3].ensure(icp_partial_doubles(n) * 8 + 16), "dp_icp_point_to_plane: partials");
+    CK(ctx->tmp[4].ensure(64 * 8), "dp_icp_point_to_plane: sums");
+    double *d_partial = ctx->tmp[3].as<double>(), *d_sums = ctx->tmp[4].as<double>();
+    double sums[29];
+    bool identity_init = true;
+    for (int i = 0; i < 16; ++i) identity_init = identity_init && T[i] == ident[i];
+    auto evaluate = [&](const double *update) -> int {
+        cudaError_t e = launch_icp_step(d_src, n, d_tp, d_tn, m, max_correspondence_distance, update, d_corr, d_partial, d_sums, s);
+        if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "dp_icp_point_to_plane: launch", e);
+        if ((e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(s)) != cudaSuccess)
+            return fail(ctx, DP_E_CUDA, "dp_icp_point_to_plane: kernels", e);
+        return DP_OK;
+    };
+    int rc = evaluate(identity_init ? nullptr : T);
+    if (rc != DP_OK) return rc;
+    double fit = n > 0 ? sums[0] / (double)n : 0.0, rmse = sums[0] > 0.0 ? sqrt(sums[1] / sums[0]) : 0.0;
+    int it = 0;
+    while (it < max_iteration) {
+        double update[16];
+        memcpy(update, ident, sizeof(update));
+        if (sums[0] > 0.0) {
+            double A[6][6], b[6], x[6] = {0, 0, 0, 0, 0, 0};
+            int e = 2;
+            for (int a = 0; a < 6; ++a)
+                for (int c = a; c < 6; ++c) { A[a][c] = sums[e]; A[c][a] = sums[e]; ++e; }
+            for (int a = 0; a < 6; ++a) b[a] = -sums[23 + a];
+            const double det = solve6(A, b, x);
+            bool okx = fabs(det) >= 1e-6 && det == det && fabs(det) <= 1.7e308;     // Open3D's determinant check
+            for (int a = 0; a < 6; ++a) okx = okx && x[a] == x[a];
+            if (okx) se3_from_vector6(x, update);
+        }
+        mat4_mul(update, T, T);
+        const double pf = fit, pr = rmse;
+        rc = evaluate(update);
+        if (rc != DP_OK) return rc;
+        ++it;
+        fit = n > 0 ? sums[0] / (double)n : 0.0;
+        rmse = sums[0] > 0.0 ? sqrt(sums[1] / sums[0]) : 0.0;
+        if (fabs(pf - fit) < relative_fitness && fabs(pr - rmse) < relative_rmse) break;
+    }
+    memcpy(T_out, T, sizeof(T));
+    if (fitness) *fitness = fit;
+    if (inlier_rmse) *inlier_rmse = rmse;
+    if (iterations) *iterations = it;
+    if (mem == DP_HOST && correspondence && n) {
+        CK(cudaMemcpyAsync(correspondence, d_corr, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_icp_point_to_plane: D2H");
+        CK(cudaStreamSynchronize(s), "dp_icp_point_to_plane: D2H");
+    }
+    return DP_OK;
+}

@@ -111,6 +111,12 @@ cudaError_t launch_pack_hits(const void *inten, int dtype, const int32_t *face, 
                              int32_t *face_out, uint32_t *pixel_out, double *inten_out, int64_t cap,
                              unsigned long long *scratch, long long *d_count, cudaStream_t s);
 
+// ---- icp.cu --------------------------------------------------------------------------------
+size_t icp_partial_doubles(int64_t n);
+// sums (device, 29 doubles): count, sum d^2, 21 upper-triangle entries of sum J J^T, 6 entries of sum J r
+cudaError_t launch_icp_step(double *src, int64_t n, const double *tp, const double *tn, int64_t m, double max_dist,
+                            const double *update_host, int32_t *corr, double *partial, double *sums, cudaStream_t s);
+
 // ---- build.cu ------------------------------------------------------------------------------
 struct BuildScratch;   // opaque, owned by the context
 

@@ -55,6 +55,8 @@ SYMBOLS = {
     "dp_transform_points": (i32, [vp, vp, i64, vp, i32, vp]),
     "dp_pack_hits": (i32, [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64), i32, vp]),
     "dp_jet_lut": (None, [vp]),
+    "dp_icp_point_to_plane": (i32, [vp, vp, i64, vp, vp, i64, f64, vp, i32, f64, f64, vp, C.POINTER(f64), C.POINTER(f64),
+                                    C.POINTER(i32), vp, i32, vp]),
     "dp_accum_reset": (i32, [vp, vp]),
     "dp_accum_get": (i32, [vp, vp, vp, vp, i32, vp]),
     "dp_accum_device_ptrs": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),

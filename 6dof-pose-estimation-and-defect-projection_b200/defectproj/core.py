@@ -434,6 +434,30 @@ class Context:
         out["m"] = m.value
         return out
 
+    # ------------------------------------------------------------------ upstream of the path (8f #4)
+    def icp_point_to_plane(self, source, target, target_normals, max_correspondence_distance, init=None,
+                           max_iteration=30, relative_fitness=1e-6, relative_rmse=1e-6, want_correspondence=False,
+                           stream=None):
+        """registration_icp with TransformationEstimationPointToPlane on the GPU.
+        Returns dict(transformation [4,4], fitness, inlier_rmse, iterations[, correspondence [n] int32])."""
+        src = np.ascontiguousarray(source, dtype=np.float64).reshape(-1, 3)
+        tp = np.ascontiguousarray(target, dtype=np.float64).reshape(-1, 3)
+        tn = np.ascontiguousarray(target_normals, dtype=np.float64).reshape(-1, 3)
+        if len(tn) != len(tp):
+            raise ValueError("target normals and points differ in length")
+        T0 = None if init is None else np.ascontiguousarray(init, dtype=np.float64).reshape(16)
+        T = np.empty(16, np.float64)
+        fit, rmse, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        corr = np.empty(len(src), np.int32) if want_correspondence else None
+        self._check(self._L.dp_icp_point_to_plane(self._h, _ptr(src), len(src), _ptr(tp), _ptr(tn), len(tp),
+                                                  float(max_correspondence_distance), _ptr(T0), int(max_iteration),
+                                                  float(relative_fitness), float(relative_rmse), _ptr(T), C.byref(fit),
+                                                  C.byref(rmse), C.byref(it), _ptr(corr), DP_HOST, self._stream(stream)))
+        out = dict(transformation=T.reshape(4, 4), fitness=fit.value, inlier_rmse=rmse.value, iterations=it.value)
+        if want_correspondence:
+            out["correspondence"] = corr
+        return out
+
     # ------------------------------------------------------------------ H6 / H7
     def accum_reset(self, stream=None):
         self._check(self._L.dp_accum_reset(self._h, self._stream(stream)))

@@ -189,6 +189,21 @@ DP_API int dp_pack_hits(dp_ctx *ctx, const void *intensity, int dtype, const int
 /* the colour table used above: lut [256*3] float64 RGB (host helper, no device work) */
 DP_API void dp_jet_lut(double *lut);
 
+/* ---- upstream of the path: point-to-plane ICP (src/pose_estimation.py:505-522, :577-613, :654-660) */
+/* o3d.pipelines.registration.registration_icp(source, target, max_correspondence_distance, init,
+ * TransformationEstimationPointToPlane(), ICPConvergenceCriteria(relative_fitness, relative_rmse, max_iteration)):
+ * source [n*3], target [m*3] with normals [m*3], float64; init: 16 HOST doubles (NULL = identity).
+ * Per iteration the device finds the exact nearest target point of every source point (ties to the smaller index)
+ * within the distance, and reduces the 6 x 6 normal equations in a fixed order; the host solves them and composes
+ * update = [Rz Ry Rx | t].  Outputs (HOST): T_out[16] (source -> target), fitness = |corr| / n, inlier_rmse,
+ * iterations performed; correspondence: optional [n] int32 (target index or -1) of the final alignment.
+ * Open3D defaults: max_iteration 30, relative_fitness = relative_rmse = 1e-6. */
+DP_API int dp_icp_point_to_plane(dp_ctx *ctx, const double *source, int64_t n, const double *target,
+                                 const double *target_normals, int64_t m, double max_correspondence_distance,
+                                 const double *init, int max_iteration, double relative_fitness, double relative_rmse,
+                                 double *T_out, double *fitness, double *inlier_rmse, int *iterations,
+                                 int32_t *correspondence, int mem, void *stream);
+
 /* ---- H6/H7: accumulators (extensions named by north_star) ------------------ */
 DP_API int dp_accum_reset(dp_ctx *ctx, void *stream);
 /* hist: [nF] int32, fmax: [nF] float32, vmax: [nV] float32; any may be NULL */

@@ -402,3 +402,60 @@ def pack_hits(intensity, face=None, point64=None, T=None):
         pts = np.asarray(point64, np.float64).reshape(-1, 3)[sel]
         out["points"] = transform_points(pts, T) if T is not None else pts
     return out
+
+
+# ------------------------------------------------------------------ point-to-plane ICP
+def _nn_within(q, t, max_dist):
+    idx = np.empty(len(q), np.int64)
+    d2 = np.empty(len(q), np.float64)
+    for s in range(0, len(q), 256):
+        d = q[s:s + 256, None, :] - t[None, :, :]
+        dd = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        j = np.argmin(dd, axis=1)
+        idx[s:s + 256] = j
+        d2[s:s + 256] = dd[np.arange(len(j)), j]
+    ok = d2 <= max_dist * max_dist
+    return idx, d2, ok
+
+
+def icp_point_to_plane(source, target, normals, max_dist, init=None, max_iteration=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """Open3D's RegistrationICP + TransformationEstimationPointToPlane restated in numpy (PARITY UNPINNED: open3d
+    is absent; algorithm as published in Registration.cpp / TransformationEstimation.cpp / Eigen.cpp).
+    Returns (T, fitness, inlier_rmse, iterations, correspondence)."""
+    src = np.asarray(source, np.float64).reshape(-1, 3)
+    tp = np.asarray(target, np.float64).reshape(-1, 3)
+    tn = np.asarray(normals, np.float64).reshape(-1, 3)
+    T = np.eye(4) if init is None else np.array(init, np.float64)
+    pcd = src if np.array_equal(T, np.eye(4)) else transform_points(src, T)
+
+    def evaluate(p):
+        idx, d2, ok = _nn_within(p, tp, max_dist)
+        k = int(ok.sum())
+        return idx, ok, (k / len(p) if len(p) else 0.0), (np.sqrt(d2[ok].sum() / k) if k else 0.0)
+
+    idx, ok, fit, rmse = evaluate(pcd)
+    it = 0
+    while it < max_iteration:
+        update = np.eye(4)
+        if ok.any():
+            s, t, n = pcd[ok], tp[idx[ok]], tn[idx[ok]]
+            r = np.einsum("ij,ij->i", s - t, n)
+            J = np.concatenate([np.cross(s, n), n], axis=1)
+            JTJ, JTr = J.T @ J, J.T @ r
+            det = np.linalg.det(JTJ)
+            if np.isfinite(det) and abs(det) >= 1e-6:
+                x = np.linalg.solve(JTJ, -JTr)
+                ca, sa, cb, sb, cg, sg = np.cos(x[0]), np.sin(x[0]), np.cos(x[1]), np.sin(x[1]), np.cos(x[2]), np.sin(x[2])
+                Rx = np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]])
+                Ry = np.array([[cb, 0, sb], [0, 1, 0], [-sb, 0, cb]])
+                Rz = np.array([[cg, -sg, 0], [sg, cg, 0], [0, 0, 1]])
+                update[:3, :3] = Rz @ Ry @ Rx
+                update[:3, 3] = x[3:]
+        T = update @ T
+        pcd = transform_points(pcd, update)
+        pf, pr = fit, rmse
+        idx, ok, fit, rmse = evaluate(pcd)
+        it += 1
+        if abs(pf - fit) < rel_fitness and abs(pr - rmse) < rel_rmse:
+            break
+    return T, fit, rmse, it, np.where(ok, idx, -1).astype(np.int32)

@@ -165,3 +165,24 @@ def test_transform_points_oracle_is_a_rigid_map(orc):
     q = orc.transform_points(p, T)
     assert np.allclose(q, p @ T[:3, :3].T + T[:3, 3], rtol=0, atol=1e-10)
     assert np.allclose(orc.transform_points(q, np.linalg.inv(T)), p, rtol=0, atol=1e-9)
+
+
+# ------------------------------------------------------------------ point-to-plane ICP (8f #4)
+def test_icp_oracle_recovers_a_known_pose(orc):
+    from defectproj import synth
+    V, F = synth.param_mesh(30, 20, seed=4)
+    V = V.astype(np.float64)
+    fn = np.cross(V[F[:, 1]] - V[F[:, 0]], V[F[:, 2]] - V[F[:, 0]])
+    vn = np.zeros_like(V)
+    for k in range(3):
+        np.add.at(vn, F[:, k], fn)
+    vn /= np.linalg.norm(vn, axis=1, keepdims=True)
+    T = np.eye(4)
+    T[:3, :3] = synth.rot_z(2.0) @ synth.rot_x(-1.5)
+    T[:3, 3] = [0.8, -0.5, 0.6]
+    src = orc.transform_points(V[::2], np.linalg.inv(T))
+    Tr, fit, rmse, it, corr = orc.icp_point_to_plane(src, V, vn, 5.0)
+    assert fit == 1.0 and rmse < 1e-9 and 1 <= it <= 30 and np.abs(Tr - T).max() < 1e-9
+    assert np.array_equal(corr, np.arange(0, len(V), 2))              # every point found its own vertex
+    T1, _, _, it1, _ = orc.icp_point_to_plane(src, V, vn, 5.0, max_iteration=1)
+    assert it1 == 1 and np.abs(T1 - T).max() < np.abs(np.eye(4) - T).max()
