@@ -56,7 +56,7 @@ struct dp_ctx {
     bool has_mesh = false, has_bvh = false, has_cam = false;
 
     BvhStorage obj, cam;
-    DevBuf obj_nodes, obj_tris, obj_wlo, obj_whi, cam_nodes, cam_tris, cam_wlo, cam_whi, scales, tri_face;
+    DevBuf obj_nodes, obj_tris, obj_wlo, obj_whi, cam_nodes, cam_tris, cam_wlo, cam_whi, scales, tri_face, wparent, arrived;
     Topology topo;
     void *build_scratch = nullptr;
     size_t build_scratch_bytes = 0;
@@ -178,7 +178,7 @@ void dp_destroy(dp_ctx *ctx)
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
-                      &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face,
+                      &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
                       &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
                       &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats, &ctx->jet};
@@ -263,6 +263,8 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
         CK(ctx->obj_wlo.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
         CK(ctx->obj_whi.ensure(cap_nodes * 12), "dp_build_bvh: boxes");
         CK(ctx->tri_face.ensure(nf * 4), "dp_build_bvh: tri_face");
+        CK(ctx->wparent.ensure(cap_nodes * 4), "dp_build_bvh: topology");
+        CK(ctx->arrived.ensure(cap_nodes * 4), "dp_build_bvh: topology");
         ctx->obj.nodes = ctx->obj_nodes.as<WideNode>();
         ctx->obj.tris = ctx->obj_tris.as<TriRec>();
         ctx->obj.wlo = ctx->obj_wlo.as<float>();
@@ -270,6 +272,8 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
         ctx->obj.cap_nodes = (int64_t)cap_nodes;
         ctx->obj.d_scale = ctx->scales.as<float>();
         ctx->topo.tri_face = ctx->tri_face.as<int32_t>();
+        ctx->topo.wparent = ctx->wparent.as<int32_t>();
+        ctx->topo.arrived = ctx->arrived.as<unsigned>();
         ctx->has_bvh = ctx->has_cam = false;
         CK(cudaEventRecord(ctx->ev[8], s), "dp_build_bvh");
         e = build_lbvh(ctx->V.as<float>(), ctx->nV, ctx->F.as<int32_t>(), ctx->nF, ctx->obj, ctx->topo,

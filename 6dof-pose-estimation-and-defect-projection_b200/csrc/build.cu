@@ -11,8 +11,8 @@
 //   whose octant matches their direction from the node centre -> bottom-up fit that quantises
 //   the child boxes to 8 bits per plane (conservatively, in double precision).
 //
-// The same bottom-up fit is the refit used after dp_pose_mesh: the topology (meta bytes, child
-// and triangle bases) is shared, only boxes and triangle records are recomputed.
+// The same bottom-up fit (ONE launch, k_fit_all) is the refit used after dp_pose_mesh: the topology (meta
+// bytes, child and triangle bases, parent links) is shared, only boxes and triangle records are recomputed.
 #include "dp_internal.cuh"
 
 #include <math.h>
@@ -360,7 +360,7 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
                            const int32_t *__restrict__ last, const float *__restrict__ blo,
                            const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
                            WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
-                           float c_prim, int greedy_mode)
+                           float c_prim, int greedy_mode, int32_t *wparent)
 {
     const long long w = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (w >= end) return;
@@ -498,6 +498,7 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
         if ((inner_mask >> c) & 1u) {
             imask |= 1u << s;
             meta = 0x20u | (24u + (unsigned)s);
+            if (wparent) wparent[cbase + k_inner] = (int32_t)w;
             wroot[cbase + k_inner++] = id;
         } else {
             const int cnt = count(id);
@@ -512,46 +513,38 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
     nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
 }
 
-__global__ void k_fill_tris(const float *__restrict__ V, const int32_t *__restrict__ F,
-                            const int32_t *__restrict__ tri_face, long long n, TriRec *tris)
+// Fit of one wide node by EIGHT lanes, one per child slot: exact node box into wlo/whi, quantised child boxes into
+// dst.  The boxes of the inner children must already be in wlo/whi (read past L1: another thread wrote them); the
+// records of the leaf triangles are (re)written here from the vertex array, so the refit needs no separate pass over
+// the triangles.  `gmask` names the eight lanes of the group, `s` is this lane's slot.
+//
+// Quantisation: per axis the smallest power of two 2^e with 255 * 2^e >= extent; child planes are rounded outwards
+// in float64 (all products with 2^e and 2^-e are exact) with an explicit containment check, plus 1/128 of a step.
+__device__ __forceinline__ void fit_node8(long long w, int s, unsigned gmask, const WideNode *src, WideNode *dst,
+                                          TriRec *tris, float *wlo, float *whi, float pad, const float *__restrict__ V,
+                                          const int32_t *__restrict__ F, const int32_t *__restrict__ tri_face)
 {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t f = tri_face[i];
-    const long long a = F[3ll * f], b = F[3ll * f + 1], c = F[3ll * f + 2];
-    TriRec t;
-    t.v0 = make_float4(V[3 * a], V[3 * a + 1], V[3 * a + 2], __int_as_float(f));
-    t.v1 = make_float4(V[3 * b], V[3 * b + 1], V[3 * b + 2], 0.0f);
-    t.v2 = make_float4(V[3 * c], V[3 * c + 1], V[3 * c + 2], 0.0f);
-    tris[i] = t;
-}
-
-// bottom-up fit of one level: exact boxes into wlo/whi, quantised child boxes into dst
-__global__ void k_widefit(long long begin, long long end, const WideNode *__restrict__ src, WideNode *dst,
-                          const TriRec *__restrict__ tris, float *wlo, float *whi, const float *__restrict__ d_scale)
-{
-    const long long w = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (w >= end) return;
     const uint4 w1 = src[w].w[1];
     const unsigned imask = src[w].w[0].w >> 24;
-    const float pad = 3.8146973e-6f * (*d_scale);        // 2^-18 * max |coordinate|
-    float clo[8][3], chi[8][3];
-    bool valid[8];
-    float nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    int k_inner = 0;
-    for (int s = 0; s < 8; ++s) {
-        const unsigned meta = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xffu;
-        valid[s] = meta != 0;
-        if (!valid[s]) continue;
+    const unsigned meta = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xffu;
+    const bool valid = meta != 0;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (valid) {
         if ((meta & 0x18u) == 0x18u) {
-            const long long c = (long long)w1.x + k_inner++;
-            for (int k = 0; k < 3; ++k) { clo[s][k] = wlo[3 * c + k]; chi[s][k] = whi[3 * c + k]; }
+            const long long c = (long long)w1.x + __popc(imask & ((1u << s) - 1u));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] = __ldcg(&wlo[3 * c + k]); hi[k] = __ldcg(&whi[3 * c + k]); }
         } else {
             const int cnt = __popc(meta >> 5);
             const long long t0 = (long long)w1.y + (meta & 31u);
-            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
             for (int k = 0; k < cnt; ++k) {
-                const TriRec t = tris[t0 + k];
+                const int32_t f = tri_face[t0 + k];
+                const long long a = F[3ll * f], b = F[3ll * f + 1], c = F[3ll * f + 2];
+                TriRec t;
+                t.v0 = make_float4(V[3 * a], V[3 * a + 1], V[3 * a + 2], __int_as_float(f));
+                t.v1 = make_float4(V[3 * b], V[3 * b + 1], V[3 * b + 2], 0.0f);
+                t.v2 = make_float4(V[3 * c], V[3 * c + 1], V[3 * c + 2], 0.0f);
+                tris[t0 + k] = t;
                 lo[0] = fminf(lo[0], fminf(t.v0.x, fminf(t.v1.x, t.v2.x)));
                 lo[1] = fminf(lo[1], fminf(t.v0.y, fminf(t.v1.y, t.v2.y)));
                 lo[2] = fminf(lo[2], fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
@@ -559,57 +552,107 @@ __global__ void k_widefit(long long begin, long long end, const WideNode *__rest
                 hi[1] = fmaxf(hi[1], fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)));
                 hi[2] = fmaxf(hi[2], fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
             }
-            for (int k = 0; k < 3; ++k) { clo[s][k] = lo[k] - pad; chi[s][k] = hi[k] + pad; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
         }
-        for (int k = 0; k < 3; ++k) { nlo[k] = fminf(nlo[k], clo[s][k]); nhi[k] = fmaxf(nhi[k], chi[s][k]); }
     }
-    if (!(nlo[0] <= nhi[0])) { for (int k = 0; k < 3; ++k) { nlo[k] = 0.0f; nhi[k] = 0.0f; } }   // empty node
-    for (int k = 0; k < 3; ++k) { wlo[3 * w + k] = nlo[k]; whi[3 * w + k] = nhi[k]; }
-
-    unsigned eb[3];
-    double sc[3];
+    // node box over the eight slots
+    float nlo[3], nhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = lo[k], b = hi[k];
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            a = fminf(a, __shfl_xor_sync(gmask, a, d));
+            b = fmaxf(b, __shfl_xor_sync(gmask, b, d));
+        }
+        nlo[k] = a; nhi[k] = b;
+    }
+    if (!(nlo[0] <= nhi[0])) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nlo[k] = 0.0f; nhi[k] = 0.0f; }     // empty node
+    }
+    unsigned eb[3], qa[3], qb[3];
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double ext = (double)nhi[k] - (double)nlo[k];
         int e = -126;
         if (ext > 0.0) {
-            int ex;
-            frexp(ext / 255.0, &ex);      // ext/255 = m * 2^ex, m in [0.5, 1)  =>  2^ex >= ext/255
-            e = ex;
-            while (ldexp(255.0, e) < ext) ++e;
+            e = ((__double2hiint(ext) >> 20) & 0x7ff) - 1023 - 7;          // 2^(e+7) <= ext < 2^(e+8)
+            if (e < -126) e = -126;
+            if (e > 127) e = 127;
+            while (e < 127 && 255.0 * __hiloint2double((e + 1023) << 20, 0) < ext) ++e;
         }
-        if (e < -126) e = -126;
-        if (e > 127) e = 127;
         eb[k] = (unsigned)(e + 127);
-        sc[k] = ldexp(1.0, e);
-    }
-    unsigned ql[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qh[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    for (int s = 0; s < 8; ++s) {
-        for (int k = 0; k < 3; ++k) {
-            unsigned a = 255u, b = 0u;
-            if (valid[s]) {
-                const double base = (double)nlo[k];
-                // 1/128 of a quantisation step of slack on top of the exact containment below
-                double x = floor(((double)clo[s][k] - base) / sc[k] - 0.0078125);
-                x = x < 0.0 ? 0.0 : (x > 255.0 ? 255.0 : x);
-                while (x > 0.0 && base + x * sc[k] > (double)clo[s][k]) x -= 1.0;
-                double y = ceil(((double)chi[s][k] - base) / sc[k] + 0.0078125);
-                y = y < 0.0 ? 0.0 : (y > 255.0 ? 255.0 : y);
-                while (y < 255.0 && base + y * sc[k] < (double)chi[s][k]) y += 1.0;
-                a = (unsigned)x;
-                b = (unsigned)y;
-            }
-            ql[k][s >> 2] |= a << (8 * (s & 3));
-            qh[k][s >> 2] |= b << (8 * (s & 3));
+        const double sc = __hiloint2double((e + 1023) << 20, 0), isc = __hiloint2double((1023 - e) << 20, 0);
+        unsigned a = 255u, b = 0u;
+        if (valid) {
+            const double base = (double)nlo[k];
+            double x = floor(((double)lo[k] - base) * isc - 0.0078125);
+            x = x < 0.0 ? 0.0 : (x > 255.0 ? 255.0 : x);
+            while (x > 0.0 && base + x * sc > (double)lo[k]) x -= 1.0;
+            double y = ceil(((double)hi[k] - base) * isc + 0.0078125);
+            y = y < 0.0 ? 0.0 : (y > 255.0 ? 255.0 : y);
+            while (y < 255.0 && base + y * sc < (double)hi[k]) y += 1.0;
+            a = (unsigned)x;
+            b = (unsigned)y;
         }
+        // bytes of four slots -> one word (lanes 0..3 end up with slots 0..3, lanes 4..7 with slots 4..7)
+        a <<= 8 * (s & 3);
+        b <<= 8 * (s & 3);
+        a |= __shfl_xor_sync(gmask, a, 1); b |= __shfl_xor_sync(gmask, b, 1);
+        a |= __shfl_xor_sync(gmask, a, 2); b |= __shfl_xor_sync(gmask, b, 2);
+        qa[k] = a; qb[k] = b;
     }
-    WideNode out;
-    out.w[0] = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]),
-                          eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
-    out.w[1] = w1;
-    out.w[2] = make_uint4(ql[0][0], ql[0][1], ql[1][0], ql[1][1]);
-    out.w[3] = make_uint4(ql[2][0], ql[2][1], qh[0][0], qh[0][1]);
-    out.w[4] = make_uint4(qh[1][0], qh[1][1], qh[2][0], qh[2][1]);
-    dst[w] = out;
+    // w2: qlo_x[0..3] qlo_x[4..7] qlo_y[0..3] qlo_y[4..7] | w3: qlo_z.. qhi_x.. | w4: qhi_y.. qhi_z..
+    unsigned *o = reinterpret_cast<unsigned *>(dst + w);
+    const int h = s >> 2;
+    if ((s & 3) == 0) {
+        o[8 + h] = qa[0];  o[10 + h] = qa[1]; o[12 + h] = qa[2];
+        o[14 + h] = qb[0]; o[16 + h] = qb[1]; o[18 + h] = qb[2];
+    }
+    if (s == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { wlo[3 * w + k] = nlo[k]; whi[3 * w + k] = nhi[k]; }
+        dst[w].w[0] = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]),
+                                 eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+        dst[w].w[1] = w1;
+    }
+}
+
+// The whole bottom-up fit in ONE launch: a group of eight lanes starts at every wide node without inner children
+// and walks up; the group that completes the last inner child of a node fits that node (arrival counters are never
+// reset: every pass adds exactly the number of inner children, so "last" is a multiple of it).
+__global__ void __launch_bounds__(256)
+k_fit_all(long long n_nodes, const WideNode *src, WideNode *dst, TriRec *tris, float *wlo, float *whi,
+          const float *__restrict__ d_scale, const float *__restrict__ V, const int32_t *__restrict__ F,
+          const int32_t *__restrict__ tri_face, const int32_t *__restrict__ wparent, unsigned *arrived)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long w = t >> 3;
+    const int s = (int)(t & 7);
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = 0xffu << (lane & 24);
+    if (w >= n_nodes) return;                            // whole groups leave together (n_nodes is per group)
+    if (src[w].w[0].w >> 24) return;                     // has inner children: fitted by the last of them
+    const float pad = 3.8146973e-6f * (*d_scale);        // 2^-18 * max |coordinate|
+    for (;;) {
+        fit_node8(w, s, gmask, src, dst, tris, wlo, whi, pad, V, F, tri_face);
+        if (w == 0) return;
+        const long long p = wparent[w];
+        const unsigned need = __popc(src[p].w[0].w >> 24);
+        unsigned last = 0;
+        __threadfence();
+        __syncwarp(gmask);
+        if (s == 0) {
+            const unsigned old = atomicAdd(&arrived[p], 1u);
+            last = ((old + 1u) % need) == 0u;
+        }
+        last = __shfl_sync(gmask, last, lane & 24);
+        if (!last) return;
+        __threadfence();
+        w = p;
+    }
 }
 
 struct Mat34 {
@@ -790,7 +833,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     while (begin < end) {
         if (L + 1 >= 127) return cudaErrorInvalidValue;
         k_collapse<<<blocks_for(end - begin, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
-                                                                wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse());
+                                                                wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse(), topo.wparent);
         unsigned cnt[2];
         if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -801,12 +844,9 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     }
     topo.n_levels = L;
     out.n_nodes = end;
-    k_fill_tris<<<blocks_for(n, 256), 256, 0, s>>>(V, F, topo.tri_face, n, out.tris);
-    for (int l = L - 1; l >= 0; --l) {
-        const long long lb = topo.level_begin[l], le = topo.level_begin[l + 1];
-        k_widefit<<<blocks_for(le - lb, 128), 128, 0, s>>>(lb, le, out.nodes, out.nodes, out.tris, out.wlo, out.whi,
-                                                           out.d_scale);
-    }
+    if ((e = cudaMemsetAsync(topo.arrived, 0, (size_t)out.n_nodes * 4, s)) != cudaSuccess) return e;
+    k_fit_all<<<blocks_for(out.n_nodes * 8, 256), 256, 0, s>>>(out.n_nodes, out.nodes, out.nodes, out.tris, out.wlo, out.whi,
+                                                           out.d_scale, V, F, topo.tri_face, topo.wparent, topo.arrived);
     return cudaGetLastError();
 }
 
@@ -837,12 +877,8 @@ cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t 
     if (nF == 0) {
         return cudaMemcpyAsync(dst.nodes, src.nodes, sizeof(WideNode), cudaMemcpyDeviceToDevice, s);
     }
-    k_fill_tris<<<blocks_for(nF, 256), 256, 0, s>>>(Vposed, F, topo.tri_face, nF, dst.tris);
-    for (int l = topo.n_levels - 1; l >= 0; --l) {
-        const long long lb = topo.level_begin[l], le = topo.level_begin[l + 1];
-        k_widefit<<<blocks_for(le - lb, 128), 128, 0, s>>>(lb, le, src.nodes, dst.nodes, dst.tris, dst.wlo, dst.whi,
-                                                           dst.d_scale);
-    }
+    k_fit_all<<<blocks_for(src.n_nodes * 8, 256), 256, 0, s>>>(src.n_nodes, src.nodes, dst.nodes, dst.tris, dst.wlo, dst.whi,
+                                                           dst.d_scale, Vposed, F, topo.tri_face, topo.wparent, topo.arrived);
     return cudaGetLastError();
 }
 

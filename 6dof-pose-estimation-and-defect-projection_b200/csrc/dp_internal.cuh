@@ -133,6 +133,8 @@ struct BvhStorage {
 
 struct Topology {                  // shared by the object-frame and camera-frame node sets
     int32_t *tri_face = nullptr;   // [nF] record -> original face id
+    int32_t *wparent = nullptr;    // [cap_nodes] wide node -> parent wide node (root: unused)
+    unsigned *arrived = nullptr;   // [cap_nodes] fit arrivals per node (monotonic, see k_fit_all)
     int64_t level_begin[128];      // wide nodes of level l are [level_begin[l], level_begin[l+1])
     int n_levels = 0;
 };
