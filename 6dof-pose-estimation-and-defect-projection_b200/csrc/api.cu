@@ -67,6 +67,8 @@ struct dp_ctx {
     // per-call scratch
     DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, counts, fcounts, xf, stats, jet;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
+    const void *counts_alias_src = nullptr;   // last dp_rays_out.counts address and its device alias
+    long long *counts_alias = nullptr;
     bool stats_on = false;
     int order_parity = 0;
     size_t order_np = 0;
@@ -483,12 +485,11 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
         if (out->cap < cap) cap = out->cap;
     }
 
-    // per-frame constants
+    // per-frame constants (uploaded by the prologue kernel below)
     std::vector<FrameXf> hxf((size_t)(nframes > 0 ? nframes : 1));
     for (int64_t f = 0; f < nframes; ++f)
         dp_frame_xform(K + 9 * (nK == 1 ? 0 : f), frame == DP_FRAME_OBJECT ? pose + 16 * f : nullptr, hxf[f].v);
     CK(ctx->xf.ensure(hxf.size() * sizeof(FrameXf)), "dp_project: xf");
-    if (nframes) CK(cudaMemcpyAsync(ctx->xf.p, hxf.data(), (size_t)nframes * sizeof(FrameXf), cudaMemcpyHostToDevice, s), "dp_project: xf");
 
     const size_t esz = dtype == DP_F64 ? 8 : 4;
     const void *d_heat = heat;
@@ -515,9 +516,41 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
 
     CK(ctx->cscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_project: scratch");
     long long *d_counts = ctx->counts.as<long long>();
-    CK(cudaMemsetAsync(d_counts, 0, 16, s), "dp_project: counts");
+    // packet schedule: read the state the previous call wrote, write the other one (double buffer)
+    const OrderState *ord_prev = nullptr;
+    OrderState *ord_next = nullptr;
+    {
+        const size_t np = (size_t)(cap / 32 + 2);
+        const size_t per = np * 4 * 2 + ((np + 15) & ~size_t(15));
+        const void *before = ctx->order.p;
+        CK(ctx->order.ensure(2 * per + 256), "dp_project: schedule");
+        char *basep = ctx->order.as<char>();
+        OrderState *dstate = reinterpret_cast<OrderState *>(basep);
+        if (ctx->order.p != before || np != ctx->order_np) {
+            OrderState h[2];
+            for (int k = 0; k < 2; ++k) {
+                char *p = basep + 256 + k * per;
+                h[k].n_valid = -1; h[k].cost_sum = 0; h[k].cnt[0] = h[k].cnt[1] = 0;
+                h[k].list0 = reinterpret_cast<uint32_t *>(p);
+                h[k].list1 = reinterpret_cast<uint32_t *>(p + np * 4);
+                h[k].flags = reinterpret_cast<unsigned char *>(p + np * 8);
+            }
+            CK(cudaMemcpyAsync(dstate, h, sizeof(h), cudaMemcpyHostToDevice, s), "dp_project: schedule");   // (re)allocation only
+            ctx->order_parity = 0;
+            ctx->order_np = np;
+        }
+        const int cur = ctx->order_parity, nxt = cur ^ 1;
+        ord_prev = dstate + cur;
+        ord_next = dstate + nxt;
+        ctx->order_parity = nxt;
+    }
+    // one launch resets the counts, the traversal work counter, the compaction scratch and the schedule state this
+    // call will write, and uploads the per-frame constants: no copy-engine work in the kernel stream
+    CK(launch_project_prologue(ctx->cscratch.as<unsigned long long>(), n_elems, d_counts, ord_next, ctx->xf.as<FrameXf>(),
+                               hxf.data(), nframes, s),
+       "dp_project: prologue");
     CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
-                      ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s),
+                      ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s, true),
        "dp_project: compaction");
     CK(cudaEventRecord(ctx->ev[1], s), "dp_project");
 
@@ -536,48 +569,30 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     // t_hit is needed by the hit-point kernel even when the caller does not want it
     if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
     CK(ctx->dir4.ensure((size_t)cap * 16 + 16), "dp_project: rays");
-    // packet schedule: read the state the previous call wrote, write the other one (double buffer)
-    const OrderState *ord_prev = nullptr;
-    OrderState *ord_next = nullptr;
-    {
-        const size_t np = (size_t)(cap / 32 + 2);
-        const size_t per = np * 4 * 2 + ((np + 15) & ~size_t(15));
-        const void *before = ctx->order.p;
-        CK(ctx->order.ensure(2 * per + 256), "dp_project: schedule");
-        char *basep = ctx->order.as<char>();
-        OrderState h[2];
-        for (int k = 0; k < 2; ++k) {
-            char *p = basep + 256 + k * per;
-            h[k].n_valid = -1; h[k].cost_sum = 0; h[k].cnt[0] = h[k].cnt[1] = 0;
-            h[k].list0 = reinterpret_cast<uint32_t *>(p);
-            h[k].list1 = reinterpret_cast<uint32_t *>(p + np * 4);
-            h[k].flags = reinterpret_cast<unsigned char *>(p + np * 8);
-        }
-        OrderState *dstate = reinterpret_cast<OrderState *>(basep);
-        if (ctx->order.p != before || np != ctx->order_np) {
-            CK(cudaMemcpyAsync(dstate, h, sizeof(h), cudaMemcpyHostToDevice, s), "dp_project: schedule");
-            ctx->order_parity = 0;
-            ctx->order_np = np;
-        }
-        const int cur = ctx->order_parity, nxt = cur ^ 1;
-        // reset the state this launch will write (n_valid, cost_sum, cnt), keep its pointers
-        CK(cudaMemcpyAsync(dstate + nxt, &h[nxt], offsetof(OrderState, list0), cudaMemcpyHostToDevice, s), "dp_project: schedule");
-        ord_prev = dstate + cur;
-        ord_next = dstate + nxt;
-        ctx->order_parity = nxt;
-    }
     CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s),
        "dp_project: ray generation");
     CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
     CK(launch_trace_pixels(view_of(b), ctx->dir4.as<float4>(), d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
-                           d_counts + 1, st, ord_prev, ord_next, s),
+                           d_counts + 1, st, ord_prev, ord_next, s, true),
        "dp_project: traversal");
     CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
     CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s),
        "dp_project: hit points");
-    if (out && out->counts)
-        CK(cudaMemcpyAsync(out->counts, d_counts, 16, cudaMemcpyDefault, s), "dp_project: counts");
+    if (out && out->counts) {
+        // device memory: plain store; pinned host memory: zero-copy store through its device alias
+        if (out->counts != ctx->counts_alias_src) {
+            cudaPointerAttributes at{};
+            ctx->counts_alias = nullptr;
+            if (cudaPointerGetAttributes(&at, out->counts) == cudaSuccess && at.devicePointer)
+                ctx->counts_alias = static_cast<long long *>(at.devicePointer);
+            else
+                cudaGetLastError();
+            ctx->counts_alias_src = out->counts;
+        }
+        if (ctx->counts_alias) CK(launch_publish_counts(d_counts, ctx->counts_alias, s), "dp_project: counts");
+        else CK(cudaMemcpyAsync(out->counts, d_counts, 16, cudaMemcpyDefault, s), "dp_project: counts");
+    }
     CK(cudaEventRecord(ctx->ev[2], s), "dp_project");
     ctx->timings_valid = true;
 

@@ -71,7 +71,14 @@ struct TraceStats {
 size_t compact_scratch_bytes(int64_t n_elems);
 cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t frame_elems, double thr,
                            uint32_t *pixel, float *intensity, int64_t cap, unsigned long long *scratch,
-                           long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s);
+                           long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s,
+                           bool scratch_zeroed = false);
+// dp_project's resets and uploads as kernel launches (no copy-engine work in the kernel stream): zeroes the
+// compaction scratch, counts[0..2] (rays, hits, traversal work counter), resets `ord_next`, writes the per-frame
+// constants.  launch_publish_counts stores counts[0..1] to a device or mapped pinned-host address.
+cudaError_t launch_project_prologue(unsigned long long *scratch, int64_t n_elems, long long *counts, struct OrderState *ord_next,
+                                    struct FrameXf *d_xf, const struct FrameXf *h_xf, int64_t n_xf, cudaStream_t s);
+cudaError_t launch_publish_counts(const long long *counts, long long *dst, cudaStream_t s);
 
 // ---- trace.cu ------------------------------------------------------------------------------
 // rays from pixels: pixel[i] = frame*HW + y*W + x ; xf[frame] ; n read from *d_n (<= n_max)
@@ -83,7 +90,8 @@ cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long 
 cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
-                                TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s);
+                                TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
+                                bool counter_zeroed = false);
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
                                 cudaStream_t s);
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,

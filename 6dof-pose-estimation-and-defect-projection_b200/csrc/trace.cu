@@ -623,7 +623,8 @@ cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long 
 cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
-                                TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s)
+                                TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
+                                bool counter_zeroed)
 {
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
@@ -631,7 +632,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     if ((e = trace_grid(&grid)) != cudaSuccess) return e;
     const long long want = (n_max + TR_THREADS - 1) / TR_THREADS;
     if (want < grid) grid = (int)want;
-    if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
+    if (!counter_zeroed && (e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
     if (knob_order() == 0) { ord_prev = nullptr; ord_next = nullptr; }
     if (stats)

@@ -166,6 +166,12 @@ class FrameStream:
         ev_out = [torch.cuda.Event() for _ in range(self.ring)]
         done_k = [False, False]
         pending = []                                   # frames whose D2H has been queued, not yet yielded
+        prof = [] if getattr(self, "profile", False) else None     # per frame: timing events around each stage
+
+        def mark(stream):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
 
         def queue_d2h(i):
             b = i % 2
@@ -174,9 +180,13 @@ class FrameStream:
             m = min(n, self.cap)
             r = i % self.ring
             with torch.cuda.stream(self.s_out):
+                if prof is not None:
+                    prof[i]["out0"] = mark(self.s_out)
                 for k in self.want:
                     self.out_h[r][k][:m].copy_(self.out_d[b][k][:m], non_blocking=True)
                 ev_out[r].record(self.s_out)
+                if prof is not None:
+                    prof[i]["out1"] = mark(self.s_out)
             pending.append((i, r, n, nh, m))
 
         def pop_result():
@@ -195,8 +205,12 @@ class FrameStream:
             with torch.cuda.stream(self.s_in):
                 if done_k[b]:
                     self.s_in.wait_event(ev_k[b])      # kernels of frame i-2 have consumed this heat buffer
+                if prof is not None:
+                    prof.append({"in0": mark(self.s_in)})
                 self.heat_d[b].copy_(heats[i].reshape(1, self.H, self.W), non_blocking=True)
                 ev_in[b].record(self.s_in)
+                if prof is not None:
+                    prof[i]["in1"] = mark(self.s_in)
             if i >= 2:
                 # the device result buffer b is free once frame i-2's D2H is done
                 self.s_k.wait_event(ev_out[(i - 2) % self.ring])
@@ -204,11 +218,15 @@ class FrameStream:
             if before_kernels is not None:
                 with torch.cuda.stream(self.s_k):
                     before_kernels(self.s_k)
+            if prof is not None:
+                prof[i]["k0"] = mark(self.s_k)
             out = dict(self.out_d[b])
             out["counts"] = self.counts_h[b]
             ctx.project_device(self.heat_d[b], K[i if len(K) > 1 else 0], None if poses is None else poses[i:i + 1], thr,
                                frame, accumulate, out=out, sync=False, stream=self.s_k)
             ev_k[b].record(self.s_k)
+            if prof is not None:
+                prof[i]["k1"] = mark(self.s_k)
             done_k[b] = True
             if i >= 1:
                 queue_d2h(i - 1)
@@ -221,3 +239,6 @@ class FrameStream:
             yield pop_result()
         t_end.synchronize()
         self.last_elapsed_ms = t_start.elapsed_time(t_end)
+        if prof is not None:
+            # ms since the start of the run for (H2D begin, H2D end, kernels begin, kernels end, D2H begin, D2H end)
+            self.timeline = [[t_start.elapsed_time(f[k]) for k in ("in0", "in1", "k0", "k1", "out0", "out1")] for f in prof]
