@@ -342,7 +342,7 @@ def run_ours(args):
                     "api": "defectproj.FrameStream.run (3-stream pipeline over dp_project); blocking_call = Context.project",
                     "l2": "132 MiB (> 126 MB L2) memset on the kernel stream before every frame, inside the timed region",
                     "outputs": "pixel u32, t_hit f32, face i32 per ray + ray/hit counts; heatmap f32 in; pinned host memory"},
-            "gpu_launches": 4 * args.steps,   # k_compact, k_raygen, k_trace, k_points per frame
+            "gpu_launches": 5 * args.steps,   # k_project_prologue, k_compact, k_raygen, k_trace, k_points per frame
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
                          "kernel": "k_trace<false,0>", "kernel_ms": k_ms, "bytes_per_ray": b_ray,
