@@ -4,7 +4,7 @@ and writes gpurun_out/configs_report.json.  Every GPU result is checked against 
 finishes in seconds."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "6dof-pose-estimation-and-defect-projection_b200"))
 import torch
 from defectproj import Context, synth

@@ -2,7 +2,7 @@
 """One-line traversal timing of configs[1] for knob sweeps (DP_REFILL, DP_TILED, DEFECTPROJ_LIB)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "6dof-pose-estimation-and-defect-projection_b200"))
 import torch
 from defectproj import Context, synth
