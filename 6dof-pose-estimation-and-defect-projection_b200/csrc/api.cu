@@ -113,7 +113,10 @@ struct DeviceGuard {
     }
 };
 
-BvhView view_of(const BvhStorage &b) { return BvhView{b.nodes, b.tris, b.d_scale}; }
+BvhView view_of(const BvhStorage &b)
+{
+    return BvhView{b.nodes, b.tris, b.d_scale, (size_t)b.n_nodes * sizeof(WideNode) + (size_t)b.n_tris * sizeof(TriRec)};
+}
 
 }  // namespace
 

@@ -132,7 +132,8 @@ k_rs_hist(const uint32_t *__restrict__ keys, long long n, int shift, uint32_t *_
     table[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of table[0..m) in place, single block
+// exclusive scan of table[0..m) in place, single block, 16 consecutive entries per thread and round
+constexpr int SCAN_ITEMS = 16;
 __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *table, long long m)
 {
     __shared__ unsigned s_warp[32];
@@ -140,10 +141,23 @@ __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *table, long long m)
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < m; base += 1024) {
-        const long long i = base + threadIdx.x;
-        const unsigned x = i < m ? table[i] : 0u;
-        unsigned inc = x;
+    for (long long base = 0; base < m; base += 1024 * SCAN_ITEMS) {
+        const long long i0 = base + (long long)threadIdx.x * SCAN_ITEMS;
+        unsigned v[SCAN_ITEMS];
+        unsigned sum = 0;
+        if (i0 + SCAN_ITEMS <= m) {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+                const uint4 x = reinterpret_cast<const uint4 *>(table + i0)[q];
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS; ++q) v[q] = i0 + q < m ? table[i0 + q] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; ++q) { const unsigned x = v[q]; v[q] = sum; sum += x; }   // thread-local exclusive
+        unsigned inc = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
@@ -163,9 +177,19 @@ __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *table, long long m)
         }
         __syncthreads();
         const unsigned carry = s_carry;
-        if (i < m) table[i] = carry + s_warp[warp] + inc - x;
+        const unsigned off = carry + s_warp[warp] + inc - sum;
+        if (i0 + SCAN_ITEMS <= m) {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+                reinterpret_cast<uint4 *>(table + i0)[q] =
+                    make_uint4(off + v[4 * q], off + v[4 * q + 1], off + v[4 * q + 2], off + v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS; ++q)
+                if (i0 + q < m) table[i0 + q] = off + v[q];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + inc;
+        if (threadIdx.x == 1023) s_carry = off + sum;
         __syncthreads();
     }
 }
@@ -353,17 +377,25 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// collapse: one thread per wide node of the current level
+// collapse: EIGHT lanes per wide node of the current level.  Lane 0 of the group picks the children (a short serial
+// walk over the cost tables); the slot assignment, the child/record allocation and the node words are then
+// produced by the group, one candidate child per lane (the levels near the root hold 1, 8, 64 ... nodes, so the
+// latency of one node is the latency of the level).
 // ------------------------------------------------------------------------------------------
-__global__ void k_collapse(long long n, long long begin, long long end, const int32_t *__restrict__ left,
+__global__ void __launch_bounds__(256)
+k_collapse(long long n, long long begin, long long end, const int32_t *__restrict__ left,
                            const int32_t *__restrict__ right, const int32_t *__restrict__ first,
                            const int32_t *__restrict__ last, const float *__restrict__ blo,
                            const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
                            WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
                            float c_prim, int greedy_mode, int32_t *wparent)
 {
-    const long long w = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (w >= end) return;
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long w = begin + (gt >> 3);
+    if (w >= end) return;                                   // whole groups leave together
+    const int gl = (int)(gt & 7), lane32 = threadIdx.x & 31;
+    const unsigned gmask = 0xffu << (lane32 & 24);
+    const int gbase = lane32 & 24;
     const int32_t r = wroot[w];
     unsigned inner_mask = 0;
     auto count = [&](int32_t id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
@@ -381,8 +413,10 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
     };
     int32_t cand[8];
     float carea[8];
-    int nc;
-    if (ctab) {
+    int nc = 0;
+    if (gl != 0) {
+        // lanes 1..7 wait for lane 0's choice
+    } else if (ctab) {
         // cost-optimal cut of the binary subtree (tables from k_binfit); `inner` marks the children that become
         // wide nodes themselves
         auto cost = [&](int32_t id, int i) -> float {
@@ -449,68 +483,114 @@ __global__ void k_collapse(long long n, long long begin, long long end, const in
             ++nc;
         }
     }
-    // ---- slot assignment: slot s (bit k set = towards +axis k) is visited first by rays
-    //      whose direction is negative along exactly the axes set in s
-    float cen[8][3], nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int c = 0; c < nc; ++c)
-        for (int k = 0; k < 3; ++k) {
-            const float a = blo[3ll * cand[c] + k], b = bhi[3ll * cand[c] + k];
-            cen[c][k] = 0.5f * (a + b);
-            nlo[k] = fminf(nlo[k], a);
-            nhi[k] = fmaxf(nhi[k], b);
-        }
-    int slot_of[8], cand_at[8];
-    for (int k = 0; k < 8; ++k) { slot_of[k] = -1; cand_at[k] = -1; }
-    for (int it = 0; it < nc; ++it) {
-        float bc = -INFINITY;
-        int bci = -1, bs = -1;
-        for (int c = 0; c < nc; ++c) {
-            if (slot_of[c] >= 0) continue;
-            for (int s = 0; s < 8; ++s) {
-                if (cand_at[s] >= 0) continue;
-                float cost = 0.0f;
-                for (int k = 0; k < 3; ++k) {
-                    const float dlt = cen[c][k] - 0.5f * (nlo[k] + nhi[k]);
-                    cost += ((s >> k) & 1) ? dlt : -dlt;
-                }
-                if (cost > bc) { bc = cost; bci = c; bs = s; }
-            }
-        }
-        slot_of[bci] = bs;
-        cand_at[bs] = bci;
-    }
-    if (!ctab)
+    if (gl == 0 && !ctab)
         for (int c = 0; c < nc; ++c)
             if (expandable(cand[c])) inner_mask |= 1u << c;
-    int n_inner = 0, n_leaf_tris = 0;
-    for (int c = 0; c < nc; ++c) {
-        if ((inner_mask >> c) & 1u) ++n_inner; else n_leaf_tris += count(cand[c]);
+    // ---- the group takes over: candidate c lives in lane c
+    nc = __shfl_sync(gmask, nc, gbase);
+    inner_mask = __shfl_sync(gmask, inner_mask, gbase);
+    int32_t my = -1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int32_t v = __shfl_sync(gmask, cand[c], gbase);
+        if (c == gl) my = v;
     }
-    const unsigned cbase = n_inner ? atomicAdd(&counters[0], (unsigned)n_inner) : 0u;
-    const unsigned tbase = n_leaf_tris ? atomicAdd(&counters[1], (unsigned)n_leaf_tris) : 0u;
-    unsigned imask = 0, meta_lo = 0, meta_hi = 0;
-    int k_inner = 0, toff = 0;
-    for (int s = 0; s < 8; ++s) {
-        const int c = cand_at[s];
-        if (c < 0) continue;
-        const int32_t id = cand[c];
-        unsigned meta;
-        if ((inner_mask >> c) & 1u) {
-            imask |= 1u << s;
-            meta = 0x20u | (24u + (unsigned)s);
-            if (wparent) wparent[cbase + k_inner] = (int32_t)w;
-            wroot[cbase + k_inner++] = id;
-        } else {
-            const int cnt = count(id);
-            const long long f0 = id < n - 1 ? first[id] : id - (n - 1);
-            meta = (((1u << cnt) - 1u) << 5) | (unsigned)toff;
-            for (int k = 0; k < cnt; ++k) tri_face[tbase + toff + k] = (int32_t)sorted_tri[f0 + k];
-            toff += cnt;
+    const bool have = gl < nc;
+    const bool my_inner = have && ((inner_mask >> gl) & 1u);
+    float cen[3] = {0.f, 0.f, 0.f}, lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (have) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = blo[3ll * my + k]; hi[k] = bhi[3ll * my + k];
+            cen[k] = 0.5f * (lo[k] + hi[k]);
         }
-        if (s < 4) meta_lo |= meta << (8 * s); else meta_hi |= meta << (8 * (s - 4));
     }
-    nodes[w].w[0] = make_uint4(0u, 0u, 0u, imask << 24);
-    nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
+    float dlt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = lo[k], b = hi[k];
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            a = fminf(a, __shfl_xor_sync(gmask, a, d));
+            b = fmaxf(b, __shfl_xor_sync(gmask, b, d));
+        }
+        dlt[k] = cen[k] - 0.5f * (a + b);
+    }
+    // ---- slot assignment: slot s (bit k set = towards +axis k) is visited first by rays whose direction is
+    //      negative along exactly the axes set in s.  Greedy: the (child, slot) pair with the largest projection
+    //      of the child's offset on the slot's diagonal first; ties to the smaller child, then the smaller slot.
+    unsigned free_slots = 0xffu;
+    int my_slot = -1;
+    for (int it = 0; it < nc; ++it) {
+        float bc = -INFINITY;
+        int bs = 0;
+        if (have && my_slot < 0) {
+#pragma unroll
+            for (int sidx = 0; sidx < 8; ++sidx) {
+                if (!((free_slots >> sidx) & 1u)) continue;
+                float cost = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cost += ((sidx >> k) & 1) ? dlt[k] : -dlt[k];
+                if (cost > bc) { bc = cost; bs = sidx; }
+            }
+        }
+        // arg max over the group: larger cost wins, ties to the smaller lane
+        float wc = bc;
+        int wl = (have && my_slot < 0) ? gl : 8, ws = bs;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const float oc = __shfl_xor_sync(gmask, wc, d);
+            const int ol = __shfl_xor_sync(gmask, wl, d), os = __shfl_xor_sync(gmask, ws, d);
+            const bool take = (ol < 8) && (wl >= 8 || oc > wc || (oc == wc && ol < wl));
+            if (take) { wc = oc; wl = ol; ws = os; }
+        }
+        if (wl == gl) my_slot = ws;
+        free_slots &= ~(1u << ws);
+    }
+    // ---- allocation: inner children and leaf records are numbered in slot order
+    const int my_cnt = (have && !my_inner) ? count(my) : 0;
+    int k_inner = 0, toff = 0, n_inner = 0, n_leaf_tris = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int sj = __shfl_sync(gmask, my_slot, gbase + j);
+        const int ij = __shfl_sync(gmask, (int)my_inner, gbase + j);
+        const int cj = __shfl_sync(gmask, my_cnt, gbase + j);
+        if (sj < 0) continue;
+        n_inner += ij; n_leaf_tris += cj;
+        if (sj < my_slot) { k_inner += ij; toff += cj; }
+    }
+    unsigned cbase = 0, tbase = 0;
+    if (gl == 0) {
+        cbase = n_inner ? atomicAdd(&counters[0], (unsigned)n_inner) : 0u;
+        tbase = n_leaf_tris ? atomicAdd(&counters[1], (unsigned)n_leaf_tris) : 0u;
+    }
+    cbase = __shfl_sync(gmask, cbase, gbase);
+    tbase = __shfl_sync(gmask, tbase, gbase);
+    unsigned meta = 0, ibit = 0;
+    if (have) {
+        if (my_inner) {
+            ibit = 1u << my_slot;
+            meta = 0x20u | (24u + (unsigned)my_slot);
+            if (wparent) wparent[cbase + k_inner] = (int32_t)w;
+            wroot[cbase + k_inner] = my;
+        } else {
+            const long long f0 = my < n - 1 ? first[my] : my - (n - 1);
+            meta = (((1u << my_cnt) - 1u) << 5) | (unsigned)toff;
+            for (int k = 0; k < my_cnt; ++k) tri_face[tbase + toff + k] = (int32_t)sorted_tri[f0 + k];
+        }
+    }
+    unsigned meta_lo = (have && my_slot < 4) ? meta << (8 * my_slot) : 0u;
+    unsigned meta_hi = (have && my_slot >= 4) ? meta << (8 * (my_slot - 4)) : 0u;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        meta_lo |= __shfl_xor_sync(gmask, meta_lo, d);
+        meta_hi |= __shfl_xor_sync(gmask, meta_hi, d);
+        ibit |= __shfl_xor_sync(gmask, ibit, d);
+    }
+    if (gl == 0) {
+        nodes[w].w[0] = make_uint4(0u, 0u, 0u, ibit << 24);
+        nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
+    }
 }
 
 // Fit of one wide node by EIGHT lanes, one per child slot: exact node box into wlo/whi, quantised child boxes into
@@ -832,7 +912,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     int L = 0;
     while (begin < end) {
         if (L + 1 >= 127) return cudaErrorInvalidValue;
-        k_collapse<<<blocks_for(end - begin, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
+        k_collapse<<<blocks_for((end - begin) * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
                                                                 wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse(), topo.wparent);
         unsigned cnt[2];
         if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;

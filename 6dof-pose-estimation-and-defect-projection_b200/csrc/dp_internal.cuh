@@ -37,6 +37,7 @@ struct BvhView {
     const WideNode *nodes;
     const TriRec *tris;
     const float *d_scale;  // device: max |vertex coordinate| of the mesh the BVH was fitted to
+    size_t bytes;          // nodes + triangle records
 };
 
 // per-frame ray generation constants: fx fy cx cy | Rinv (row-major) | tinv

@@ -101,6 +101,7 @@ struct RayState {
     unsigned octinv;
     uint2 ng;                 // current node group: (child base, hit bits | imask)
     int sp;
+    unsigned next;            // index of the node the next step fetches (valid while the ray is alive)
 };
 
 __device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -167,12 +168,19 @@ __device__ __forceinline__ float qf_i2f(unsigned w, int i) { return (float)((w >
 #define qf_xu qf_i2f
 #endif
 
-// One node step: visit the nearest pending inner child (fetch its 80-byte node, test the 8 child
-// boxes against [0, tlimit]), hand the triangle hits back as (tbase, tmask) and advance to the next
-// node group.  Returns false when nothing is left to visit.
-template <bool STATS>
-__device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restrict__ nodes, uint2 *stack, uint2 *lstack,
-                                          float tlimit, unsigned &tbase, unsigned &tmask, unsigned &n_nodes)
+// Prefetch of the next node (and of queued triangle records) into L1 one phase ahead.  Measured on B200: +2.5 % at
+// 5M triangles (BVH 290 MB, beyond L2), -1.5 % at 500k (BVH 29 MB, L2-resident), so the launcher turns it on only
+// for hierarchies larger than PREFETCH_MIN_BYTES.
+constexpr size_t PREFETCH_MIN_BYTES = 96u << 20;
+__device__ __forceinline__ void prefetch_l1(const void *p, bool on)
+{
+    if (on) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// Selection half of a node step: take the nearest pending inner child out of the current node group (the rest of
+// the group goes on the stack), remember its node index for the next visit and start fetching it.
+__device__ __forceinline__ void node_select(RayState &r, const WideNode *__restrict__ nodes, uint2 *stack, uint2 *lstack,
+                                            bool pf)
 {
     uint2 ng = r.ng;
     const unsigned hits = ng.y;
@@ -184,10 +192,22 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
     }
     const unsigned slot = (unsigned)(bit - 24) ^ r.octinv;
     const unsigned rel = __popc(hits & 0xffu & ((1u << slot) - 1u));
-    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + (ng.x + rel));
+    r.next = ng.x + rel;
+    const char *np = reinterpret_cast<const char *>(nodes + r.next);
+    prefetch_l1(np, pf);
+    prefetch_l1(np + 64, pf);
+}
+
+// Visit half: fetch the selected 80-byte node, test its 8 child boxes against [0, tlimit], hand the triangle hits
+// back as (tbase, tmask) and make the node's inner hits the current group (or pop one from the stack).  Returns
+// false when nothing is left to visit; otherwise the next node has been selected (node_select).
+template <bool STATS>
+__device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restrict__ nodes, uint2 *stack, uint2 *lstack,
+                                          float tlimit, unsigned &tbase, unsigned &tmask, unsigned &n_nodes, bool pf)
+{
+    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + r.next);
     const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), w2 = __ldg(np + 2), w3 = __ldg(np + 3), w4 = __ldg(np + 4);
     if (STATS) ++n_nodes;
-
     const float adjx = __uint_as_float((w0.w & 0xffu) << 23) * r.ix;
     const float adjy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23) * r.iy;
     const float adjz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23) * r.iz;
@@ -233,7 +253,7 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
             if (tmin <= tmax) hitmask |= ((cbits4 >> (8 * j)) & 0xffu) << ((bidx4 >> (8 * j)) & 0xffu);
         }
     }
-    ng = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
+    uint2 ng = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
     tmask = hitmask & 0x00ffffffu;
     tbase = w1.y;
     if (!(ng.y & 0xff000000u)) {
@@ -242,6 +262,7 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
         ng = (r.sp < STACK_SMEM) ? stack[r.sp * TR_THREADS] : lstack[r.sp - STACK_SMEM];
     }
     r.ng = ng;
+    node_select(r, nodes, stack, lstack, pf);
     return true;
 }
 
@@ -314,8 +335,9 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
         const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
         const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
         unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
-        const OrderState *__restrict__ ord_prev, OrderState *ord_next)
+        const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch)
 {
+    const bool pf = prefetch != 0;
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
     __shared__ unsigned s_queue[(TR_THREADS / 32) * TQ_CAP];
     __shared__ unsigned long long s_best[TR_THREADS];
@@ -345,12 +367,12 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
     unsigned long long cost_local = 0;
 
     // lane 0 keeps the next packet's base one fetch ahead, so the atomic's latency hides behind a packet
-    unsigned long long pf = 0;
-    if (lane == 0) pf = atomicAdd(work_counter, 1ull);
+    unsigned long long nextw = 0;
+    if (lane == 0) nextw = atomicAdd(work_counter, 1ull);
     for (;;) {
-        const long long w = (long long)__shfl_sync(0xffffffffu, pf, 0);
+        const long long w = (long long)__shfl_sync(0xffffffffu, nextw, 0);
         if (w >= np + c0 + c1) break;
-        if (lane == 0) pf = atomicAdd(work_counter, 1ull);
+        if (lane == 0) nextw = atomicAdd(work_counter, 1ull);
         long long packet;
         if (w < c0) packet = ord_prev->list0[w];
         else if (w < c0 + c1) packet = ord_prev->list1[w - c0];
@@ -381,6 +403,7 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
             ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
         }
         best[lane] = KEY_MISS;
+        if (alive) node_select(r, nodes, stack, lstack, pf);
         __syncwarp();
         int qhead = 0, qcount = 0;              // warp-uniform
         const unsigned nn_start = nn;
@@ -390,7 +413,7 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
             unsigned tmask = 0, tbase = 0;
             if (alive) {
                 const float tlimit = __uint_as_float((unsigned)(best[lane] >> 32)) * T_SLACK;
-                alive = node_step<STATS>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn);
+                alive = node_step<STATS>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn, pf);
                 ++steps;
             }
             // queue this step's triangles, one per lane and round; test whenever 32 are waiting
@@ -401,6 +424,7 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
                     const int b = __ffs(tmask) - 1;
                     tmask &= tmask - 1u;
                     queue[(qhead + qcount + __popc(contrib & lt)) & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
+                    prefetch_l1(tris + (tbase + b), pf);
                 }
                 qcount += __popc(contrib);
                 __syncwarp();
@@ -634,15 +658,16 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     if (want < grid) grid = (int)want;
     if (!counter_zeroed && (e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
+    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
     if (knob_order() == 0) { ord_prev = nullptr; ord_next = nullptr; }
     if (stats)
         k_trace<true, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,
                                                      total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter,
-                                                     d_hits, stats, knob_tiled(), ord_prev, ord_next);
+                                                     d_hits, stats, knob_tiled(), ord_prev, ord_next, pf);
     else
         k_trace<false, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n,
                                                       n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr,
-                                                      work_counter, d_hits, stats, knob_tiled(), ord_prev, ord_next);
+                                                      work_counter, d_hits, stats, knob_tiled(), ord_prev, ord_next, pf);
     return cudaGetLastError();
 }
 
@@ -657,12 +682,13 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
     if (want < grid) grid = (int)want;
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a{nullptr, nullptr, nullptr, nullptr};
+    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
     if (stats)
         k_trace<true, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0,
-                                                     0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr);
+                                                     0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf);
     else
         k_trace<false, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n,
-                                                      0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr);
+                                                      0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf);
     return cudaGetLastError();
 }
 

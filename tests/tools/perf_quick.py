@@ -12,6 +12,9 @@ K, H, W = synth.camera_wfov()
 pose = synth.fill_frame_pose()
 V, F = synth.param_mesh(*synth.MESH_CONFIGS[mesh], seed=0, scale=6.0)
 ctx = Context(0); ctx.set_mesh(V, F).build_bvh()
+builds = []
+for _ in range(4):
+    ctx.build_bvh(); builds.append(ctx.stats()["last_build_ms"])
 heat = torch.ones((1, H, W), dtype=torch.float32, device="cuda")
 n = H * W
 out = dict(t_hit=torch.empty(n, device="cuda"), face=torch.empty(n, dtype=torch.int32, device="cuda"))
@@ -26,7 +29,7 @@ ctx.set_stats(True)
 ctx.project_device(heat, K, pose[None], 0.5, "object", True, out=out, sync=True)
 st = ctx.stats()
 ctx.set_stats(False)
-msg = f"{mesh} collapse={os.environ.get('DP_COLLAPSE','-')} cprim={os.environ.get('DP_CPRIM','-')} wide_nodes={st['n_wide_nodes']} depth={st['wide_depth']} build_ms={st['last_build_ms']:.2f} refill={os.environ.get('DP_REFILL','-')} tiled={os.environ.get('DP_TILED','-')} lib={os.path.basename(os.environ.get('DEFECTPROJ_LIB','default'))} trace_ms min {min(ts):.4f} med {np.median(ts):.4f} -> {n/np.median(ts)/1e3:.0f} Mrays/s nodes/ray {st['nodes_fetched']/max(1,st['rays']):.2f} tris/ray {st['tris_tested']/max(1,st['rays']):.2f}"
+msg = f"{mesh} collapse={os.environ.get('DP_COLLAPSE','-')} cprim={os.environ.get('DP_CPRIM','-')} wide_nodes={st['n_wide_nodes']} depth={st['wide_depth']} build_ms={min(builds):.2f} refill={os.environ.get('DP_REFILL','-')} tiled={os.environ.get('DP_TILED','-')} lib={os.path.basename(os.environ.get('DEFECTPROJ_LIB','default'))} trace_ms min {min(ts):.4f} med {np.median(ts):.4f} -> {n/np.median(ts)/1e3:.0f} Mrays/s nodes/ray {st['nodes_fetched']/max(1,st['rays']):.2f} tris/ray {st['tris_tested']/max(1,st['rays']):.2f}"
 if check:
     from oracle import oracle as orc
     xs = np.tile(np.arange(W, dtype=np.int64), H); ys = np.repeat(np.arange(H, dtype=np.int64), W)
