@@ -143,7 +143,7 @@ __device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float
 #ifndef DP_PLANE_MODE
 #define DP_PLANE_MODE 1
 #endif
-__device__ __forceinline__ float qf_magic(unsigned w, int i)
+__device__ __forceinline__ __attribute__((unused)) float qf_magic(unsigned w, int i)
 {
     // selector as the immediate, the magic constant in a register: one PRMT, no extra move
     const unsigned magic = 0x4B000000u;

@@ -43,15 +43,21 @@ def gather_hits(records, group=None):
         return records
     world = dist.get_world_size(group)
     n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    counts_t = torch.empty(world, dtype=torch.int64, device=records.device)
+    dist.all_gather_into_tensor(counts_t, n, group=group)
+    counts = counts_t.tolist()                                  # the one host synchronisation of the gather
     m = max(counts) if counts else 0
-    pad = torch.zeros((m,) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
-    pad[:records.shape[0]] = records
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    tail = tuple(records.shape[1:])
+    if records.shape[0] == m:
+        pad = records.contiguous()
+    else:
+        pad = torch.zeros((m,) + tail, dtype=records.dtype, device=records.device)
+        pad[:records.shape[0]] = records
+    buf = torch.empty((world * m,) + tail, dtype=records.dtype, device=records.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)          # one flat collective, no per-rank staging copies
+    if all(c == m for c in counts):
+        return buf
+    return torch.cat([buf[r * m:r * m + c] for r, c in enumerate(counts)], dim=0)
 
 
 class _DevView:

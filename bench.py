@@ -18,7 +18,8 @@ threshold+compaction -> pixel rays (object frame) -> 8-wide BVH traversal -> his
              cores; the reference itself is Python over open3d/Embree, absent offline) on the same frames:
              mesh posing + BVH build per call (as the reference does, :253-254) + rays + closest hit.
 N > 1 (torchrun): frames are sharded, every rank runs K frames against its own BVH replica (weak scaling);
-the integer histogram and the float maxima are combined once per batch with NCCL inside the timed region.
+the integer histogram, the float maxima and the last frame's compacted hit records are combined once per batch with
+NCCL inside the timed region.
 """
 from __future__ import annotations
 
@@ -236,6 +237,13 @@ def run_ours(args):
     for i in range(args.warmup):
         flush.zero_()
         step_device(i)
+    if world > 1:
+        # warm-up of the per-batch combine too (the first NCCL call of each kind sets up its channels, the first
+        # use of a torch kernel loads its module)
+        from defectproj.projector import combine_accumulators, gather_hits
+        combine_accumulators(*proj.accumulators())
+        rec = torch.stack([out["pixel"][:n_rays], out["t_hit"][:n_rays].view(torch.int32), out["face"][:n_rays]], dim=1)
+        gather_hits(rec[rec[:, 2] >= 0])
     ctx.accum_reset(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -255,9 +263,14 @@ def run_ours(args):
             trace_ms.append(ctx.last_timings()["trace_ms"])
     ev_c0, ev_c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_c0.record(stream)
+    gathered = 0
     if world > 1:
-        from defectproj.projector import combine_accumulators
+        from defectproj.projector import combine_accumulators, gather_hits
         combine_accumulators(*proj.accumulators())        # one collective per batch (hist SUM, fmax/vmax MAX)
+        # compacted hit records (pixel, t bits, face) of every rank's last frame -> all ranks, in rank order
+        rec = torch.stack([out["pixel"][:n_rays], out["t_hit"][:n_rays].view(torch.int32), out["face"][:n_rays]], dim=1)
+        rec = rec[rec[:, 2] >= 0]
+        gathered = int(gather_hits(rec).shape[0])
     ev_c1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -352,6 +365,9 @@ def run_ours(args):
             "ms_per_frame": total_ms / args.steps,
             "bvh": {"build_ms": st2["last_build_ms"], "wide_nodes": st2["n_wide_nodes"], "depth": st2["wide_depth"],
                     "bytes": st2["n_wide_nodes"] * 80 + st2["n_tris"] * 48},
+            "combine": {"ms": ev_c0.elapsed_time(ev_c1), "collectives": "all_reduce(hist SUM, fmax MAX, vmax MAX) + "
+                        "count/padded all_gather of the last frame's hit records, once per batch, inside the timed total",
+                        "hit_records_gathered": gathered},
             "checks": {"rays_per_frame": n_rays, "hits_per_frame": n_hits,
                        "hist_total_equals_hits": bool(world > 1 or hist_total > 0)},
         }
