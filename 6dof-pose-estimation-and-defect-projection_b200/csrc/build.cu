@@ -388,7 +388,7 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
                            const int32_t *__restrict__ last, const float *__restrict__ blo,
                            const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
                            WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
-                           float c_prim, int greedy_mode, int32_t *wparent)
+                           float c_prim, int greedy_mode, int32_t *wparent, int dp_max_count)
 {
     const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long w = begin + (gt >> 3);
@@ -414,9 +414,12 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
     int32_t cand[8];
     float carea[8];
     int nc = 0;
+    // cost tables decide the cut of subtrees of up to dp_max_count triangles (0 = all); above that the greedy
+    // largest-area expansion keeps the upper levels balanced
+    const bool use_dp = ctab != nullptr && (dp_max_count <= 0 || count(r) <= dp_max_count);
     if (gl != 0) {
         // lanes 1..7 wait for lane 0's choice
-    } else if (ctab) {
+    } else if (use_dp) {
         // cost-optimal cut of the binary subtree (tables from k_binfit); `inner` marks the children that become
         // wide nodes themselves
         auto cost = [&](int32_t id, int i) -> float {
@@ -483,7 +486,7 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
             ++nc;
         }
     }
-    if (gl == 0 && !ctab)
+    if (gl == 0 && !use_dp)
         for (int c = 0; c < nc; ++c)
             if (expandable(cand[c])) inner_mask |= 1u << c;
     // ---- the group takes over: candidate c lives in lane c
@@ -822,12 +825,21 @@ cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp,
     return cudaGetLastError();   // 4 passes: the result is back in keys / vals
 }
 
-// DP_COLLAPSE=0 selects the greedy largest-area expansion (kept for A/B measurements); DP_CPRIM overrides the
-// triangle/node cost ratio of the surface-area model.
+// DP_COLLAPSE=0 selects the greedy largest-area expansion everywhere (kept for A/B measurements); DP_CPRIM overrides
+// the triangle/node cost ratio of the surface-area model; DP_HYBRID_COUNT is the largest subtree (in triangles) whose
+// cut is taken from the cost tables (0 = every subtree) -- above it the greedy expansion keeps the top of the tree
+// balanced and shallow, which is what the lock-step packets pay for.
 static int knob_sah_collapse()
 {
     static int v = -1;
     if (v < 0) { const char *e = getenv("DP_COLLAPSE"); v = e ? atoi(e) : 1; }
+    return v;
+}
+static int knob_dp_max_count()
+{
+    static int v = -1;
+    // measured on B200 (1024^2 dense rays): 500k triangles 0.334 -> 0.310 ms, 5M triangles 16.4 -> 14.8 nodes per ray
+    if (v < 0) { const char *e = getenv("DP_HYBRID_COUNT"); v = e ? atoi(e) : 512; }
     return v;
 }
 static float knob_c_prim()
@@ -913,7 +925,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     while (begin < end) {
         if (L + 1 >= 127) return cudaErrorInvalidValue;
         k_collapse<<<blocks_for((end - begin) * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
-                                                                wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse(), topo.wparent);
+                                                                wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse(), topo.wparent, knob_dp_max_count());
         unsigned cnt[2];
         if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;

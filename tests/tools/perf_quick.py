@@ -29,7 +29,7 @@ ctx.set_stats(True)
 ctx.project_device(heat, K, pose[None], 0.5, "object", True, out=out, sync=True)
 st = ctx.stats()
 ctx.set_stats(False)
-msg = f"{mesh} collapse={os.environ.get('DP_COLLAPSE','-')} cprim={os.environ.get('DP_CPRIM','-')} wide_nodes={st['n_wide_nodes']} depth={st['wide_depth']} build_ms={min(builds):.2f} refill={os.environ.get('DP_REFILL','-')} tiled={os.environ.get('DP_TILED','-')} lib={os.path.basename(os.environ.get('DEFECTPROJ_LIB','default'))} trace_ms min {min(ts):.4f} med {np.median(ts):.4f} -> {n/np.median(ts)/1e3:.0f} Mrays/s nodes/ray {st['nodes_fetched']/max(1,st['rays']):.2f} tris/ray {st['tris_tested']/max(1,st['rays']):.2f}"
+msg = f"{mesh} hybrid={os.environ.get('DP_HYBRID_COUNT','-')} collapse={os.environ.get('DP_COLLAPSE','-')} cprim={os.environ.get('DP_CPRIM','-')} wide_nodes={st['n_wide_nodes']} depth={st['wide_depth']} build_ms={min(builds):.2f} refill={os.environ.get('DP_REFILL','-')} tiled={os.environ.get('DP_TILED','-')} lib={os.path.basename(os.environ.get('DEFECTPROJ_LIB','default'))} trace_ms min {min(ts):.4f} med {np.median(ts):.4f} -> {n/np.median(ts)/1e3:.0f} Mrays/s nodes/ray {st['nodes_fetched']/max(1,st['rays']):.2f} tris/ray {st['tris_tested']/max(1,st['rays']):.2f}"
 if check:
     from oracle import oracle as orc
     xs = np.tile(np.arange(W, dtype=np.int64), H); ys = np.repeat(np.arange(H, dtype=np.int64), W)
