@@ -187,6 +187,32 @@ def config_dict(args, nF, H, W):
             "frame": "object (rays through the inverse pose, static BVH)"}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on (and first-touch the pinned buffers from) the CPUs of the GPU's own NUMA node,
+    so that eight ranks do not all stream their frames through one socket's memory.  Returns a short description
+    for the bench line; does nothing when the topology is not visible or the node has none of our CPUs."""
+    if os.environ.get("DP_NUMA_BIND", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = cpus & os.sched_getaffinity(0)
+        if node < 0 or not mine or mine == os.sched_getaffinity(0):
+            return f"node {node}: no narrower cpu set"
+        os.sched_setaffinity(0, mine)
+        return f"node {node}: {len(mine)} cpus"
+    except Exception as e:                                  # topology not visible in this container
+        return f"unavailable ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -195,6 +221,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single process"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
@@ -349,6 +376,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, len(F), H, W),
             "clocks": clocks,
+            "numa": numa,
             "e2e": {"value": e2e_rays_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_frame": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "wall_ms_per_frame": 1e3 * e2e_wall / e2e_steps, "blocking_call_ms_per_frame": blocking_ms,

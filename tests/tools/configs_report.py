@@ -95,5 +95,36 @@ for cfg in ("ns_1m", "c4_5m"):
                         "parity_t": bool(np.array_equal(o["t_hit"].cpu().numpy().view(np.uint32), t.view(np.uint32)))}
     print(cfg, json.dumps(out["C4_" + cfg]), flush=True)
     del bv
+# ---------------------------------------------------------------- the rows either side of the path (8f), host-buffer calls
+def wall(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize()
+    return 1e3 * (time.perf_counter() - t0) / reps
+rng = np.random.default_rng(0)
+fr = {}
+data = rng.random((224, 224))
+fr["prepare_heatmap_224_to_1024x1024_f64_ms"] = wall(lambda: ctx.prepare_heatmap(data, 1024, 1024))
+d_data = torch.from_numpy(data).cuda()
+fr["prepare_heatmap_device_ms"] = wall(lambda: ctx.prepare_heatmap(d_data, 1024, 1024, np.float32))
+t0 = time.perf_counter(); orc.prepare_heatmap(data, 1024, 1024); fr["prepare_heatmap_cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+n = 1 << 20
+I = rng.random(n).astype(np.float32); face = rng.integers(-1, 1000, n).astype(np.int32); p64 = rng.normal(size=(n, 3))
+fr["pack_hits_1M_host_buffers_ms"] = wall(lambda: ctx.pack_hits(I, face, None, p64, T=np.eye(4)), reps=3)
+t0 = time.perf_counter(); orc.pack_hits(I, face, p64, np.eye(4)); fr["pack_hits_cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+Vi, Fi = synth.param_mesh(300, 200, seed=9)
+Vi = Vi.astype(np.float64)
+fn_ = np.cross(Vi[Fi[:, 1]] - Vi[Fi[:, 0]], Vi[Fi[:, 2]] - Vi[Fi[:, 0]]); vn = np.zeros_like(Vi)
+for k in range(3): np.add.at(vn, Fi[:, k], fn_)
+vn /= np.linalg.norm(vn, axis=1, keepdims=True)
+Ti = np.eye(4); Ti[:3, :3] = synth.rot_z(1.5) @ synth.rot_x(-1.0); Ti[:3, 3] = [0.4, -0.3, 0.5]
+src = (Vi[::3] @ np.linalg.inv(Ti)[:3, :3].T + np.linalg.inv(Ti)[:3, 3])
+r = ctx.icp_point_to_plane(src, Vi, vn, 3.0)
+ms = wall(lambda: ctx.icp_point_to_plane(src, Vi, vn, 3.0), reps=2)
+fr["icp_20k_x_60k"] = {"ms_total": ms, "iterations": r["iterations"], "ms_per_iteration": ms / (r["iterations"] + 1),
+                       "fitness": r["fitness"], "inlier_rmse": r["inlier_rmse"], "max_abs_error_vs_applied_pose": float(np.abs(r["transformation"] - Ti).max())}
+out["f_rows"] = fr
+print("f_rows", json.dumps(fr), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_report.json"), "w"), indent=1)
