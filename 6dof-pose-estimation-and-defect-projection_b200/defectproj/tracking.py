@@ -35,16 +35,32 @@ class DefectTracker:
         self.threshold = heatmap_threshold
         self.intersection_pcds = []
         self.previous_transformation = None
-        self.hist = np.zeros(len(self.F), np.int64)
-        self.fmax = np.zeros(len(self.F), np.float32)
-        self.vmax = np.zeros(len(self.V), np.float32)
         self.mesh_in_camera = None
+        # the tracker's own context: its device accumulators are never reset, so the per-face histogram and the
+        # per-face / per-vertex maxima persist across detections without leaving the GPU
+        from .core import Context
+        self.ctx = Context(_dp.get_context().device)
+        self.ctx.set_mesh(self.V, self.F)
+        self.ctx.build_bvh()
+        self.ctx.accum_reset()
+
+    @property
+    def hist(self):
+        return self.ctx.accum_get()[0]
+
+    @property
+    def fmax(self):
+        return self.ctx.accum_get()[1]
+
+    @property
+    def vmax(self):
+        return self.ctx.accum_get()[2]
 
     def add_detection(self, heatmap, current_transformation):
         """One defect-detection frame.  ``current_transformation`` is the ICP result (camera -> model); the mesh is
         posed by its inverse and by inv(color_to_depth), exactly the product ray_tracing applies (:549-550)."""
         cur = np.asarray(current_transformation, dtype=np.float64)
-        ctx = _dp._scene(self.V, self.F)
+        ctx = self.ctx
         heat = np.asarray(heatmap)
         if heat.dtype not in (np.float32, np.float64):
             heat = heat.astype(np.float64)
@@ -53,15 +69,10 @@ class DefectTracker:
         T_depth = np.linalg.inv(cur)
         T = np.linalg.inv(self.color_to_depth) @ T_depth
         ctx.pose_mesh(T)
-        ctx.accum_reset()
         res = ctx.project(heat, self.K, None, self.threshold, frame="camera", accumulate=True,
                           want=("pixel", "t_hit", "face", "point64"))
         pix = res["pixel"].astype(np.int64)
         inten = heat.reshape(-1)[pix]
-        hist, fmax, vmax = ctx.accum_get()
-        self.hist += hist
-        np.maximum(self.fmax, fmax, out=self.fmax)
-        np.maximum(self.vmax, vmax, out=self.vmax)
         # step 3: earlier clouds follow the object
         if self.previous_transformation is not None:
             rel = relative_transformation(cur, self.previous_transformation)
@@ -82,5 +93,5 @@ class DefectTracker:
         """What update_dash_data ships (:205), plus the accumulated per-face arrays."""
         from .web_vis import build_payload
         p = build_payload(self.intersection_pcds, self.mesh_in_camera, with_face_intensity=False)
-        p["face_hits"], p["face_intensity"], p["vertex_intensity"] = self.hist, self.fmax, self.vmax
+        p["face_hits"], p["face_intensity"], p["vertex_intensity"] = self.ctx.accum_get()
         return p
