@@ -16,6 +16,8 @@
 #include "dp_internal.cuh"
 
 #include <math.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 namespace dp {
@@ -47,21 +49,32 @@ __device__ __forceinline__ void tri_box(const float *__restrict__ V, const int32
     }
 }
 
-// bounds_u[0..2] = min (ordered uint), [3..5] = max, [6] = max |coordinate| (float bits)
-__global__ void k_scene_bounds(const float *__restrict__ V, const int32_t *__restrict__ F, long long n,
-                               unsigned *bounds_u)
+// bounds_u[0..2] = min (ordered uint), [3..5] = max.  Grid-stride loop, warp then block reduction, six atomics per
+// block (one atomic set per warp made the kernel atomics-bound: 0.61 ms at 5M triangles).
+__global__ void __launch_bounds__(256)
+k_scene_bounds(const float *__restrict__ V, const int32_t *__restrict__ F, long long n, unsigned *bounds_u)
 {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    __shared__ unsigned s_mn[8][3], s_mx[8][3];
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (i < n) tri_box(V, F, i, lo, hi);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float a[3], b[3];
+        tri_box(V, F, i, a, b);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], a[k]); hi[k] = fmaxf(hi[k], b[k]); }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const unsigned mn = __reduce_min_sync(0xffffffffu, f2ord(lo[k]));
         const unsigned mx = __reduce_max_sync(0xffffffffu, f2ord(hi[k]));
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&bounds_u[k], mn);
-            atomicMax(&bounds_u[3 + k], mx);
-        }
+        if (lane == 0) { s_mn[warp][k] = mn; s_mx[warp][k] = mx; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned mn = s_mn[0][threadIdx.x], mx = s_mx[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) { mn = min(mn, s_mn[w][threadIdx.x]); mx = max(mx, s_mx[w][threadIdx.x]); }
+        atomicMin(&bounds_u[threadIdx.x], mn);
+        atomicMax(&bounds_u[3 + threadIdx.x], mx);
     }
 }
 
@@ -132,31 +145,22 @@ k_rs_hist(const uint32_t *__restrict__ keys, long long n, int shift, uint32_t *_
     table[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of table[0..m) in place, single block, 16 consecutive entries per thread and round
-constexpr int SCAN_ITEMS = 16;
-__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *table, long long m)
+// Digit table: table[d * nb + b] = count of digit d in tile b.  One block per digit scans its row in place
+// (exclusive, over the tiles) and leaves the row total in totals[d]; the scatter kernel adds the exclusive scan of
+// the 256 totals itself.
+__global__ void __launch_bounds__(256) k_rs_scan_rows(uint32_t *table, int nb, uint32_t *totals)
 {
-    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_warp[8];
     __shared__ unsigned s_carry;
+    uint32_t *row = table + (long long)blockIdx.x * nb;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < m; base += 1024 * SCAN_ITEMS) {
-        const long long i0 = base + (long long)threadIdx.x * SCAN_ITEMS;
-        unsigned v[SCAN_ITEMS];
-        unsigned sum = 0;
-        if (i0 + SCAN_ITEMS <= m) {
+    for (int base = 0; base < nb; base += 256 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        unsigned v[4], sum = 0;
 #pragma unroll
-            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
-                const uint4 x = reinterpret_cast<const uint4 *>(table + i0)[q];
-                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < SCAN_ITEMS; ++q) v[q] = i0 + q < m ? table[i0 + q] : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < SCAN_ITEMS; ++q) { const unsigned x = v[q]; v[q] = sum; sum += x; }   // thread-local exclusive
+        for (int q = 0; q < 4; ++q) { const unsigned x = i0 + q < nb ? row[i0 + q] : 0u; v[q] = sum; sum += x; }
         unsigned inc = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -165,40 +169,27 @@ __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *table, long long m)
         }
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        if (warp == 0) {
-            const unsigned w = s_warp[lane];
-            unsigned winc = w;
+        unsigned woff = 0, wtot = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, winc, d);
-                if (lane >= d) winc += y;
-            }
-            s_warp[lane] = winc - w;
-        }
+        for (int w = 0; w < 8; ++w) { const unsigned c = s_warp[w]; if (w < warp) woff += c; wtot += c; }
+        const unsigned off = s_carry + woff + inc - sum;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (i0 + q < nb) row[i0 + q] = off + v[q];
         __syncthreads();
-        const unsigned carry = s_carry;
-        const unsigned off = carry + s_warp[warp] + inc - sum;
-        if (i0 + SCAN_ITEMS <= m) {
-#pragma unroll
-            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
-                reinterpret_cast<uint4 *>(table + i0)[q] =
-                    make_uint4(off + v[4 * q], off + v[4 * q + 1], off + v[4 * q + 2], off + v[4 * q + 3]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < SCAN_ITEMS; ++q)
-                if (i0 + q < m) table[i0 + q] = off + v[q];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = off + sum;
+        if (threadIdx.x == 0) s_carry += wtot;
         __syncthreads();
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t *__restrict__ keys_out,
-             uint32_t *__restrict__ vals_out, long long n, int shift, const uint32_t *__restrict__ table, int nblocks)
+             uint32_t *__restrict__ vals_out, long long n, int shift, const uint32_t *__restrict__ table, int nblocks,
+             const uint32_t *__restrict__ totals)
 {
     __shared__ unsigned cnt[RS_WARPS][256];
+    __shared__ unsigned s_wsum[RS_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < RS_WARPS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
@@ -223,8 +214,22 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
     }
     __syncthreads();
     {
+        // exclusive scan of the 256 digit totals (thread d owns digit d)
+        const unsigned tot = totals[tid];
+        unsigned inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        unsigned dbase = inc - tot;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w)
+            if (w < warp) dbase += s_wsum[w];
         // thread d turns the per-warp counts of digit d into starting offsets
-        unsigned run = table[(long long)tid * nblocks + blockIdx.x];
+        unsigned run = dbase + table[(long long)tid * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const unsigned c = cnt[w][tid];
@@ -382,18 +387,22 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
 // produced by the group, one candidate child per lane (the levels near the root hold 1, 8, 64 ... nodes, so the
 // latency of one node is the latency of the level).
 // ------------------------------------------------------------------------------------------
+// MODE 0: selection and emission fused (small levels: one launch, lowest latency)
+// MODE 1: selection only, ONE THREAD per node, result to `sel` (large levels: all lanes busy with the serial walk)
+// MODE 2: emission only, eight lanes per node, selection read from `sel`
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_collapse(long long n, long long begin, long long end, const int32_t *__restrict__ left,
                            const int32_t *__restrict__ right, const int32_t *__restrict__ first,
                            const int32_t *__restrict__ last, const float *__restrict__ blo,
                            const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
                            WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
-                           float c_prim, int greedy_mode, int32_t *wparent, int dp_max_count)
+                           float c_prim, int greedy_mode, int32_t *wparent, int dp_max_count, int32_t *sel)
 {
     const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long w = begin + (gt >> 3);
+    const long long w = begin + (MODE == 1 ? gt : (gt >> 3));
     if (w >= end) return;                                   // whole groups leave together
-    const int gl = (int)(gt & 7), lane32 = threadIdx.x & 31;
+    const int gl = MODE == 1 ? 0 : (int)(gt & 7), lane32 = threadIdx.x & 31;
     const unsigned gmask = 0xffu << (lane32 & 24);
     const int gbase = lane32 & 24;
     const int32_t r = wroot[w];
@@ -417,8 +426,8 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
     // cost tables decide the cut of subtrees of up to dp_max_count triangles (0 = all); above that the greedy
     // largest-area expansion keeps the upper levels balanced
     const bool use_dp = ctab != nullptr && (dp_max_count <= 0 || count(r) <= dp_max_count);
-    if (gl != 0) {
-        // lanes 1..7 wait for lane 0's choice
+    if (gl != 0 || MODE == 2) {
+        // lanes 1..7 wait for lane 0's choice; MODE 2 reads it below
     } else if (use_dp) {
         // cost-optimal cut of the binary subtree (tables from k_binfit); `inner` marks the children that become
         // wide nodes themselves
@@ -486,9 +495,21 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
             ++nc;
         }
     }
-    if (gl == 0 && !use_dp)
+    if (MODE != 2 && gl == 0 && !use_dp)
         for (int c = 0; c < nc; ++c)
             if (expandable(cand[c])) inner_mask |= 1u << c;
+    if (MODE == 1) {
+        int32_t *o = sel + 9 * (w - begin);
+        for (int c = 0; c < 8; ++c) o[c] = c < nc ? cand[c] : -1;
+        o[8] = nc | (int)(inner_mask << 8);
+        return;
+    }
+    if (MODE == 2 && gl == 0) {
+        const int32_t *o = sel + 9 * (w - begin);
+        for (int c = 0; c < 8; ++c) cand[c] = o[c];
+        nc = o[8] & 0xff;
+        inner_mask = (unsigned)o[8] >> 8;
+    }
     // ---- the group takes over: candidate c lives in lane c
     nc = __shfl_sync(gmask, nc, gbase);
     inner_mask = __shfl_sync(gmask, inner_mask, gbase);
@@ -804,7 +825,7 @@ cudaError_t ensure_scratch(void **scratch, size_t *have, size_t need)
 size_t radix_table_entries(int64_t n)
 {
     const int64_t nb = (n + RS_TILE - 1) / RS_TILE;
-    return (size_t)(256 * (nb > 0 ? nb : 1));
+    return (size_t)(256 * (nb > 0 ? nb : 1) + 256);      // counts per (digit, tile) + the 256 digit totals
 }
 
 cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
@@ -817,8 +838,8 @@ cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp,
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
         k_rs_hist<<<nb, RS_THREADS, 0, s>>>(ki, n, shift, table, nb);
-        k_rs_scan<<<1, 1024, 0, s>>>(table, 256ll * nb);
-        k_rs_scatter<<<nb, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, table, nb);
+        k_rs_scan_rows<<<256, 256, 0, s>>>(table, nb, table + 256ll * nb);
+        k_rs_scatter<<<nb, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, table, nb, table + 256ll * nb);
         uint32_t *t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
     }
@@ -856,7 +877,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     const long long n = nF;
     const size_t N = (size_t)(n > 0 ? n : 1);
     size_t need = 4096 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
-                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + 1024;
+                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + (9 * (N / 2 + 64) * 4 + 256) + 1024;
     if ((e = ensure_scratch(scratch, scratch_bytes, need)) != cudaSuccess) return e;
     Bump b{static_cast<char *>(*scratch)};
     unsigned *bounds_u = b.take<unsigned>(8);
@@ -871,6 +892,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     float *blo = b.take<float>(2 * N * 3), *bhi = b.take<float>(2 * N * 3);
     int *flags = b.take<int>(N);
     int32_t *wroot = b.take<int32_t>(N);
+    int32_t *selbuf = b.take<int32_t>(9 * (N / 2 + 64));       // selection of one level (two-phase collapse)
     float *ctab = knob_sah_collapse() == 1 ? b.take<float>(8 * N) : nullptr;
     const float c_prim = knob_c_prim();
 
@@ -882,7 +904,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     {
         const unsigned init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
         if ((e = cudaMemcpyAsync(bounds_u, init, sizeof(init), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
-        if (n > 0) k_scene_bounds<<<blocks_for(n, 256), 256, 0, s>>>(V, F, n, bounds_u);
+        if (n > 0) k_scene_bounds<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(V, F, n, bounds_u);
         k_finish_bounds<<<1, 1, 0, s>>>(bounds_u, sbounds, out.d_scale, n);
     }
     if (n == 0) {
@@ -924,8 +946,19 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     int L = 0;
     while (begin < end) {
         if (L + 1 >= 127) return cudaErrorInvalidValue;
-        k_collapse<<<blocks_for((end - begin) * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals,
-                                                                wroot, out.nodes, topo.tri_face, counters, ctab, c_prim, knob_sah_collapse(), topo.wparent, knob_dp_max_count());
+        const long long lvl = end - begin;
+        if (lvl < 2048 || lvl > (long long)(N / 2 + 64)) {
+            k_collapse<0><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
+                                                               out.nodes, topo.tri_face, counters, ctab, c_prim,
+                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf);
+        } else {
+            k_collapse<1><<<blocks_for(lvl, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
+                                                               out.nodes, topo.tri_face, counters, ctab, c_prim,
+                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf);
+            k_collapse<2><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
+                                                               out.nodes, topo.tri_face, counters, ctab, c_prim,
+                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf);
+        }
         unsigned cnt[2];
         if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;

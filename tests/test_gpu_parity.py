@@ -503,9 +503,10 @@ def test_facade_matches_reference_run(golden, tmp_path, built_lib):
 
 
 # ------------------------------------------------------------------------------------------ full size
-@pytest.mark.parametrize("cfg", ["c2_500k", "ns_1m"])
+@pytest.mark.parametrize("cfg", ["c2_500k", "ns_1m", "c4_5m"])
 def test_full_size_dense_frame(ctx, orc, cfg):
-    """BASELINE configs[1] (and the north-star 1M-triangle mesh): 1024x1024 dense frame, every ray checked
+    """BASELINE configs[1], the north-star 1M-triangle mesh and configs[3] (5M triangles, a hierarchy larger than L2,
+    which also switches the traversal's L1 prefetch on): 1024x1024 dense frame, every ray checked
     against the oracle's own BVH caster, plus the size-independent properties."""
     import torch
     V, F = synth.param_mesh(*synth.MESH_CONFIGS[cfg], seed=0, scale=6.0)
