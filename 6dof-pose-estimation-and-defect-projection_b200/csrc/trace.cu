@@ -172,6 +172,9 @@ __device__ __forceinline__ float qf_i2f(unsigned w, int i) { return (float)((w >
 // 5M triangles (BVH 290 MB, beyond L2), -1.5 % at 500k (BVH 29 MB, L2-resident), so the launcher turns it on only
 // for hierarchies larger than PREFETCH_MIN_BYTES.
 constexpr size_t PREFETCH_MIN_BYTES = 96u << 20;
+#ifndef DP_PREFETCH_CHILDREN
+#define DP_PREFETCH_CHILDREN 0
+#endif
 __device__ __forceinline__ void prefetch_l1(const void *p, bool on)
 {
     if (on) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -254,6 +257,16 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
         }
     }
     uint2 ng = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
+#if DP_PREFETCH_CHILDREN
+    if (pf && (hitmask & 0xff000000u)) {
+        // the inner children of this node are contiguous: start pulling their lines towards L2 now, long before the
+        // farther ones are popped from the stack
+        const char *cb = reinterpret_cast<const char *>(nodes + w1.x);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cb));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + 256));
+    }
+#endif
     tmask = hitmask & 0x00ffffffu;
     tbase = w1.y;
     if (!(ng.y & 0xff000000u)) {
@@ -328,8 +341,11 @@ __device__ __forceinline__ void tri_batch(const RayState &r, const TriRec *__res
 #ifndef DP_MIN_BLOCKS
 #define DP_MIN_BLOCKS 7      // 72 registers: 7 CTAs (28 warps) per SM; measured ~9 % faster than 80 registers / 6 CTAs
 #endif
-template <bool STATS, int SRC>
-__global__ void __launch_bounds__(TR_THREADS, DP_MIN_BLOCKS)
+#ifndef DP_MIN_BLOCKS_BIG
+#define DP_MIN_BLOCKS_BIG 5  // hierarchies beyond L2 (5M triangles: 0.511 -> 0.49 ms): fewer packets share an SM's L1
+#endif
+template <bool STATS, int SRC, int MINB>
+__global__ void __launch_bounds__(TR_THREADS, MINB)
 k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
         const float4 *__restrict__ dir4, const float *__restrict__ rays6, const float *__restrict__ intensity,
         const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
@@ -601,20 +617,23 @@ int knob_tiled()
     return g_tiled;
 }
 
-int g_trace_grid = 0;     // persistent grid: CTAs resident on the device at once
+int g_trace_grid[2] = {0, 0};     // persistent grid (CTAs resident on the device at once) of the two occupancy variants
 
-cudaError_t trace_grid(int *grid)
+cudaError_t trace_grid(int big, int *grid)
 {
-    if (g_trace_grid == 0) {
+    if (g_trace_grid[big] == 0) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaError_t e;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0>, TR_THREADS, 0)) != cudaSuccess)
-            return e;
-        g_trace_grid = sms * (per_sm > 0 ? per_sm : 1);
+        if (big) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS_BIG>, TR_THREADS, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS>, TR_THREADS, 0);
+        if (e != cudaSuccess) return e;
+        const int target = big ? DP_MIN_BLOCKS_BIG : DP_MIN_BLOCKS;
+        if (per_sm > target) per_sm = target;       // the variant's point is its residency, not just its registers
+        g_trace_grid[big] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    *grid = g_trace_grid;
+    *grid = g_trace_grid[big];
     return cudaSuccess;
 }
 
@@ -653,21 +672,20 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
     int grid = 0;
-    if ((e = trace_grid(&grid)) != cudaSuccess) return e;
+    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
+    if ((e = trace_grid(pf, &grid)) != cudaSuccess) return e;
     const long long want = (n_max + TR_THREADS - 1) / TR_THREADS;
     if (want < grid) grid = (int)want;
     if (!counter_zeroed && (e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
-    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
     if (knob_order() == 0) { ord_prev = nullptr; ord_next = nullptr; }
-    if (stats)
-        k_trace<true, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,
-                                                     total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter,
-                                                     d_hits, stats, knob_tiled(), ord_prev, ord_next, pf);
-    else
-        k_trace<false, 0><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n,
-                                                      n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr,
-                                                      work_counter, d_hits, stats, knob_tiled(), ord_prev, ord_next, pf);
+#define DP_LAUNCH_TRACE0(ST, MB)                                                                                        \
+    k_trace<ST, 0, MB><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,   \
+                                                   total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, d_hits, \
+                                                   stats, knob_tiled(), ord_prev, ord_next, pf)
+    if (stats) { if (pf) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS); }
+    else       { if (pf) DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS); }
+#undef DP_LAUNCH_TRACE0
     return cudaGetLastError();
 }
 
@@ -677,18 +695,18 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
     if (n <= 0) return cudaSuccess;
     cudaError_t e;
     int grid = 0;
-    if ((e = trace_grid(&grid)) != cudaSuccess) return e;
+    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
+    if ((e = trace_grid(pf, &grid)) != cudaSuccess) return e;
     const long long want = (n + TR_THREADS - 1) / TR_THREADS;
     if (want < grid) grid = (int)want;
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a{nullptr, nullptr, nullptr, nullptr};
-    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
-    if (stats)
-        k_trace<true, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0,
-                                                     0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf);
-    else
-        k_trace<false, 1><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n,
-                                                      0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf);
+#define DP_LAUNCH_TRACE1(ST, MB)                                                                                          \
+    k_trace<ST, 1, MB><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0, 0, 0, \
+                                                   nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf)
+    if (stats) { if (pf) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS); }
+    else       { if (pf) DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS); }
+#undef DP_LAUNCH_TRACE1
     return cudaGetLastError();
 }
 
