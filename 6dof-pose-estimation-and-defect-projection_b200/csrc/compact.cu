@@ -19,9 +19,6 @@ constexpr int CT_THREADS = 256;
 constexpr int CT_CHUNKS = 4;                       // 16-byte (f32) / 32-byte (f64) loads per thread
 constexpr int CT_TILE = CT_THREADS * CT_CHUNKS * 4;  // 4096 pixels per tile
 
-constexpr unsigned long long ST_AGG = 1ull << 62;   // tile aggregate published
-constexpr unsigned long long ST_INC = 2ull << 62;   // inclusive prefix published
-constexpr unsigned long long ST_VAL = (1ull << 62) - 1;
 
 template <typename T>
 struct Vec4 {
@@ -101,27 +98,13 @@ k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__
         if (lane == 31) s_block_total = inc;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
         const unsigned long long total = s_block_total;
-        unsigned long long prefix = 0;
-        if (tile == 0) {
-            atomicExch(&state[0], ST_INC | total);
-        } else {
-            atomicExch(&state[tile], ST_AGG | total);
-            long long j = (long long)tile - 1;
-            for (;;) {
-                unsigned long long s;
-                do {
-                    s = *reinterpret_cast<volatile unsigned long long *>(&state[j]);
-                } while ((s >> 62) == 0);
-                prefix += s & ST_VAL;
-                if (s & ST_INC) break;
-                --j;
-            }
-            atomicExch(&state[tile], ST_INC | (prefix + total));
+        const unsigned long long prefix = lookback_exclusive_prefix(state, tile, total, lane);
+        if (lane == 0) {
+            s_base = (long long)prefix;
+            if (tile_base + CT_TILE >= n) *d_count = (long long)(prefix + total);   // last tile
         }
-        s_base = (long long)prefix;
-        if (tile_base + CT_TILE >= n) *d_count = (long long)(prefix + total);   // last tile
     }
     __syncthreads();
     const long long base = s_base;

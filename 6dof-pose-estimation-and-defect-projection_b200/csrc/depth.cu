@@ -18,7 +18,6 @@ namespace {
 constexpr int DS_THREADS = 256;
 constexpr int DS_ITEMS = 8;
 constexpr int DS_TILE = DS_THREADS * DS_ITEMS;
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_max(const T *__restrict__ a, long long n, double *out_max, int *out_nan)
@@ -57,7 +56,7 @@ k_depth_select(const T *__restrict__ heat, int H, int W, const uint16_t *__restr
                const double *__restrict__ d_max, double thr, double fx, double fy, double cx, double cy,
                double *__restrict__ out4, long long cap, unsigned long long *scratch, long long *d_count)
 {
-    __shared__ unsigned s_tile, s_warp_tot[DS_THREADS / 32], s_warp_off[DS_THREADS / 32], s_total;
+    __shared__ unsigned s_tile, s_warp_tot[DS_THREADS / 32], s_warp_off[DS_THREADS / 32];
     __shared__ long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned *>(scratch), 1u);
@@ -95,28 +94,15 @@ k_depth_select(const T *__restrict__ heat, int H, int W, const uint16_t *__restr
     }
     if (lane == 31) s_warp_tot[warp] = inc;
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
         unsigned run = 0;
-        for (int w = 0; w < DS_THREADS / 32; ++w) { s_warp_off[w] = run; run += s_warp_tot[w]; }
-        s_total = run;
+        for (int w = 0; w < DS_THREADS / 32; ++w) { const unsigned c = s_warp_tot[w]; if (lane == 0) s_warp_off[w] = run; run += c; }
         const unsigned long long total = run;
-        unsigned long long prefix = 0;
-        if (tile == 0) {
-            atomicExch(&state[0], ST_INC | total);
-        } else {
-            atomicExch(&state[tile], ST_AGG | total);
-            long long j = (long long)tile - 1;
-            for (;;) {
-                unsigned long long s;
-                do { s = *reinterpret_cast<volatile unsigned long long *>(&state[j]); } while ((s >> 62) == 0);
-                prefix += s & ST_VAL;
-                if (s & ST_INC) break;
-                --j;
-            }
-            atomicExch(&state[tile], ST_INC | (prefix + total));
+        const unsigned long long prefix = lookback_exclusive_prefix(state, tile, total, lane);
+        if (lane == 0) {
+            s_base = (long long)prefix;
+            if ((long long)(tile + 1) * DS_TILE >= n) *d_count = (long long)(prefix + total);
         }
-        s_base = (long long)prefix;
-        if ((long long)(tile + 1) * DS_TILE >= n) *d_count = (long long)(prefix + total);
     }
     __syncthreads();
     long long off = s_base + s_warp_off[warp] + (inc - cnt);

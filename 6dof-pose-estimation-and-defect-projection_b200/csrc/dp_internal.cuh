@@ -66,6 +66,46 @@ struct TraceStats {
     unsigned *ray_nodes;   // optional [n]: nodes fetched by each ray (debug)
 };
 
+// ---- decoupled look-back shared by the order-preserving selections (compact.cu, depth.cu, prep.cu) --------
+// state[tile] holds (flag << 62 | value): flag 1 = the tile's own count is published, 2 = its inclusive prefix is.
+// Called by ALL 32 lanes of one warp of the tile with the tile's count; returns the exclusive prefix of the tile
+// (the same value in every lane) after publishing the tile's inclusive prefix.  Tiles take their id from an atomic
+// ticket, so a predecessor a lane waits for is always already running.  32 predecessors are inspected per round.
+#ifdef __CUDACC__
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_VAL = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned long long *state, unsigned tile,
+                                                                        unsigned long long total, int lane)
+{
+    unsigned long long prefix = 0;
+    if (tile == 0) {
+        if (lane == 0) atomicExch(&state[0], LB_INC | total);
+        return 0;
+    }
+    if (lane == 0) atomicExch(&state[tile], LB_AGG | total);
+    long long j0 = (long long)tile - 1;                      // lane l looks at tile j0 - l
+    for (;;) {
+        const long long j = j0 - lane;
+        unsigned long long sv = LB_INC;                      // "tiles" before the first one: inclusive prefix 0
+        if (j >= 0) {
+            do {
+                sv = *reinterpret_cast<volatile unsigned long long *>(&state[j]);
+            } while ((sv >> 62) == 0);
+        }
+        const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv & LB_INC) != 0);
+        const int first_inc = __ffs(inc_mask) - 1;           // nearest predecessor with an inclusive prefix
+        unsigned long long v = (first_inc < 0 || lane <= first_inc) ? (sv & LB_VAL) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        prefix += v;
+        if (first_inc >= 0) break;
+        j0 -= 32;
+    }
+    if (lane == 0) atomicExch(&state[tile], LB_INC | (prefix + total));
+    return prefix;
+}
+#endif
+
 // ---- compact.cu ----------------------------------------------------------------------------
 // tile_state: [ntiles+1] u64 scratch (zeroed by the call); d_count: device int64 total;
 // d_frame_count: [nframes] device int64 (zeroed by the call) or nullptr.

@@ -151,7 +151,6 @@ __global__ void __launch_bounds__(256) k_transform_points(double *__restrict__ p
 constexpr int PK_THREADS = 256;
 constexpr int PK_ITEMS = 4;
 constexpr int PK_TILE = PK_THREADS * PK_ITEMS;
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
 
 template <typename T>
 __global__ void __launch_bounds__(PK_THREADS)
@@ -184,27 +183,15 @@ k_pack_hits(const T *__restrict__ inten, const int32_t *__restrict__ face, const
     }
     if (lane == 31) s_warp_tot[warp] = inc;
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
         unsigned run = 0;
-        for (int w = 0; w < PK_THREADS / 32; ++w) { s_warp_off[w] = run; run += s_warp_tot[w]; }
+        for (int w = 0; w < PK_THREADS / 32; ++w) { const unsigned c = s_warp_tot[w]; if (lane == 0) s_warp_off[w] = run; run += c; }
         const unsigned long long total = run;
-        unsigned long long prefix = 0;
-        if (tile == 0) {
-            atomicExch(&state[0], ST_INC | total);
-        } else {
-            atomicExch(&state[tile], ST_AGG | total);
-            long long j = (long long)tile - 1;
-            for (;;) {
-                unsigned long long s;
-                do { s = *reinterpret_cast<volatile unsigned long long *>(&state[j]); } while ((s >> 62) == 0);
-                prefix += s & ST_VAL;
-                if (s & ST_INC) break;
-                --j;
-            }
-            atomicExch(&state[tile], ST_INC | (prefix + total));
+        const unsigned long long prefix = lookback_exclusive_prefix(state, tile, total, lane);
+        if (lane == 0) {
+            s_base = (long long)prefix;
+            if ((long long)(tile + 1) * PK_TILE >= n) *d_count = (long long)(prefix + total);
         }
-        s_base = (long long)prefix;
-        if ((long long)(tile + 1) * PK_TILE >= n) *d_count = (long long)(prefix + total);
     }
     __syncthreads();
     if (!m) return;
