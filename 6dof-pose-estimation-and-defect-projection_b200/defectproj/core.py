@@ -434,6 +434,44 @@ class Context:
         out["m"] = m.value
         return out
 
+    def pack_hits_device(self, intensity, face=None, pixel=None, point64=None, T=None,
+                         want=("points", "colors", "face", "pixel", "intensity"), stream=None):
+        """pack_hits on CUDA tensors (the per-ray outputs of project_device): nothing but the count crosses PCIe.
+        intensity: float32/float64 [n]; face: int32 [n]; pixel: int32 [n] (bits of the uint32 index); point64:
+        float64 [n,3].  Returns CUDA tensors cut to the number of selected rays, plus 'm'."""
+        import torch
+        if not intensity.is_cuda or intensity.dtype not in (torch.float32, torch.float64):
+            raise ValueError("intensity must be a float32/float64 CUDA tensor")
+        dev, n = intensity.device, intensity.numel()
+        chk = {"face": (face, torch.int32, n), "pixel": (pixel, torch.int32, n), "point64": (point64, torch.float64, 3 * n)}
+        for name, (t, dt, cnt) in chk.items():
+            if t is not None and (not t.is_cuda or t.dtype != dt or t.numel() != cnt or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous {dt} CUDA tensor matching the intensities")
+        if not intensity.is_contiguous():
+            intensity = intensity.contiguous()
+        Tm = None if T is None else np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        out = {}
+        if "points" in want and point64 is not None:
+            out["points"] = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        if "colors" in want:
+            out["colors"] = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        if "face" in want and face is not None:
+            out["face"] = torch.empty(n, dtype=torch.int32, device=dev)
+        if "pixel" in want:
+            out["pixel"] = torch.empty(n, dtype=torch.int32, device=dev)
+        if "intensity" in want:
+            out["intensity"] = torch.empty(n, dtype=torch.float64, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev)
+        m = C.c_int64(0)
+        self._check(self._L.dp_pack_hits(self._h, _ptr(intensity), DP_F64 if intensity.dtype == torch.float64 else DP_F32,
+                                         _ptr(face), _ptr(pixel), _ptr(point64), n, _ptr(Tm), _ptr(out.get("points")),
+                                         _ptr(out.get("colors")), _ptr(out.get("face")), _ptr(out.get("pixel")),
+                                         _ptr(out.get("intensity")), n, C.byref(m), DP_DEVICE, self._stream(stream)))
+        out = {k: v[:m.value] for k, v in out.items()}
+        out["m"] = m.value
+        return out
+
     # ------------------------------------------------------------------ upstream of the path (8f #4)
     def icp_point_to_plane(self, source, target, target_normals, max_correspondence_distance, init=None,
                            max_iteration=30, relative_fitness=1e-6, relative_rmse=1e-6, want_correspondence=False,

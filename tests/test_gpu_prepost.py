@@ -139,6 +139,36 @@ def test_pack_hits_equals_oracle(ctx, orc, dt, n):
     assert none["m"] == 0 and none["points"].shape == (0, 3)
 
 
+def test_pack_hits_device_resident_chain(ctx, orc):
+    """project_device -> pack_hits_device: the viewer payload is built from the per-ray device buffers; only the
+    counts cross PCIe.  Equals the host-buffer path and the oracle."""
+    torch = pytest.importorskip("torch")
+    V, F = synth.param_mesh(40, 25, seed=4)
+    K, H, W = synth.camera_720p()
+    pose = synth.fixed_pose()
+    ctx.set_mesh(V, F).build_bvh()
+    heat_np = synth.gaussian_heatmap((H, W), dtype=np.float32)
+    heat = torch.from_numpy(heat_np)[None].cuda()
+    n = H * W
+    o = dict(pixel=torch.empty(n, dtype=torch.int32, device="cuda"), intensity=torch.empty(n, device="cuda"),
+             face=torch.empty(n, dtype=torch.int32, device="cuda"), point64=torch.empty((n, 3), dtype=torch.float64, device="cuda"))
+    nr, nh = ctx.project_device(heat, K, pose[None], 0.5, "object", False, out=o, sync=True)
+    T = np.eye(4)
+    T[:3, :3] = synth.rot_y(1.5)
+    T[:3, 3] = [-32.0, -2.0, 4.0]
+    dev = ctx.pack_hits_device(o["intensity"][:nr], o["face"][:nr], o["pixel"][:nr], o["point64"][:nr], T=T)
+    assert dev["m"] == nh and all(v.is_cuda for k, v in dev.items() if k != "m")
+    host = ctx.pack_hits(o["intensity"][:nr].cpu().numpy(), o["face"][:nr].cpu().numpy(),
+                         o["pixel"][:nr].cpu().numpy().view(np.uint32), o["point64"][:nr].cpu().numpy(), T=T)
+    ref = orc.pack_hits(o["intensity"][:nr].cpu().numpy(), o["face"][:nr].cpu().numpy(), o["point64"][:nr].cpu().numpy(), T)
+    for k in ("points", "colors", "face", "intensity"):
+        assert np.array_equal(dev[k].cpu().numpy(), host[k]), k
+    assert np.array_equal(dev["pixel"].cpu().numpy().view(np.uint32), host["pixel"])
+    assert np.array_equal(host["colors"], ref["colors"]) and np.array_equal(host["points"], ref["points"])
+    with pytest.raises(ValueError):
+        ctx.pack_hits_device(o["intensity"][:nr], o["face"][:nr - 1])
+
+
 def test_pack_hits_capacity_and_arguments(ctx, built_lib):
     import ctypes as C
     I = np.ones(16, np.float32)
