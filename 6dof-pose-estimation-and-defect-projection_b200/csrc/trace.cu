@@ -294,7 +294,7 @@ __device__ __forceinline__ long long work_to_slot(long long i, bool tiled, int W
     return (trow * 4 + (l >> 3)) * W + tcol * 8 + (l & 7);
 }
 
-constexpr int TQ_CAP = 64;                      // triangle queue entries per warp (power of two)
+constexpr int TQ_CAP = 256;                     // triangle queue entries per warp (power of two)
 #ifndef DP_TQ_FLUSH
 #define DP_TQ_FLUSH 32
 #endif
@@ -432,23 +432,59 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
                 alive = node_step<STATS>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn, pf);
                 ++steps;
             }
-            // queue this step's triangles, one per lane and round; test whenever 32 are waiting
-            for (;;) {
-                const unsigned contrib = __ballot_sync(0xffffffffu, tmask != 0u);
-                if (!contrib) break;
-                if (tmask) {
-                    const int b = __ffs(tmask) - 1;
-                    tmask &= tmask - 1u;
-                    queue[(qhead + qcount + __popc(contrib & lt)) & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
-                    prefetch_l1(tris + (tbase + b), pf);
+            // queue this step's triangles: one warp prefix sum gives every lane the slots of all its triangles, which
+            // it then fills in a short private loop; the queue is tested 32 pairs at a time
+            if (__any_sync(0xffffffffu, tmask != 0u)) {
+                const unsigned k = __popc(tmask);
+                unsigned inc = k;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += y;
                 }
-                qcount += __popc(contrib);
-                __syncwarp();
-                if (qcount >= TQ_FLUSH) {
-                    const int c = qcount < 32 ? qcount : 32;
-                    tri_batch<STATS>(r, tris, queue, best, qhead, c, lane, nt);
-                    qhead = (qhead + c) & (TQ_CAP - 1);
-                    qcount -= c;
+                const int total = (int)__shfl_sync(0xffffffffu, inc, 31);
+                if (qcount + total > TQ_CAP) {
+                    // does not fit behind what is pending (at most 31 pairs): test those first; a step never yields
+                    // more than 32 x 24 pairs, and more than TQ_CAP only on pathological nodes -> chunked below
+                    if (qcount) {
+                        tri_batch<STATS>(r, tris, queue, best, qhead, qcount, lane, nt);
+                        qhead = (qhead + qcount) & (TQ_CAP - 1);
+                        qcount = 0;
+                    }
+                }
+                if (total <= TQ_CAP) {
+                    unsigned pos = (unsigned)(qhead + qcount) + inc - k;
+                    while (tmask) {
+                        const int b = __ffs(tmask) - 1;
+                        tmask &= tmask - 1u;
+                        queue[pos++ & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
+                        prefetch_l1(tris + (tbase + b), pf);
+                    }
+                    qcount += total;
+                    __syncwarp();
+                    while (qcount >= TQ_FLUSH) {
+                        tri_batch<STATS>(r, tris, queue, best, qhead, 32, lane, nt);
+                        qhead = (qhead + 32) & (TQ_CAP - 1);
+                        qcount -= 32;
+                    }
+                } else {
+                    // more pairs than the queue holds: one per lane and round
+                    for (;;) {
+                        const unsigned contrib = __ballot_sync(0xffffffffu, tmask != 0u);
+                        if (!contrib) break;
+                        if (tmask) {
+                            const int b = __ffs(tmask) - 1;
+                            tmask &= tmask - 1u;
+                            queue[(qhead + qcount + __popc(contrib & lt)) & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
+                        }
+                        qcount += __popc(contrib);
+                        __syncwarp();
+                        if (qcount >= 32) {
+                            tri_batch<STATS>(r, tris, queue, best, qhead, 32, lane, nt);
+                            qhead = (qhead + 32) & (TQ_CAP - 1);
+                            qcount -= 32;
+                        }
+                    }
                 }
             }
         }
