@@ -98,7 +98,8 @@ struct RayState {
     float ox, oy, oz;         // origin
     float ix, iy, iz;         // clamped reciprocal direction
     float px, py, pz;         // slab padding in t
-    unsigned octinv;
+    unsigned order;           // three 8-bit slot masks (bytes 0..2 = bit 2, 1, 0 of the slot index): the slots a ray
+                              // prefers on that bit, nearest child = the hit slot s that maximises s ^ (7 ^ octant)
     uint2 ng;                 // current node group: (child base, hit bits | imask)
     int sp;
     unsigned next;            // index of the node the next step fetches (valid while the ray is alive)
@@ -129,7 +130,8 @@ __device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float
     const float pad_abs = 1.9073486e-6f * (scale + fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))));
     r.px = pad_abs * fabsf(r.ix); r.py = pad_abs * fabsf(r.iy); r.pz = pad_abs * fabsf(r.iz);
     const unsigned oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
-    r.octinv = 7u ^ oct;
+    const unsigned octinv = 7u ^ oct;
+    r.order = ((octinv & 4u) ? 0x0fu : 0xf0u) | (((octinv & 2u) ? 0x33u : 0xccu) << 8) | (((octinv & 1u) ? 0x55u : 0xaau) << 16);
     r.ng = make_uint2(0u, 0x80000000u);      // the root as the only inner child of a virtual group
     r.sp = 0;
 }
@@ -187,13 +189,18 @@ __device__ __forceinline__ void node_select(RayState &r, const WideNode *__restr
 {
     uint2 ng = r.ng;
     const unsigned hits = ng.y;
-    const int bit = 31 - __clz(hits);
-    ng.y &= ~(1u << bit);
+    // inner hits sit at bit 24 + slot; the nearest one is the slot s maximising s ^ octinv: filter the candidates
+    // bit by bit, most significant first (a filter that would leave nothing is skipped)
+    unsigned c = hits >> 24, t;
+    t = c & r.order;          c = t ? t : c;
+    t = c & (r.order >> 8);   c = t ? t : c;
+    t = c & (r.order >> 16);  c = t ? t : c;
+    const unsigned slot = (unsigned)__ffs((int)c) - 1u;
+    ng.y &= ~(0x01000000u << slot);
     if (ng.y & 0xff000000u) {
         if (r.sp < STACK_SMEM) stack[r.sp * TR_THREADS] = ng; else lstack[r.sp - STACK_SMEM] = ng;
         ++r.sp;
     }
-    const unsigned slot = (unsigned)(bit - 24) ^ r.octinv;
     const unsigned rel = __popc(hits & 0xffu & ((1u << slot) - 1u));
     r.next = ng.x + rel;
     const char *np = reinterpret_cast<const char *>(nodes + r.next);
@@ -228,7 +235,6 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
     const unsigned fy0 = sy ? w2.z : w4.x, fy1 = sy ? w2.w : w4.y;
     const unsigned nz0 = sz ? w4.z : w3.x, nz1 = sz ? w4.w : w3.y;
     const unsigned fz0 = sz ? w3.x : w4.z, fz1 = sz ? w3.y : w4.w;
-    const unsigned octinv4 = r.octinv * 0x01010101u;
 
     unsigned hitmask = 0;
 #pragma unroll
@@ -237,11 +243,9 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
         const unsigned nxw = half ? nx1 : nx0, fxw = half ? fx1 : fx0;
         const unsigned nyw = half ? ny1 : ny0, fyw = half ? fy1 : fy0;
         const unsigned nzw = half ? nz1 : nz0, fzw = half ? fz1 : fz0;
-        // four children at a time: bit index of each child in the hit word (inner children are
-        // placed by slot ^ octinv so that the highest set bit is the nearest), and its unary count
-        const unsigned inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;           // bit 4 set <=> inner
-        const unsigned imask4 = (inner4 >> 4) * 0x07u;                          // 0x07 per inner byte
-        const unsigned bidx4 = (meta4 ^ (octinv4 & imask4)) & 0x1f1f1f1fu;
+        // four children at a time: first bit of each child in the hit word and its unary triangle count.  An inner
+        // child is encoded as "one triangle at bit 24 + slot", so both kinds go through the same shift
+        const unsigned off4 = meta4 & 0x1f1f1f1fu;
         const unsigned cbits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -253,7 +257,7 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
             const float tfz = fmaf(qf(fzw, j), adjz, foz);
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
-            if (tmin <= tmax) hitmask |= ((cbits4 >> (8 * j)) & 0xffu) << ((bidx4 >> (8 * j)) & 0xffu);
+            if (tmin <= tmax) hitmask |= ((cbits4 >> (8 * j)) & 0xffu) << ((off4 >> (8 * j)) & 0xffu);
         }
     }
     uint2 ng = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
