@@ -571,7 +571,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
     // t_hit is needed by the hit-point kernel even when the caller does not want it
     if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
-    CK(ctx->dir4.ensure((size_t)cap * 16 + 16), "dp_project: rays");
+    CK(ctx->dir4.ensure((size_t)cap * 32 + 32), "dp_project: rays");
     CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s),
        "dp_project: ray generation");
     CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
@@ -886,12 +886,26 @@ int dp_accum_reset(dp_ctx *ctx, void *stream)
     return DP_OK;
 }
 
+int dp_accum_flush(dp_ctx *ctx, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_flush: no mesh");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(launch_vertex_max(ctx->fmax.as<uint32_t>(), ctx->F.as<int32_t>(), ctx->nF, ctx->vmax.as<uint32_t>(), s), "dp_accum_flush");
+    return DP_OK;
+}
+
 int dp_accum_get(dp_ctx *ctx, int32_t *hist, float *fmax, float *vmax, int mem, void *stream)
 {
     if (!ctx) return DP_E_ARG;
     if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_get: no mesh");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (vmax) {
+        const int rc = dp_accum_flush(ctx, stream);
+        if (rc != DP_OK) return rc;
+    }
     const cudaMemcpyKind kind = mem == DP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (hist && ctx->nF) CK(cudaMemcpyAsync(hist, ctx->hist.p, (size_t)ctx->nF * 4, kind, s), "dp_accum_get");
     if (fmax && ctx->nF) CK(cudaMemcpyAsync(fmax, ctx->fmax.p, (size_t)ctx->nF * 4, kind, s), "dp_accum_get");

@@ -127,12 +127,14 @@ cudaError_t launch_raygen(const uint32_t *pixel, const long long *d_n, int64_t n
                           int64_t n_xf, float4 *dir4, cudaStream_t s);
 cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long long *d_n, int64_t n_max, int H, int W,
                           const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s);
-// dir4[i] = (object-frame direction, frame index bits) of compacted ray i, written by launch_raygen
+// dir4[2i] = origin (object frame), dir4[2i+1] = (direction, frame index bits) of compacted ray i, written by launch_raygen
 cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
                                 bool counter_zeroed = false);
+// per-vertex maxima from the per-face maxima (run when the accumulators are read, not per hit)
+cudaError_t launch_vertex_max(const uint32_t *fmax, const int32_t *F, int64_t nF, uint32_t *vmax, cudaStream_t s);
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
                                 cudaStream_t s);
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,

@@ -410,10 +410,11 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
             if (valid) {
                 slot = work_to_slot(i, tiled, W);
                 if (SRC == 0) {
-                    const float4 d = __ldg(dir4 + slot);
-                    const double *c = xf[__float_as_uint(d.w)].v;
-                    ox = (float)c[13]; oy = (float)c[14]; oz = (float)c[15];
+                    // 32 bytes per ray written by k_raygen: origin (object frame) | direction
+                    const float4 o4 = __ldg(dir4 + 2 * slot), d = __ldg(dir4 + 2 * slot + 1);
+                    ox = o4.x; oy = o4.y; oz = o4.z;
                     dx = d.x; dy = d.y; dz = d.z;
+                    if (has_acc && intensity) prefetch_l1(intensity + slot, true);   // read by the packet epilogue
                 } else {
                     const float *q = rays6 + 6 * slot;
                     ox = q[0]; oy = q[1]; oz = q[2]; dx = q[3]; dy = q[4]; dz = q[5];
@@ -527,12 +528,9 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
                 I = I > 0.0f ? I : 0.0f;
                 const unsigned mx = __reduce_max_sync(peers, __float_as_uint(I));
                 if (lane == __ffs(peers) - 1) {
+                    // per-vertex maxima are derived from fmax when the accumulators are read (launch_vertex_max)
                     atomicAdd(&acc.hist[bf], __popc(peers));
                     atomicMax(&acc.fmax[bf], mx);
-                    const int32_t *f3 = acc.F + 3ll * bf;
-                    atomicMax(&acc.vmax[f3[0]], mx);
-                    atomicMax(&acc.vmax[f3[1]], mx);
-                    atomicMax(&acc.vmax[f3[2]], mx);
                 }
             }
         }
@@ -601,7 +599,10 @@ k_raygen(const uint32_t *__restrict__ pixel, const long long *__restrict__ d_n, 
     d.y = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[3], dcx), __dmul_rn(Ri[4], dcy)), __dmul_rn(Ri[5], dcz));
     d.z = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[6], dcx), __dmul_rn(Ri[7], dcy)), __dmul_rn(Ri[8], dcz));
     d.w = __uint_as_float(fr);
-    dir4[i] = d;
+    // the ray's origin in the object frame (the frame's inverse translation), float32 like the direction
+    const double *ti = xf[fr].v + 13;
+    dir4[2 * i] = make_float4((float)ti[0], (float)ti[1], (float)ti[2], 0.0f);
+    dir4[2 * i + 1] = d;
 }
 
 // hit point in the camera frame: p = d_cam (float64) * t (float32)   (:261-263 with origin 0)
@@ -645,6 +646,20 @@ __global__ void k_compute_rays(const int32_t *__restrict__ xs, const int32_t *__
     rays3[3 * i + 2] = __ddiv_rn(1.0, nrm);
 }
 
+// vmax[v] = max over the faces incident to v of fmax[f]  (== max over the rays that hit those faces: max is
+// associative, so deriving it once per read is bit-identical to accumulating it per hit)
+__global__ void __launch_bounds__(256)
+k_vertex_max(const uint32_t *__restrict__ fmax, const int32_t *__restrict__ F, long long nF, uint32_t *__restrict__ vmax)
+{
+    const long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    const uint32_t m = fmax[f];
+    if (m == 0u) return;
+    atomicMax(&vmax[F[3 * f]], m);
+    atomicMax(&vmax[F[3 * f + 1]], m);
+    atomicMax(&vmax[F[3 * f + 2]], m);
+}
+
 int g_order = -1;
 int knob_order()
 {
@@ -678,6 +693,13 @@ cudaError_t trace_grid(int big, int *grid)
 }
 
 }  // namespace
+
+cudaError_t launch_vertex_max(const uint32_t *fmax, const int32_t *F, int64_t nF, uint32_t *vmax, cudaStream_t s)
+{
+    if (nF <= 0) return cudaSuccess;
+    k_vertex_max<<<(unsigned)((nF + 255) / 256), 256, 0, s>>>(fmax, F, nF, vmax);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
                                 cudaStream_t s)

@@ -58,6 +58,7 @@ SYMBOLS = {
     "dp_icp_point_to_plane": (i32, [vp, vp, i64, vp, vp, i64, f64, vp, i32, f64, f64, vp, C.POINTER(f64), C.POINTER(f64),
                                     C.POINTER(i32), vp, i32, vp]),
     "dp_accum_reset": (i32, [vp, vp]),
+    "dp_accum_flush": (i32, [vp, vp]),
     "dp_accum_get": (i32, [vp, vp, vp, vp, i32, vp]),
     "dp_accum_device_ptrs": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "dp_set_stats": (i32, [vp, i32]),

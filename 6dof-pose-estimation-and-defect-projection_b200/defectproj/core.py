@@ -507,6 +507,10 @@ class Context:
         self._check(self._L.dp_accum_get(self._h, _ptr(hist), _ptr(fmax), _ptr(vmax), DP_HOST, self._stream(stream)))
         return hist, fmax, vmax
 
+    def accum_flush(self, stream=None):
+        """Bring the per-vertex maxima up to date on the device (they are derived from the per-face maxima)."""
+        self._check(self._L.dp_accum_flush(self._h, self._stream(stream)))
+
     def accum_device_ptrs(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._L.dp_accum_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))

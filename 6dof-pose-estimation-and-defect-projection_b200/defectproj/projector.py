@@ -89,6 +89,7 @@ class Projector:
     def accumulators(self):
         """Torch views (no copy) of hist int32 [nF], fmax float32 [nF], vmax float32 [nV]."""
         import torch
+        self.ctx.accum_flush(torch.cuda.current_stream(self.device))
         h, f, v = self.ctx.accum_device_ptrs()
         dev = f"cuda:{self.device}"
         return (torch.as_tensor(_DevView(h, max(self.nF, 1), "<i4"), device=dev)[:self.nF],

@@ -208,6 +208,10 @@ DP_API int dp_icp_point_to_plane(dp_ctx *ctx, const double *source, int64_t n, c
 DP_API int dp_accum_reset(dp_ctx *ctx, void *stream);
 /* hist: [nF] int32, fmax: [nF] float32, vmax: [nV] float32; any may be NULL */
 DP_API int dp_accum_get(dp_ctx *ctx, int32_t *hist, float *fmax, float *vmax, int mem, void *stream);
+/* The per-vertex maxima are derived from the per-face maxima (vmax[v] = max over the faces incident to v of
+ * fmax[f]) when they are read, not per hit: dp_accum_get does it itself; call dp_accum_flush on the stream before
+ * reading vmax through dp_accum_device_ptrs. */
+DP_API int dp_accum_flush(dp_ctx *ctx, void *stream);
 /* device addresses of the accumulators, for in-place NCCL reductions by the host layer */
 DP_API int dp_accum_device_ptrs(dp_ctx *ctx, int32_t **hist, float **fmax, float **vmax);
 
