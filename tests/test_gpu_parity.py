@@ -600,6 +600,28 @@ def test_repeated_calls_are_identical_and_schedule_state_is_safe(ctx, orc):
         assert np.array_equal(res["face"], f) and np.array_equal(_bits(res["t_hit"]), _bits(t))
 
 
+def test_vertex_maxima_are_derived_on_read(ctx, orc):
+    """vmax is not accumulated per hit: dp_accum_flush derives it from fmax (max over incident faces), which must
+    equal the oracle's per-hit accumulation bit for bit, also through the raw device pointers."""
+    import torch
+    V, F = synth.param_mesh(40, 25, seed=7)
+    K, H, W = synth.camera_720p()
+    pose = synth.fixed_pose()
+    ctx.set_mesh(V, F).build_bvh()
+    ctx.accum_reset()
+    heat = synth.blob_heatmap((H, W), seed=3)
+    res = ctx.project(heat, K, pose[None], 0.3, frame="object", accumulate=True, want=("face", "intensity"))
+    _, _, v_ref = orc.accumulate(res["face"], res["intensity"], F, len(V))
+    hp, fp, vp = ctx.accum_device_ptrs()
+    from defectproj.projector import _DevView
+    v_dev = torch.as_tensor(_DevView(vp, len(V), "<f4"), device="cuda")
+    assert float(v_dev.max()) == 0.0                       # nothing derived yet: the kernel only writes hist / fmax
+    ctx.accum_flush(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(v_dev.cpu().numpy(), v_ref) and v_ref.max() > 0
+    assert np.array_equal(ctx.accum_get()[2], v_ref)       # idempotent
+
+
 def test_statistics_counters(ctx):
     V, F = synth.param_mesh(*synth.MESH_CONFIGS["small"], seed=0)
     K, H, W = synth.camera_720p()
