@@ -76,6 +76,7 @@ struct dp_ctx {
     dp_stats last_stats{};
     cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timings_valid = false;
+    bool timing_on = false;          // stage events inside dp_project (dp_set_timing): 5 records = 14 us per call
     float build_ms = 0.f, refit_ms = 0.f;
 };
 
@@ -496,7 +497,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
 
     const size_t esz = dtype == DP_F64 ? 8 : 4;
     const void *d_heat = heat;
-    CK(cudaEventRecord(ctx->ev[0], s), "dp_project");
+    if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[0], s), "dp_project");
     if (mem == DP_HOST) {
         CK(ctx->heat.ensure((size_t)n_elems * esz + 16), "dp_project: heat");
         if (n_elems) CK(cudaMemcpyAsync(ctx->heat.p, heat, (size_t)n_elems * esz, cudaMemcpyHostToDevice, s), "dp_project: H2D");
@@ -555,7 +556,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
                       ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s, true),
        "dp_project: compaction");
-    CK(cudaEventRecord(ctx->ev[1], s), "dp_project");
+    if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[1], s), "dp_project");
 
     TraceStats *st = nullptr;
     if (ctx->stats_on) {
@@ -574,12 +575,12 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     CK(ctx->dir4.ensure((size_t)cap * 32 + 32), "dp_project: rays");
     CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s),
        "dp_project: ray generation");
-    CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
+    if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
     CK(launch_trace_pixels(view_of(b), ctx->dir4.as<float4>(), d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
                            d_counts + 1, st, ord_prev, ord_next, s, true),
        "dp_project: traversal");
-    CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
+    if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
     CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s),
        "dp_project: hit points");
     if (out && out->counts) {
@@ -596,8 +597,8 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
         if (ctx->counts_alias) CK(launch_publish_counts(d_counts, ctx->counts_alias, s), "dp_project: counts");
         else CK(cudaMemcpyAsync(out->counts, d_counts, 16, cudaMemcpyDefault, s), "dp_project: counts");
     }
-    CK(cudaEventRecord(ctx->ev[2], s), "dp_project");
-    ctx->timings_valid = true;
+    if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[2], s), "dp_project");
+    ctx->timings_valid = ctx->timing_on;
 
     if (n_rays || n_hits) {
         CK(cudaMemcpyAsync(ctx->h_counts, d_counts, 16, cudaMemcpyDeviceToHost, s), "dp_project: counts");
@@ -924,6 +925,14 @@ int dp_accum_device_ptrs(dp_ctx *ctx, int32_t **hist, float **fmax, float **vmax
     return DP_OK;
 }
 
+int dp_set_timing(dp_ctx *ctx, int enable)
+{
+    if (!ctx) return DP_E_ARG;
+    ctx->timing_on = enable != 0;
+    if (!ctx->timing_on) ctx->timings_valid = false;
+    return DP_OK;
+}
+
 int dp_set_stats(dp_ctx *ctx, int enable)
 {
     if (!ctx) return DP_E_ARG;
@@ -958,7 +967,7 @@ int dp_get_stats(dp_ctx *ctx, dp_stats *out)
 int dp_last_timings(dp_ctx *ctx, float *ms4)
 {
     if (!ctx || !ms4) return fail(ctx, DP_E_ARG, "dp_last_timings: bad arguments");
-    if (!ctx->timings_valid) return fail(ctx, DP_E_STATE, "dp_last_timings: no dp_project call yet");
+    if (!ctx->timings_valid) return fail(ctx, DP_E_STATE, "dp_last_timings: no dp_project call with timing enabled yet (dp_set_timing)");
     DeviceGuard g(ctx->device);
     CK(cudaEventSynchronize(ctx->ev[2]), "dp_last_timings");
     CK(cudaEventElapsedTime(&ms4[0], ctx->ev[0], ctx->ev[1]), "dp_last_timings");

@@ -64,6 +64,7 @@ SYMBOLS = {
     "dp_set_stats": (i32, [vp, i32]),
     "dp_get_stats": (i32, [vp, C.POINTER(Stats)]),
     "dp_last_timings": (i32, [vp, vp]),
+    "dp_set_timing": (i32, [vp, i32]),
     "dp_debug_dump_bvh": (i32, [vp, i32, vp, C.POINTER(i64), vp, C.POINTER(i64)]),
     "dp_debug_ray_nodes": (i32, [vp, vp, i64]),
     "dp_debug_radix_sort": (i32, [vp, vp, vp, i64]),

@@ -525,6 +525,10 @@ class Context:
         self._check(self._L.dp_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
 
+    def set_timing(self, on: bool):
+        """Stage events inside dp_project on/off (off: no last_timings, a few microseconds less per call)."""
+        self._check(self._L.dp_set_timing(self._h, int(bool(on))))
+
     def last_timings(self):
         ms = (C.c_float * 4)()
         self._check(self._L.dp_last_timings(self._h, ms))

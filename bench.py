@@ -282,12 +282,16 @@ def run_ours(args):
     trace_ms = []
     for i in range(args.steps):
         flush.zero_()
+        sampled = i % 16 == 15 or i == args.steps - 1
+        if sampled:
+            ctx.set_timing(True)         # stage events inside the library on this step only (14 us per call)
         ev[i][0].record(stream)
         step_device(args.warmup + i)
         ev[i][1].record(stream)
-        if i % 16 == 15 or i == args.steps - 1:
-            # kernel-only duration of the traversal launch of this step (events inside the library)
+        if sampled:
+            # kernel-only duration of the traversal launch of this step
             trace_ms.append(ctx.last_timings()["trace_ms"])
+            ctx.set_timing(False)
     ev_c0, ev_c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_c0.record(stream)
     gathered = 0

@@ -31,3 +31,10 @@ a = torch.empty(n * 3, dtype=torch.int32, device="cuda"); h = torch.empty(n * 3,
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(20): h.copy_(a, non_blocking=True)
 torch.cuda.synchronize(); print("D2H 12.6MB ms", 1e3 * (time.perf_counter() - t0) / 20)
+for on in (True, False, True, False):
+    ctx.set_timing(on)
+    for _ in range(5): ctx.project_device(hd, K, pose[None], 0.5, "object", True, out=o, sync=False)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(200): ctx.project_device(hd, K, pose[None], 0.5, "object", True, out=o, sync=False)
+    torch.cuda.synchronize(); print("stage events", on, "-> %.4f ms/call" % (1e3 * (time.perf_counter() - t0) / 200), flush=True)
+ctx.set_timing(True)

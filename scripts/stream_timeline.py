@@ -7,6 +7,7 @@ from defectproj import Context, FrameStream, synth
 K, H, W = synth.camera_wfov(); pose = synth.fill_frame_pose()
 V, F = synth.param_mesh(*synth.MESH_CONFIGS["c2_500k"], seed=0, scale=6.0)
 ctx = Context(0); ctx.set_mesh(V, F).build_bvh()
+ctx.set_timing(True)
 heats = [torch.ones((H, W)).pin_memory() for _ in range(4)]
 N = 40
 poses = np.stack([pose] * N)

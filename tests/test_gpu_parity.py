@@ -639,6 +639,26 @@ def test_statistics_counters(ctx):
         ctx.set_stats(False)
 
 
+def test_stage_timings_are_opt_in(ctx):
+    """dp_project records its stage events only after dp_set_timing(1): five event records cost ~14 us per call."""
+    from defectproj import DefectProjError
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["small"], seed=0)
+    K, H, W = synth.camera_720p()
+    ctx.set_mesh(V, F).build_bvh()
+    heat = synth.gaussian_heatmap((H, W), dtype=np.float32)
+    ctx.set_timing(False)
+    ctx.project(heat, K, synth.fixed_pose()[None], 0.5)
+    with pytest.raises(DefectProjError):
+        ctx.last_timings()
+    ctx.set_timing(True)
+    try:
+        ctx.project(heat, K, synth.fixed_pose()[None], 0.5)
+        t = ctx.last_timings()
+        assert 0 < t["trace_ms"] <= t["total_ms"] and t["compact_ms"] > 0 and t["raygen_ms"] > 0
+    finally:
+        ctx.set_timing(False)
+
+
 def test_frame_stream_equals_blocking_calls(ctx, orc):
     """The pipelined host-buffer API (H2D | kernels | D2H on three streams) returns what Context.project returns."""
     import torch

@@ -12,6 +12,7 @@ from oracle import oracle as orc
 
 out = {}
 ctx = Context(0)
+ctx.set_timing(True)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 
 def timed(fn, reps=10, warm=2):

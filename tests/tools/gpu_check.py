@@ -19,6 +19,7 @@ def run(fn):
         print("!!! FAILED", fn.__name__, flush=True)
 
 ctx = Context(0)
+ctx.set_timing(True)
 
 def t_radix():
     section("radix sort")

@@ -12,6 +12,7 @@ K, H, W = synth.camera_wfov()
 pose = synth.fill_frame_pose()
 V, F = synth.param_mesh(*synth.MESH_CONFIGS[mesh], seed=0, scale=6.0)
 ctx = Context(0); ctx.set_mesh(V, F).build_bvh()
+ctx.set_timing(True)
 builds = []
 for _ in range(4):
     ctx.build_bvh(); builds.append(ctx.stats()["last_build_ms"])
