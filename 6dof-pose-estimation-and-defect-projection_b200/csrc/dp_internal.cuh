@@ -28,8 +28,11 @@ struct __align__(16) TriRec {
 static_assert(sizeof(TriRec) == 48, "triangle record must be 48 bytes");
 
 constexpr int LEAF_MAX = 3;           // triangles per leaf slot
-constexpr int STACK_SMEM = 10;        // per-ray stack entries kept in shared memory
-constexpr int STACK_LOCAL = 54;       // overflow entries in local memory
+#ifndef DP_STACK_SMEM
+#define DP_STACK_SMEM 10
+#endif
+constexpr int STACK_SMEM = DP_STACK_SMEM;   // per-ray stack entries kept in shared memory
+constexpr int STACK_LOCAL = 64 - STACK_SMEM; // overflow entries in local memory
 constexpr int MAX_WIDE_DEPTH = STACK_SMEM + STACK_LOCAL - 2;
 constexpr float T_SLACK = 1.0001f;    // culling bound = best * T_SLACK (same as oracle.c)
 

@@ -298,7 +298,10 @@ __device__ __forceinline__ long long work_to_slot(long long i, bool tiled, int W
     return (trow * 4 + (l >> 3)) * W + tcol * 8 + (l & 7);
 }
 
-constexpr int TQ_CAP = 256;                     // triangle queue entries per warp (power of two)
+#ifndef DP_TQ_CAP
+#define DP_TQ_CAP 256
+#endif
+constexpr int TQ_CAP = DP_TQ_CAP;               // triangle queue entries per warp (power of two)
 #ifndef DP_TQ_FLUSH
 #define DP_TQ_FLUSH 32
 #endif
