@@ -126,7 +126,8 @@ class FrameStream:
 
     Three CUDA streams: H2D of frame i+1, kernels of frame i and D2H of frame i-1 run concurrently on
     double-buffered device memory; the host only waits for the 16-byte ray/hit counts of a frame before it
-    queues that frame's (exact-size) result copy.  Inputs and outputs are pinned host tensors, so
+    queues that frame's (exact-size) result copy.  A dense frame (every pixel selected) does not ship its pixel
+    list: it is the identity, handed out as one shared read-only array.  Inputs and outputs are pinned host tensors, so
     every copy is a real DMA.  Results are identical to Context.project on the same frame.
     """
 
@@ -154,6 +155,8 @@ class FrameStream:
         self.out_d = [outs(dev, False) for _ in range(2)]
         self.out_h = [outs("cpu", True) for _ in range(self.ring)]
         self.counts_h = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._identity = None
+        self.last_d2h_bytes = 0
 
     def run(self, heats, K, poses, thr=0.5, frame="object", accumulate=True, before_kernels=None):
         """heats: sequence of pinned host tensors [H,W]; K [3,3] or per frame; poses [B,4,4].
@@ -186,22 +189,34 @@ class FrameStream:
             n, nh = int(self.counts_h[b][0]), int(self.counts_h[b][1])
             m = min(n, self.cap)
             r = i % self.ring
+            dense = n == self.H * self.W and m == n        # every pixel selected: the pixel list is 0..n-1
             with torch.cuda.stream(self.s_out):
                 if prof is not None:
                     prof[i]["out0"] = mark(self.s_out)
                 for k in self.want:
+                    if k == "pixel" and dense:
+                        continue                           # not copied: pop_result hands out the identity
                     self.out_h[r][k][:m].copy_(self.out_d[b][k][:m], non_blocking=True)
                 ev_out[r].record(self.s_out)
                 if prof is not None:
                     prof[i]["out1"] = mark(self.s_out)
+            self.last_d2h_bytes = 16 + sum(self.out_h[r][k][:m].numel() * self.out_h[r][k].element_size()
+                                           for k in self.want if not (k == "pixel" and dense))
             pending.append((i, r, n, nh, m))
 
         def pop_result():
             i, r, n, nh, m = pending.pop(0)
             ev_out[r].synchronize()
-            res = {k: self.out_h[r][k][:m].numpy() for k in self.want}
-            if "pixel" in res:
-                res["pixel"] = res["pixel"].view(np.uint32)
+            dense = n == self.H * self.W and m == n
+            res = {k: self.out_h[r][k][:m].numpy() for k in self.want if not (k == "pixel" and dense)}
+            if "pixel" in self.want:
+                if dense:
+                    if self._identity is None:
+                        self._identity = np.arange(self.H * self.W, dtype=np.uint32)
+                        self._identity.flags.writeable = False
+                    res["pixel"] = self._identity          # read-only, shared between dense frames
+                else:
+                    res["pixel"] = res["pixel"].view(np.uint32)
             res["n"], res["hits"] = n, nh
             if n > self.cap:
                 raise MemoryError(f"frame {i}: {n} selected pixels exceed the stream capacity {self.cap}")

@@ -669,6 +669,7 @@ def test_frame_stream_equals_blocking_calls(ctx, orc):
     poses = synth.helix_poses(B, turns=1)
     heats = [torch.from_numpy(synth.blob_heatmap((H, W), seed=40 + i)).pin_memory() for i in range(B)]
     heats[3] = torch.zeros((H, W)).pin_memory()                                   # an empty frame in the middle
+    heats[5] = torch.ones((H, W)).pin_memory()                                    # a dense one: its pixel list is the identity
     ctx.set_mesh(V, F).build_bvh()
     ctx.accum_reset()
     fs = FrameStream(ctx, H, W, want=("pixel", "t_hit", "face", "point"))
@@ -684,6 +685,7 @@ def test_frame_stream_equals_blocking_calls(ctx, orc):
         for k in ("pixel", "t_hit", "face", "point"):
             assert np.array_equal(got[i][k], ref[k], equal_nan=(k in ("t_hit", "point"))), (i, k)
     assert got[3]["n"] == 0
+    assert got[5]["n"] == H * W and np.array_equal(got[5]["pixel"], np.arange(H * W, dtype=np.uint32))
     assert np.array_equal(hist_stream, ctx.accum_get()[0]) and hist_stream.sum() == sum(g["hits"] for g in got.values())
 
 
