@@ -348,6 +348,175 @@ __device__ __forceinline__ void tri_batch(const RayState &r, const TriRec *__res
 #ifndef DP_MIN_BLOCKS
 #define DP_MIN_BLOCKS 7      // 72 registers: 7 CTAs (28 warps) per SM; measured ~9 % faster than 80 registers / 6 CTAs
 #endif
+
+// ------------------------------------------------------------------------------------------
+// Sparse frames (the reference's production case: a thresholded defect blob, a few thousand rays).  With fewer rays
+// than the device has warps a launch of k_trace is bound by the LATENCY of its slowest ray: ~100 dependent node
+// visits of ~330 instructions each, executed by a lone warp.  k_trace_narrow gives every ray EIGHT lanes, one per
+// child slot of the wide node: a visit is one box test per lane (6 conversions, 6 FMAs), a ballot and the selection,
+// ~80 instructions; the lanes whose child is a hit leaf test its (<= 3) triangles themselves and the group reduces
+// the 64-bit (t, face) key by shuffles.  Same arithmetic, same order, same culling bound as k_trace: results are
+// bit-identical.  k_trace reads the ray count on the device and branches here when the frame is sparse (the host does
+// not know the count: no extra launch, no read-back).
+// ------------------------------------------------------------------------------------------
+constexpr int NR_THREADS = 128;                       // = TR_THREADS: 4 warps x 4 rays
+constexpr int NR_STACK = 64;                          // stack entries per ray (shared memory)
+#ifndef DP_NARROW_MAX_RAYS
+#define DP_NARROW_MAX_RAYS 49152                      // below this the narrow kernel takes the frame
+#endif
+
+template <bool STATS>
+__device__ __noinline__ void
+trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
+             const float4 *__restrict__ dir4, const float *__restrict__ intensity, long long n,
+             float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
+             unsigned long long *work_counter, long long *d_hits, TraceStats *stats, uint2 *s_stack)
+{
+    const int lane = threadIdx.x & 31, c = lane & 7, g = lane >> 3;
+    const unsigned gmask = 0xffu << (8 * g);
+    uint2 *stack = s_stack + (threadIdx.x >> 3) * NR_STACK;
+    const float scale = __ldg(d_scale);
+    const long long nitems = (n + 3) >> 2;                        // one work item = four consecutive rays = one warp
+    unsigned long long nn = 0, nt = 0, nhit = 0, nray = 0;
+    for (;;) {
+        unsigned long long wv = 0;
+        if (lane == 0) wv = atomicAdd(work_counter, 1ull);
+        const long long w = (long long)__shfl_sync(0xffffffffu, wv, 0);
+        if (w >= nitems) break;
+        const long long i = w * 4 + g;
+        const bool valid = i < n;
+        bool alive = valid;
+        RayState r;
+        {
+            float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
+            if (valid) {
+                const float4 o4 = __ldg(dir4 + 2 * i), d = __ldg(dir4 + 2 * i + 1);
+                ox = o4.x; oy = o4.y; oz = o4.z; dx = d.x; dy = d.y; dz = d.z;
+            }
+            ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
+        }
+        const bool sx = r.ix < 0.0f, sy = r.iy < 0.0f, sz = r.iz < 0.0f;
+        unsigned long long best = KEY_MISS;
+        uint2 ng = make_uint2(0u, 0x80000000u);                   // the root as the only inner child of a virtual group
+        int sp = 0;
+        unsigned steps_nodes = 0;
+        while (__any_sync(0xffffffffu, alive)) {
+            bool hit = false;
+            unsigned meta = 0, child_base = 0, tri_base = 0, imask = 0;
+            if (alive) {
+                // ---- select: nearest pending inner child of the current group (octant order, as node_select)
+                const unsigned hits = ng.y;
+                unsigned cc = hits >> 24, t;
+                t = cc & r.order;          cc = t ? t : cc;
+                t = cc & (r.order >> 8);   cc = t ? t : cc;
+                t = cc & (r.order >> 16);  cc = t ? t : cc;
+                const unsigned slot = (unsigned)__ffs((int)cc) - 1u;
+                ng.y &= ~(0x01000000u << slot);
+                if (ng.y & 0xff000000u) {
+                    stack[sp] = ng;                               // all eight lanes store the same value: no hand-over needed
+                    ++sp;
+                }
+                const unsigned node = ng.x + __popc(hits & 0xffu & ((1u << slot) - 1u));
+                // ---- visit: this lane tests child slot c
+                const uint4 *np = reinterpret_cast<const uint4 *>(nodes + node);
+                const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), w2 = __ldg(np + 2), w3 = __ldg(np + 3), w4 = __ldg(np + 4);
+                if (STATS) ++steps_nodes;
+                const int sh = 8 * (c & 3);
+                const bool hi4 = c >= 4;
+                meta = ((hi4 ? w1.w : w1.z) >> sh) & 0xffu;
+                child_base = w1.x; tri_base = w1.y; imask = w0.w >> 24;
+                const unsigned qlx = ((hi4 ? w2.y : w2.x) >> sh) & 0xffu, qly = ((hi4 ? w2.w : w2.z) >> sh) & 0xffu;
+                const unsigned qlz = ((hi4 ? w3.y : w3.x) >> sh) & 0xffu, qhx = ((hi4 ? w3.w : w3.z) >> sh) & 0xffu;
+                const unsigned qhy = ((hi4 ? w4.y : w4.x) >> sh) & 0xffu, qhz = ((hi4 ? w4.w : w4.z) >> sh) & 0xffu;
+                const float adjx = __uint_as_float((w0.w & 0xffu) << 23) * r.ix;
+                const float adjy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23) * r.iy;
+                const float adjz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23) * r.iz;
+                const float orgx = (__uint_as_float(w0.x) - r.ox) * r.ix;
+                const float orgy = (__uint_as_float(w0.y) - r.oy) * r.iy;
+                const float orgz = (__uint_as_float(w0.z) - r.oz) * r.iz;
+                const float tnx = fmaf((float)(sx ? qhx : qlx), adjx, orgx - r.px), tfx = fmaf((float)(sx ? qlx : qhx), adjx, orgx + r.px);
+                const float tny = fmaf((float)(sy ? qhy : qly), adjy, orgy - r.py), tfy = fmaf((float)(sy ? qly : qhy), adjy, orgy + r.py);
+                const float tnz = fmaf((float)(sz ? qhz : qlz), adjz, orgz - r.pz), tfz = fmaf((float)(sz ? qlz : qhz), adjz, orgz + r.pz);
+                const float tlimit = __uint_as_float((unsigned)(best >> 32)) * T_SLACK;
+                const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+                const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
+                hit = meta != 0u && tmin <= tmax;
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, hit);
+            const unsigned hit8 = (ball >> (8 * g)) & 0xffu;
+            unsigned long long key = KEY_MISS;
+            if (alive) {
+                // ---- triangles of this lane's child, when it is a hit leaf
+                if (hit && !((imask >> c) & 1u)) {
+                    const int cnt = __popc(meta >> 5);
+                    const float4 *tp = reinterpret_cast<const float4 *>(tris + (tri_base + (meta & 31u)));
+                    for (int k = 0; k < cnt; ++k) {
+                        const float4 p0 = __ldg(tp + 3 * k), p1 = __ldg(tp + 3 * k + 1), p2 = __ldg(tp + 3 * k + 2);
+                        if (STATS) ++nt;
+                        float t;
+                        if (tri_test(r.w, p0, p1, p2, t)) {
+                            t += 0.0f;
+                            const unsigned long long kk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)__float_as_int(p0.w);
+                            key = kk < key ? kk : key;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+                key = o < key ? o : key;
+            }
+            if (alive) {
+                best = key < best ? key : best;
+                // ---- the node's inner hits become the current group, or one is popped from the stack
+                ng = make_uint2(child_base, ((hit8 & imask) << 24) | imask);
+                if (!(ng.y & 0xff000000u)) {
+                    if (sp == 0) alive = false;
+                    else { --sp; ng = stack[sp]; }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- result of the ray (lane c == 0 of its group)
+        const float tb = __uint_as_float((unsigned)(best >> 32));
+        const int bf = (int)(unsigned)best;
+        if (valid && c == 0) {
+            if (t_hit) t_hit[i] = tb;
+            if (face) face[i] = bf;
+            if (STATS) { ++nray; nn += steps_nodes; if (stats->ray_nodes) stats->ray_nodes[i] = steps_nodes; }
+            if (bf >= 0) {
+                ++nhit;
+                if (has_acc) {
+                    float I = intensity ? intensity[i] : 0.0f;
+                    I = I > 0.0f ? I : 0.0f;
+                    atomicAdd(&acc.hist[bf], 1);
+                    atomicMax(&acc.fmax[bf], __float_as_uint(I));
+                }
+            }
+        }
+    }
+    // ---- per-warp totals
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        nhit += __shfl_xor_sync(0xffffffffu, nhit, d);
+        if (STATS) {
+            nn += __shfl_xor_sync(0xffffffffu, nn, d);
+            nt += __shfl_xor_sync(0xffffffffu, nt, d);
+            nray += __shfl_xor_sync(0xffffffffu, nray, d);
+        }
+    }
+    if (lane == 0) {
+        if (d_hits && nhit) atomicAdd(reinterpret_cast<unsigned long long *>(d_hits), nhit);
+        if (STATS) {
+            atomicAdd(&stats->rays, nray);
+            atomicAdd(&stats->hits, nhit);
+            atomicAdd(&stats->nodes, nn);
+            atomicAdd(&stats->tris, nt);
+        }
+    }
+}
+
 #ifndef DP_MIN_BLOCKS_BIG
 #define DP_MIN_BLOCKS_BIG 5  // hierarchies beyond L2 (5M triangles: 0.511 -> 0.49 ms): fewer packets share an SM's L1
 #endif
@@ -358,7 +527,7 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
         const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
         const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
         unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
-        const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch)
+        const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch, int narrow_enabled)
 {
     const bool pf = prefetch != 0;
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
@@ -372,6 +541,12 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
     const unsigned lt = (1u << lane) - 1u;
     long long n = d_n ? *d_n : n_max;
     if (n > n_max) n = n_max;
+    if (SRC == 0 && narrow_enabled && n <= DP_NARROW_MAX_RAYS) {
+        // sparse frame: eight lanes per ray (work items come from the second counter)
+        static_assert(STACK_SMEM * TR_THREADS >= (NR_THREADS / 8) * NR_STACK, "the narrow path borrows the packet stack");
+        trace_narrow<STATS>(nodes, tris, d_scale, dir4, intensity, n, t_hit, face, acc, has_acc, work_counter + 1, d_hits, stats, s_stack);
+        return;
+    }
     const bool tiled = SRC == 0 && allow_tiled && n == total_px && (W & 7) == 0 && (H & 3) == 0 && W > 0;
     const float scale = __ldg(d_scale);
     unsigned nn = 0, nt = 0, n_hit_local = 0, n_ray_local = 0;
@@ -669,6 +844,12 @@ int knob_order()
     if (g_order < 0) { const char *e = getenv("DP_ORDER"); g_order = e ? atoi(e) : 1; }
     return g_order;
 }
+int g_narrow = -1;
+int knob_narrow()
+{
+    if (g_narrow < 0) { const char *e = getenv("DP_NARROW"); g_narrow = e ? atoi(e) : 1; }
+    return g_narrow;
+}
 int knob_tiled()
 {
     if (g_tiled < 0) { const char *e = getenv("DP_TILED"); g_tiled = e ? atoi(e) : 1; }
@@ -741,13 +922,14 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     if ((e = trace_grid(pf, &grid)) != cudaSuccess) return e;
     const long long want = (n_max + TR_THREADS - 1) / TR_THREADS;
     if (want < grid) grid = (int)want;
-    if (!counter_zeroed && (e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
+    if (!counter_zeroed && (e = cudaMemsetAsync(work_counter, 0, 2 * sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
     if (knob_order() == 0) { ord_prev = nullptr; ord_next = nullptr; }
+    const int narrow = knob_narrow() && d_n != nullptr;
 #define DP_LAUNCH_TRACE0(ST, MB)                                                                                        \
     k_trace<ST, 0, MB><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,   \
                                                    total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, d_hits, \
-                                                   stats, knob_tiled(), ord_prev, ord_next, pf)
+                                                   stats, knob_tiled(), ord_prev, ord_next, pf, narrow)
     if (stats) { if (pf) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS); }
     else       { if (pf) DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS); }
 #undef DP_LAUNCH_TRACE0
@@ -768,7 +950,7 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
     Accum a{nullptr, nullptr, nullptr, nullptr};
 #define DP_LAUNCH_TRACE1(ST, MB)                                                                                          \
     k_trace<ST, 1, MB><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0, 0, 0, \
-                                                   nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf)
+                                                   nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf, 0)
     if (stats) { if (pf) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS); }
     else       { if (pf) DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS); }
 #undef DP_LAUNCH_TRACE1

@@ -8,8 +8,7 @@ from defectproj import Context, synth
 K, H, W = synth.camera_720p(); pose = synth.fixed_pose()
 for mesh in ("c1_30k", "c2_500k"):
     V, F = synth.param_mesh(*synth.MESH_CONFIGS[mesh], seed=0)
-    ctx = Context(0); ctx.set_mesh(V, F).build_bvh()
-ctx.set_timing(True)
+    ctx = Context(0); ctx.set_timing(True); ctx.set_mesh(V, F).build_bvh()
     heat = torch.from_numpy(synth.gaussian_heatmap((H, W), dtype=np.float32))[None].cuda()
     n = H * W
     o = dict(t_hit=torch.empty(n, device="cuda"), face=torch.empty(n, dtype=torch.int32, device="cuda"))
