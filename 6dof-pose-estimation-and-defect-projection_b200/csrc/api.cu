@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -1141,8 +1142,20 @@ extern "C" int dp_icp_point_to_plane(dp_ctx *ctx, const double *source, int64_t 
     double sums[29];
     bool identity_init = true;
     for (int i = 0; i < 16; ++i) identity_init = identity_init && T[i] == ident[i];
+    // Targets of some size get a uniform grid (cells >= the search radius, built once per call); DP_ICP_GRID=0 keeps the
+    // tiled scan of the whole target (same correspondences and sums bit for bit, kept for A/B measurements).
+    IcpGridView gv;
+    gv.tps = nullptr;
+    const char *knob = getenv("DP_ICP_GRID");                        // read per call: tests flip it within one process
+    const int use_grid = knob ? atoi(knob) : 1;
+    if (use_grid && n > 0 && m >= ICP_GRID_MIN_POINTS && m < (int64_t)1 << 31) {
+        CK(ctx->tmp[6].ensure(icp_grid_bytes(m)), "dp_icp_point_to_plane: grid");
+        CK(icp_grid_build(d_tp, d_tn, m, max_correspondence_distance, ctx->tmp[6].p, &gv, s), "dp_icp_point_to_plane: grid build");
+    }
     auto evaluate = [&](const double *update) -> int {
-        cudaError_t e = launch_icp_step(d_src, n, d_tp, d_tn, m, max_correspondence_distance, update, d_corr, d_partial, d_sums, s);
+        cudaError_t e = gv.tps ? launch_icp_step_grid(d_src, n, gv, max_correspondence_distance, update, d_corr, d_partial, d_sums, s)
+                               : launch_icp_step(d_src, n, d_tp, d_tn, m, max_correspondence_distance, update, d_corr, d_partial,
+                                                 d_sums, s);
         if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "dp_icp_point_to_plane: launch", e);
         if ((e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
             (e = cudaStreamSynchronize(s)) != cudaSuccess)

@@ -166,6 +166,26 @@ cudaError_t launch_pack_hits(const void *inten, int dtype, const int32_t *face, 
                              unsigned long long *scratch, long long *d_count, cudaStream_t s);
 
 // ---- icp.cu --------------------------------------------------------------------------------
+constexpr int ICP_GRID_MIN_POINTS = 256;   // smaller targets are scanned (one shared-memory tile)
+constexpr int ICP_GRID_MIN_CELLS = 216;
+constexpr int ICP_GRID_MAX_DIM = 96;   // cells per axis of the target grid (2 x 3.5 MB of cell ranges at most)
+struct IcpGrid {
+    double lo[3];
+    double inv_cell;
+    int dim[3];
+};
+struct IcpGridView {
+    IcpGrid grid;
+    double ext[3];
+    const double *tps, *tns;          // target points / normals in cell order
+    const uint32_t *orig;             // cell order -> original target index
+    const int32_t *cell_start, *cell_end;
+};
+size_t icp_grid_bytes(int64_t m);
+cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double max_dist, void *scratch, IcpGridView *out,
+                           cudaStream_t s);
+cudaError_t launch_icp_step_grid(double *src, int64_t n, const IcpGridView &gv, double max_dist, const double *update_host,
+                                 int32_t *corr, double *partial, double *sums, cudaStream_t s);
 size_t icp_partial_doubles(int64_t n);
 // sums (device, 29 doubles): count, sum d^2, 21 upper-triangle entries of sum J J^T, 6 entries of sum J r
 cudaError_t launch_icp_step(double *src, int64_t n, const double *tp, const double *tn, int64_t m, double max_dist,

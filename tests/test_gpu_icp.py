@@ -118,3 +118,27 @@ def test_icp_full_size_property(ctx):
     r = ctx.icp_point_to_plane(src, V, vn, 3.0)
     assert r["fitness"] == 1.0 and r["inlier_rmse"] < 1e-6
     assert np.abs(r["transformation"] - T).max() < 1e-6
+
+
+def test_icp_grid_search_equals_the_scan_bit_for_bit(ctx, monkeypatch):
+    """The uniform grid over the target (targets of >= 256 points) and the tiled scan of the whole target
+    (DP_ICP_GRID=0) return the same correspondences, hence the same 29 sums, transform and iteration count --
+    including a radius larger than a cell's minimum (coarse grid), duplicated target points (ties to the smaller
+    original index) and source points outside the target's box."""
+    V, vn = _cloud_with_normals(90, 60, seed=5)
+    V = np.concatenate([V, V[:500]])                                # exact duplicates: equal distances
+    vn = np.concatenate([vn, vn[:500]])
+    T = _rigid(2.5, -1.0, [0.7, -0.4, 0.9])
+    Ti = np.linalg.inv(T)
+    src = V[::3] @ Ti[:3, :3].T + Ti[:3, 3]
+    src = np.concatenate([src, V[:40] + 30.0, V[:40] - 500.0])     # near and far outside the box
+    for dist in (0.8, 3.0, 12.0, 400.0):                           # 400: too few cells, the library scans anyway
+        monkeypatch.setenv("DP_ICP_GRID", "1")
+        a = ctx.icp_point_to_plane(src, V, vn, dist, want_correspondence=True)
+        monkeypatch.setenv("DP_ICP_GRID", "0")
+        b = ctx.icp_point_to_plane(src, V, vn, dist, want_correspondence=True)
+        assert np.array_equal(a["correspondence"], b["correspondence"]), dist
+        assert a["iterations"] == b["iterations"] and a["fitness"] == b["fitness"]
+        assert a["inlier_rmse"] == b["inlier_rmse"]
+        assert np.array_equal(a["transformation"], b["transformation"]), dist
+    assert (a["correspondence"] >= 0).any()
