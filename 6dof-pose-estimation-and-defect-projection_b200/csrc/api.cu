@@ -743,6 +743,47 @@ int dp_align_to_surface(dp_ctx *ctx, const double *query, int stride, int64_t n,
     return DP_OK;
 }
 
+int dp_estimate_normals(dp_ctx *ctx, const double *points, int64_t n, double radius, int max_nn, double *normals,
+                        int has_normals, int32_t *neighbours, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || n >= (int64_t)1 << 31 || !(radius > 0.0) || max_nn < 1 || max_nn > NORMALS_MAX_NN ||
+        (n > 0 && (!points || !normals)))
+        return fail(ctx, DP_E_ARG, "dp_estimate_normals: bad arguments (max_nn is limited to 64)");
+    if (n == 0) return DP_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double *dp_ = points;
+    double *dn = normals;
+    int32_t *dc = neighbours;
+    if (mem == DP_HOST) {
+        CK(ctx->tmp[0].ensure((size_t)n * 24 + 16), "dp_estimate_normals: points");
+        CK(ctx->tmp[1].ensure((size_t)n * 24 + 16), "dp_estimate_normals: normals");
+        CK(cudaMemcpyAsync(ctx->tmp[0].p, points, (size_t)n * 24, cudaMemcpyHostToDevice, s), "dp_estimate_normals: H2D");
+        if (has_normals)
+            CK(cudaMemcpyAsync(ctx->tmp[1].p, normals, (size_t)n * 24, cudaMemcpyHostToDevice, s), "dp_estimate_normals: H2D");
+        dp_ = ctx->tmp[0].as<double>();
+        dn = ctx->tmp[1].as<double>();
+        if (neighbours) {
+            CK(ctx->tmp[5].ensure((size_t)n * 4 + 16), "dp_estimate_normals: counts");
+            dc = ctx->tmp[5].as<int32_t>();
+        }
+    }
+    // the grid of the ICP row over the cloud itself: cells at least `radius` wide, so the neighbours are in 27 cells
+    IcpGridView gv;
+    gv.tps = nullptr;
+    CK(ctx->tmp[6].ensure(icp_grid_bytes(n)), "dp_estimate_normals: grid");
+    CK(icp_grid_build(dp_, nullptr, n, radius, 1, ctx->tmp[6].p, &gv, s), "dp_estimate_normals: grid build");
+    if (!gv.tps) return fail(ctx, DP_E_ARG, "dp_estimate_normals: the cloud has non-finite coordinates");
+    CK(launch_estimate_normals(gv, n, radius, max_nn, dn, has_normals, dc, s), "dp_estimate_normals: launch");
+    if (mem == DP_HOST) {
+        CK(cudaMemcpyAsync(normals, dn, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_estimate_normals: D2H");
+        if (neighbours) CK(cudaMemcpyAsync(neighbours, dc, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "dp_estimate_normals: D2H");
+        CK(cudaStreamSynchronize(s), "dp_estimate_normals: kernels");
+    }
+    return DP_OK;
+}
+
 int dp_prepare_heatmap(dp_ctx *ctx, const void *data, int dtype, int src_h, int src_w, int H, int W, void *out, int out_dtype,
                        int mem, void *stream)
 {
@@ -1150,7 +1191,7 @@ extern "C" int dp_icp_point_to_plane(dp_ctx *ctx, const double *source, int64_t 
     const int use_grid = knob ? atoi(knob) : 1;
     if (use_grid && n > 0 && m >= ICP_GRID_MIN_POINTS && m < (int64_t)1 << 31) {
         CK(ctx->tmp[6].ensure(icp_grid_bytes(m)), "dp_icp_point_to_plane: grid");
-        CK(icp_grid_build(d_tp, d_tn, m, max_correspondence_distance, ctx->tmp[6].p, &gv, s), "dp_icp_point_to_plane: grid build");
+        CK(icp_grid_build(d_tp, d_tn, m, max_correspondence_distance, ICP_GRID_MIN_CELLS, ctx->tmp[6].p, &gv, s), "dp_icp_point_to_plane: grid build");
     }
     auto evaluate = [&](const double *update) -> int {
         cudaError_t e = gv.tps ? launch_icp_step_grid(d_src, n, gv, max_correspondence_distance, update, d_corr, d_partial, d_sums, s)

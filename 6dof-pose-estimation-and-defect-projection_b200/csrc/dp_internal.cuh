@@ -181,15 +181,27 @@ struct IcpGridView {
     const uint32_t *orig;             // cell order -> original target index
     const int32_t *cell_start, *cell_end;
 };
+// cell coordinate of v along one axis, clamped into the grid (NaN -> 0)
+__device__ __forceinline__ int grid_coord(double v, double lo, double inv_cell, int dim)
+{
+    const double c = floor((v - lo) * inv_cell);
+    if (!(c >= 0.0)) return 0;                       // below the grid, or NaN (never handed to the conversion)
+    return c >= (double)dim ? dim - 1 : (int)c;
+}
 size_t icp_grid_bytes(int64_t m);
-cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double max_dist, void *scratch, IcpGridView *out,
-                           cudaStream_t s);
+cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double max_dist, size_t min_cells, void *scratch,
+                           IcpGridView *out, cudaStream_t s);
 cudaError_t launch_icp_step_grid(double *src, int64_t n, const IcpGridView &gv, double max_dist, const double *update_host,
                                  int32_t *corr, double *partial, double *sums, cudaStream_t s);
 size_t icp_partial_doubles(int64_t n);
 // sums (device, 29 doubles): count, sum d^2, 21 upper-triangle entries of sum J J^T, 6 entries of sum J r
 cudaError_t launch_icp_step(double *src, int64_t n, const double *tp, const double *tn, int64_t m, double max_dist,
                             const double *update_host, int32_t *corr, double *partial, double *sums, cudaStream_t s);
+
+// ---- normals.cu ----------------------------------------------------------------------------
+constexpr int NORMALS_MAX_NN = 64;
+cudaError_t launch_estimate_normals(const IcpGridView &gv, int64_t n, double radius, int max_nn, double *normals, int has_normals,
+                                    int32_t *neighbours, cudaStream_t s);
 
 // ---- build.cu ------------------------------------------------------------------------------
 struct BuildScratch;   // opaque, owned by the context

@@ -154,12 +154,6 @@ __global__ void __launch_bounds__(256) k_icp_bounds(const double *__restrict__ t
     }
 }
 
-__device__ __forceinline__ int grid_coord(double v, double lo, double inv_cell, int dim)
-{
-    const double c = floor((v - lo) * inv_cell);
-    return c < 0.0 ? 0 : (c >= (double)dim ? dim - 1 : (int)c);
-}
-
 __global__ void __launch_bounds__(256)
 k_icp_grid_keys(const double *__restrict__ tp, long long m, IcpGrid g, uint32_t *keys, uint32_t *vals)
 {
@@ -182,7 +176,7 @@ k_icp_grid_gather(const double *__restrict__ tp, const double *__restrict__ tn, 
     if (k >= m) return;
     const uint32_t j = vals[k], key = keys[k];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { tps[3 * k + a] = tp[3ll * j + a]; tns[3 * k + a] = tn[3ll * j + a]; }
+    for (int a = 0; a < 3; ++a) { tps[3 * k + a] = tp[3ll * j + a]; if (tn) tns[3 * k + a] = tn[3ll * j + a]; }
     if (k == 0 || keys[k - 1] != key) cell_start[key] = (int32_t)k;
     if (k == m - 1 || keys[k + 1] != key) cell_end[key] = (int32_t)k + 1;
 }
@@ -267,8 +261,10 @@ size_t icp_grid_bytes(int64_t m)
 }
 
 // Builds the grid over the target in `scratch` (icp_grid_bytes(m) bytes).  One 48-byte read-back (the bounding box).
-cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double max_dist, void *scratch, IcpGridView *out,
-                           cudaStream_t s)
+// `tn` may be null (points only); out->tps stays null when the grid is not worth building (fewer than `min_cells`
+// cells) or cannot be built (non-finite coordinates).
+cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double max_dist, size_t min_cells, void *scratch,
+                           IcpGridView *out, cudaStream_t s)
 {
     cudaError_t e;
     char *p = static_cast<char *>(scratch);
@@ -317,7 +313,7 @@ cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double
     }
     const size_t cells = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
     // 27 of `cells` cells per query against one tiled scan of all of them: below ~8 x 27 cells the scan is as fast
-    if (cells < ICP_GRID_MIN_CELLS) return cudaSuccess;
+    if (cells < min_cells) return cudaSuccess;
     k_icp_grid_keys<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(tp, m, g, keys, vals);
     bool in_tmp = false;
     if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, m, table, s, &in_tmp)) != cudaSuccess) return e;

@@ -51,6 +51,7 @@ SYMBOLS = {
     "dp_depth_backproject": (i32, [vp, vp, i32, i32, i32, vp, i32, i32, vp, f64, vp, i64, C.POINTER(i64), i32, vp]),
     "dp_calc_coordinates": (i32, [vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, i32, vp]),
     "dp_align_to_surface": (i32, [vp, vp, i32, i64, vp, vp, i64, f64, vp, vp, vp, i32, vp]),
+    "dp_estimate_normals": (i32, [vp, vp, i64, f64, i32, vp, i32, vp, i32, vp]),
     "dp_prepare_heatmap": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp]),
     "dp_transform_points": (i32, [vp, vp, i64, vp, i32, vp]),
     "dp_pack_hits": (i32, [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64), i32, vp]),

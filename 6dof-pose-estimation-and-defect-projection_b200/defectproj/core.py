@@ -496,6 +496,17 @@ class Context:
             out["correspondence"] = corr
         return out
 
+    def estimate_normals(self, points, radius, max_nn=30, normals=None, want_counts=False, stream=None):
+        """PointCloud.estimate_normals(KDTreeSearchParamHybrid(radius, max_nn)) on the GPU.  `normals`: the cloud's
+        existing normals (the new ones keep their side) or None.  Returns normals [n,3] (and the neighbour counts)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        has = normals is not None and len(normals) == len(pts) and len(pts) > 0
+        out = np.array(normals, dtype=np.float64).reshape(-1, 3) if has else np.empty((len(pts), 3), np.float64)
+        cnt = np.empty(len(pts), np.int32) if want_counts else None
+        self._check(self._L.dp_estimate_normals(self._h, _ptr(pts), len(pts), float(radius), int(max_nn), _ptr(out),
+                                                int(has), _ptr(cnt), DP_HOST, self._stream(stream)))
+        return (out, cnt) if want_counts else out
+
     # ------------------------------------------------------------------ H6 / H7
     def accum_reset(self, stream=None):
         self._check(self._L.dp_accum_reset(self._h, self._stream(stream)))

@@ -36,7 +36,8 @@ from .core import Context
 __all__ = ["heatmap_to_points", "compute_rays", "intersect_rays_with_mesh", "create_intersection_pcd",
            "project_debug_rays", "ray_tracing", "load_extrinsics", "PointCloud", "LineSet", "TriangleMesh",
            "last_result", "get_context", "face_intensities",
-           "heatmap_to_point3d", "pcd_from_point3d", "align_to_surface", "calc_coordinates", "depth_projection_heatmap"]
+           "heatmap_to_point3d", "pcd_from_point3d", "align_to_surface", "calc_coordinates", "depth_projection_heatmap",
+           "KDTreeSearchParamHybrid", "estimate_normals"]
 
 _CTX = None
 _SCENE = {"V": None, "F": None}
@@ -59,6 +60,14 @@ def last_result():
 # ------------------------------------------------------------------------------------------
 # light geometry containers (the attributes src/web_vis.py:203-217 reads)
 # ------------------------------------------------------------------------------------------
+class KDTreeSearchParamHybrid:
+    """o3d.geometry.KDTreeSearchParamHybrid: at most max_nn neighbours within radius (the only search the
+    reference uses for normals: :184-185, :433-435, src/pose_estimation.py:304-305)."""
+
+    def __init__(self, radius, max_nn):
+        self.radius, self.max_nn = float(radius), int(max_nn)
+
+
 class PointCloud:
     def __init__(self, points=None, colors=None, normals=None):
         self.points = np.zeros((0, 3)) if points is None else np.asarray(points, dtype=np.float64)
@@ -70,6 +79,18 @@ class PointCloud:
 
     def has_normals(self):
         return len(self.normals) == len(self.points) and len(self.points) > 0
+
+    def estimate_normals(self, search_param=None, fast_normal_computation=True):
+        """o3d.geometry.PointCloud.estimate_normals on the GPU (dp_estimate_normals): existing normals keep their
+        side, points with fewer than 3 neighbours get (0, 0, 1).  Only the hybrid search the reference uses."""
+        if not isinstance(search_param, KDTreeSearchParamHybrid):
+            raise NotImplementedError("estimate_normals needs search_param=KDTreeSearchParamHybrid(radius, max_nn)")
+        if not fast_normal_computation:
+            raise NotImplementedError("only fast_normal_computation=True (Open3D's default) is implemented")
+        if len(self.points):
+            self.normals = get_context().estimate_normals(self.points, search_param.radius, search_param.max_nn,
+                                                          normals=self.normals if self.has_normals() else None)
+        return self
 
     def transform(self, T):
         """In place, like o3d.geometry.PointCloud.transform (used at run.py:118)."""
@@ -313,13 +334,25 @@ def pcd_from_point3d(points_3D):
     return PointCloud(np.asarray(points_3D)[:, :3])
 
 
+def estimate_normals(pcd):
+    """Normals of a cloud with the reference's parameters (:181-186: radius 10, at most 30 neighbours)."""
+    pcd.estimate_normals(search_param=KDTreeSearchParamHybrid(radius=10, max_nn=30))
+    return pcd
+
+
 def align_to_surface(defect_points, target_pcd, offset=0.1):
     """(offset_points, aligned_points): nearest target point of every defect point and that point moved along its
-    normal (:441-459).  The target must carry normals (estimating them is Open3D's job, :431-436)."""
-    tp = np.asarray(target_pcd.points, dtype=np.float64)
-    tn = np.asarray(getattr(target_pcd, "normals", np.zeros((0, 3))), dtype=np.float64)
+    normal (:441-459).  A target without normals gets them estimated in place first, with the reference's
+    parameters (:431-436: radius 0.1, at most 30 neighbours); a plain object with ``.points`` only is left untouched
+    and its normals are computed on the side."""
+    tp = np.asarray(target_pcd.points, dtype=np.float64).reshape(-1, 3)
+    tn = np.asarray(getattr(target_pcd, "normals", np.zeros((0, 3))), dtype=np.float64).reshape(-1, 3)
     if len(tn) != len(tp):
-        raise ValueError("target point cloud has no normals; estimate them before align_to_surface")
+        if hasattr(target_pcd, "estimate_normals"):
+            target_pcd.estimate_normals(search_param=KDTreeSearchParamHybrid(radius=0.1, max_nn=30))
+            tn = np.asarray(target_pcd.normals, dtype=np.float64).reshape(-1, 3)
+        else:
+            tn = get_context().estimate_normals(tp, 0.1, 30) if len(tp) else np.zeros((0, 3))
     dp = np.asarray(defect_points, dtype=np.float64)
     if dp.size == 0:
         return np.array([]), np.array([])

@@ -4,7 +4,8 @@ Mirrors the ICP call sites of /root/reference/src/pose_estimation.py -- ``refine
 the restart loop of ``improve_result`` (:547-620) and the one-iteration probes of ``predict_z_axis_adjustment``
 (:654-660) -- with Open3D's ``registration_icp`` replaced by ``dp_icp_point_to_plane`` (csrc/icp.cu): exact
 nearest neighbours and the 6x6 normal equations on the GPU, the solve on the host.  Only the ICP inner loop is on
-this row; RANSAC/FPFH global registration, normal estimation and FoundationPose stay out of scope.
+this row, plus the normals its target needs (``estimate_normals`` :301-306 -> ``dp_estimate_normals``); RANSAC/FPFH
+global registration and FoundationPose stay out of scope.
 
 Point clouds are duck-typed: anything with ``.points`` (and ``.normals`` for the target), or plain arrays.
 """
@@ -15,10 +16,10 @@ import logging
 
 import numpy as np
 
-from .defect_projection import get_context
+from .defect_projection import KDTreeSearchParamHybrid, get_context
 
 __all__ = ["ICPConvergenceCriteria", "TransformationEstimationPointToPlane", "RegistrationResult", "registration_icp",
-           "refine_registration", "improve_result", "get_rotation_matrix_from_xyz"]
+           "refine_registration", "improve_result", "get_rotation_matrix_from_xyz", "estimate_normals"]
 
 
 class ICPConvergenceCriteria:
@@ -42,6 +43,13 @@ class RegistrationResult:
     def __repr__(self):
         return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e}, "
                 f"and correspondence_set size of {len(self.correspondence_set)}")
+
+
+def estimate_normals(pcd, params=None):
+    """Normals of a cloud with the reference's parameters (:301-306: radius 2, at most 5 neighbours; ``params`` is
+    accepted and ignored like there)."""
+    pcd.estimate_normals(search_param=KDTreeSearchParamHybrid(radius=2, max_nn=5))
+    return pcd
 
 
 def _points(pcd):

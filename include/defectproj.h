@@ -189,6 +189,16 @@ DP_API int dp_pack_hits(dp_ctx *ctx, const void *intensity, int dtype, const int
 /* the colour table used above: lut [256*3] float64 RGB (host helper, no device work) */
 DP_API void dp_jet_lut(double *lut);
 
+/* o3d.geometry.PointCloud.estimate_normals(search_param=KDTreeSearchParamHybrid(radius, max_nn)) as called by
+ * src/defect_projection.py:181-186, :431-436 (inside align_to_surface) and src/pose_estimation.py:301-306:
+ * points [n*3] float64; neighbours of a point = its max_nn (<= 64) nearest points, itself included, with squared
+ * distance < radius^2, ordered by (distance, index); fewer than 3 -> (0, 0, 1) (or the existing normal); else the
+ * eigenvector of the smallest eigenvalue of the neighbours' covariance (Open3D's closed-form FastEigen3x3).
+ * normals [n*3] float64: output; with has_normals != 0 also input, and every new normal keeps the side of the old
+ * one.  neighbours: optional [n] int32 neighbour counts.  Open3D is absent offline: parity unpinned. */
+DP_API int dp_estimate_normals(dp_ctx *ctx, const double *points, int64_t n, double radius, int max_nn, double *normals,
+                               int has_normals, int32_t *neighbours, int mem, void *stream);
+
 /* ---- upstream of the path: point-to-plane ICP (src/pose_estimation.py:505-522, :577-613, :654-660) */
 /* o3d.pipelines.registration.registration_icp(source, target, max_correspondence_distance, init,
  * TransformationEstimationPointToPlane(), ICPConvergenceCriteria(relative_fitness, relative_rmse, max_iteration)):

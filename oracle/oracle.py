@@ -459,3 +459,164 @@ def icp_point_to_plane(source, target, normals, max_dist, init=None, max_iterati
         if abs(pf - fit) < rel_fitness and abs(pr - rmse) < rel_rmse:
             break
     return T, fit, rmse, it, np.where(ok, idx, -1).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Normal estimation (PointCloud.estimate_normals with KDTreeSearchParamHybrid): numpy / pure-Python restatement
+# of Open3D 0.18's published algorithm as recalled (EstimateNormals.cpp, KDTreeFlann::SearchHybrid,
+# utility::ComputeCovariance, FastEigen3x3 after Eberly's robust 3x3 eigensolver).  PARITY UNPINNED: Open3D is
+# absent offline.  Call sites: /root/reference/src/defect_projection.py:181-186, :431-436,
+# /root/reference/src/pose_estimation.py:301-306.
+def _eigenvector0(A, ev):
+    import math
+    r0 = (A[0][0] - ev, A[0][1], A[0][2])
+    r1 = (A[0][1], A[1][1] - ev, A[1][2])
+    r2 = (A[0][2], A[1][2], A[2][2] - ev)
+
+    def cross(a, b):
+        return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
+
+    cs = [cross(r0, r1), cross(r0, r2), cross(r1, r2)]
+    ds = [c[0] * c[0] + c[1] * c[1] + c[2] * c[2] for c in cs]
+    imax, dmax = 0, ds[0]
+    if ds[1] > dmax:
+        dmax, imax = ds[1], 1
+    if ds[2] > dmax:
+        imax = 2
+    s = math.sqrt(ds[imax])
+    if s == 0.0:                                    # 0 / 0 in IEEE arithmetic (Python would raise)
+        return (float("nan"),) * 3
+    return tuple(x / s for x in cs[imax])
+
+
+def _eigenvector1(A, e0, ev):
+    import math
+    if abs(e0[0]) > abs(e0[1]):
+        inv = 1.0 / math.sqrt(e0[0] * e0[0] + e0[2] * e0[2])
+        U = (-e0[2] * inv, 0.0, e0[0] * inv)
+    else:
+        inv = 1.0 / math.sqrt(e0[1] * e0[1] + e0[2] * e0[2])
+        U = (0.0, e0[2] * inv, -e0[1] * inv)
+    V = (e0[1] * U[2] - e0[2] * U[1], e0[2] * U[0] - e0[0] * U[2], e0[0] * U[1] - e0[1] * U[0])
+    AU = tuple(A[r][0] * U[0] + A[r][1] * U[1] + A[r][2] * U[2] for r in range(3))
+    AV = tuple(A[r][0] * V[0] + A[r][1] * V[1] + A[r][2] * V[2] for r in range(3))
+    dot = lambda a, b: a[0] * b[0] + a[1] * b[1] + a[2] * b[2]   # noqa: E731
+    m00, m01, m11 = dot(U, AU) - ev, dot(U, AV), dot(V, AV) - ev
+    a00, a01, a11 = abs(m00), abs(m01), abs(m11)
+    if a00 >= a11:
+        if max(a00, a01) > 0.0:
+            if a00 >= a01:
+                m01 /= m00
+                m00 = 1.0 / math.sqrt(1.0 + m01 * m01)
+                m01 *= m00
+            else:
+                m00 /= m01
+                m01 = 1.0 / math.sqrt(1.0 + m00 * m00)
+                m00 *= m01
+            return tuple(m01 * U[k] - m00 * V[k] for k in range(3))
+        return U
+    if max(a11, a01) > 0.0:
+        if a11 >= a01:
+            m01 /= m11
+            m11 = 1.0 / math.sqrt(1.0 + m01 * m01)
+            m01 *= m11
+        else:
+            m11 /= m01
+            m01 = 1.0 / math.sqrt(1.0 + m11 * m11)
+            m11 *= m01
+        return tuple(m11 * U[k] - m01 * V[k] for k in range(3))
+    return U
+
+
+def fast_eigen3x3(C):
+    """Eigenvector of the smallest eigenvalue of the symmetric 3x3 matrix C (nested lists / array)."""
+    import math
+    C = [[float(C[r][c]) for c in range(3)] for r in range(3)]
+    mx = max(max(row) for row in C)
+    if mx == 0.0:
+        return (0.0, 0.0, 0.0)
+    A = [[C[r][c] / mx for c in range(3)] for r in range(3)]
+    norm = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2]
+    cross = lambda a, b: (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])   # noqa: E731
+    if norm > 0.0:
+        q = (A[0][0] + A[1][1] + A[2][2]) / 3.0
+        b00, b11, b22 = A[0][0] - q, A[1][1] - q, A[2][2] - q
+        p = math.sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) / 6.0)
+        c00 = b11 * b22 - A[1][2] * A[1][2]
+        c01 = A[0][1] * b22 - A[1][2] * A[0][2]
+        c02 = A[0][1] * A[1][2] - b11 * A[0][2]
+        det = (b00 * c00 - A[0][1] * c01 + A[0][2] * c02) / (p * p * p)
+        half_det = min(max(det * 0.5, -1.0), 1.0)
+        angle = math.acos(half_det) / 3.0
+        two_thirds_pi = 2.09439510239319549
+        beta2 = math.cos(angle) * 2.0
+        beta0 = math.cos(angle + two_thirds_pi) * 2.0
+        beta1 = -(beta0 + beta2)
+        e0, e1, e2 = q + p * beta0, q + p * beta1, q + p * beta2
+        if half_det >= 0.0:
+            v2 = _eigenvector0(A, e2)
+            if e2 < e0 and e2 < e1:
+                return v2
+            v1 = _eigenvector1(A, v2, e1)
+            if e1 < e0 and e1 < e2:
+                return v1
+            return cross(v1, v2)
+        v0 = _eigenvector0(A, e0)
+        if e0 < e1 and e0 < e2:
+            return v0
+        v1 = _eigenvector1(A, v0, e1)
+        if e1 < e0 and e1 < e2:
+            return v1
+        return cross(v0, v1)
+    if C[0][0] < C[1][1] and C[0][0] < C[2][2]:
+        return (1.0, 0.0, 0.0)
+    if C[1][1] < C[0][0] and C[1][1] < C[2][2]:
+        return (0.0, 1.0, 0.0)
+    return (0.0, 0.0, 1.0)
+
+
+def hybrid_neighbours(points, i, radius, max_nn):
+    """Indices of the max_nn nearest points of points[i] (itself included) with squared distance < radius^2,
+    ordered by (distance, index); every operation of the distance individually rounded (float64)."""
+    d = points[i] - points
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    cand = np.nonzero(d2 < radius * radius)[0]
+    order = np.lexsort((cand, d2[cand]))
+    return cand[order][:max_nn]
+
+
+def neighbourhood_covariance(points, idx):
+    """utility::ComputeCovariance: nine cumulants summed in the order of idx, then E[xx^T] - E[x]E[x]^T."""
+    c = [0.0] * 9
+    for j in idx:
+        x, y, z = float(points[j, 0]), float(points[j, 1]), float(points[j, 2])
+        c[0] += x; c[1] += y; c[2] += z                                   # noqa: E702
+        c[3] += x * x; c[4] += x * y; c[5] += x * z                       # noqa: E702
+        c[6] += y * y; c[7] += y * z; c[8] += z * z                       # noqa: E702
+    m = float(len(idx))
+    c = [v / m for v in c]
+    return [[c[3] - c[0] * c[0], c[4] - c[0] * c[1], c[5] - c[0] * c[2]],
+            [c[4] - c[0] * c[1], c[6] - c[1] * c[1], c[7] - c[1] * c[2]],
+            [c[5] - c[0] * c[2], c[7] - c[1] * c[2], c[8] - c[2] * c[2]]]
+
+
+def estimate_normals(points, radius, max_nn=30, normals=None):
+    """(normals [n,3], neighbour counts [n], covariances [n,3,3]) for small clouds (O(n^2) distances)."""
+    points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    n = len(points)
+    has = normals is not None and len(normals) == n and n > 0
+    out = np.zeros((n, 3))
+    counts = np.zeros(n, np.int32)
+    covs = np.zeros((n, 3, 3))
+    for i in range(n):
+        idx = hybrid_neighbours(points, i, radius, max_nn) if np.all(np.isfinite(points[i])) else np.zeros(0, np.int64)
+        counts[i] = len(idx)
+        C = neighbourhood_covariance(points, idx) if len(idx) >= 3 else [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]
+        covs[i] = C
+        v = fast_eigen3x3(C)
+        if v[0] * v[0] + v[1] * v[1] + v[2] * v[2] == 0.0:
+            v = tuple(normals[i]) if has else (0.0, 0.0, 1.0)
+        if has and v[0] * normals[i][0] + v[1] * normals[i][1] + v[2] * normals[i][2] < 0.0:
+            v = (-v[0], -v[1], -v[2])
+        out[i] = v
+    return out, counts, covs

@@ -142,3 +142,14 @@ def test_icp_grid_search_equals_the_scan_bit_for_bit(ctx, monkeypatch):
         assert a["inlier_rmse"] == b["inlier_rmse"]
         assert np.array_equal(a["transformation"], b["transformation"]), dist
     assert (a["correspondence"] >= 0).any()
+    # NaN points: a NaN target point is nobody's neighbour, a NaN source point has none (float64 -> int32 of a NaN is
+    # INT_MIN on the device: the cell coordinate must never see it)
+    V2, src2 = V.copy(), src.copy()
+    V2[7] = np.nan
+    src2[3] = np.nan
+    monkeypatch.setenv("DP_ICP_GRID", "1")
+    a = ctx.icp_point_to_plane(src2, V2, vn, 3.0, want_correspondence=True, max_iteration=2)
+    monkeypatch.setenv("DP_ICP_GRID", "0")
+    b = ctx.icp_point_to_plane(src2, V2, vn, 3.0, want_correspondence=True, max_iteration=2)
+    assert np.array_equal(a["correspondence"], b["correspondence"]) and a["correspondence"][3] == -1
+    assert not (a["correspondence"] == 7).any() and np.array_equal(a["transformation"], b["transformation"])

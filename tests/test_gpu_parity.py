@@ -711,8 +711,11 @@ def test_depth_projection_path_matches_reference(built_lib, orc):
     assert np.array_equal(ali, g["d_proj_aligned"]) and np.array_equal(offs, g["d_proj_offset"])
     o2, a2 = dpj.align_to_surface(g["d_point3d_050"], target, offset=0.1)
     assert np.array_equal(o2, g["d_align_offset_01"]) and np.array_equal(a2, g["d_align_aligned_01"])
-    with pytest.raises(ValueError, match="normals"):
-        dpj.align_to_surface(g["d_point3d_050"], dpj.PointCloud(g["d_target_points"]))
+    bare = dpj.PointCloud(g["d_target_points"])                   # no normals: estimated in place like :431-436
+    o3, a3 = dpj.align_to_surface(g["d_point3d_050"], bare, offset=0.1)
+    assert bare.has_normals() and np.array_equal(a3, a2)
+    o4, _ = dpj.align_to_surface(g["d_point3d_050"], dpj.PointCloud(bare.points, normals=bare.normals), offset=0.1)
+    assert np.array_equal(o3, o4)
     with pytest.raises(ValueError, match="uint16"):
         dpj.heatmap_to_point3d(heat, depth.astype(np.float32), K)
 

@@ -186,3 +186,30 @@ def test_icp_oracle_recovers_a_known_pose(orc):
     assert np.array_equal(corr, np.arange(0, len(V), 2))              # every point found its own vertex
     T1, _, _, it1, _ = orc.icp_point_to_plane(src, V, vn, 5.0, max_iteration=1)
     assert it1 == 1 and np.abs(T1 - T).max() < np.abs(np.eye(4) - T).max()
+
+
+# ------------------------------------------------------------------ normal estimation (8f #1 / #4)
+def test_normals_oracle_against_numpy_eigh(orc):
+    """The restated closed-form solver returns numpy's eigenvector of the smallest eigenvalue; the hybrid search
+    keeps the max_nn nearest within the radius, the point itself included."""
+    rng = np.random.default_rng(0)
+    S = rng.normal(size=(600, 3))
+    S /= np.linalg.norm(S, axis=1, keepdims=True)
+    S *= 40.0
+    N, cnt, covs = orc.estimate_normals(S, 12.0, 30)
+    w, v = np.linalg.eigh(covs)
+    assert np.abs(np.abs((v[:, :, 0] * N).sum(1)) - 1.0).max() < 1e-9
+    assert np.abs((N * S).sum(1) / 40.0).min() > 0.97                 # radial on a sphere
+    assert cnt.max() <= 30 and cnt.min() >= 3
+    i = 17
+    d2 = ((S - S[i]) ** 2).sum(1)
+    assert cnt[i] == min(30, int((d2 < 144.0).sum()))
+    assert orc.hybrid_neighbours(S, i, 12.0, 30)[0] == i
+    flat = np.c_[rng.uniform(-1, 1, (200, 2)), np.zeros(200)]
+    assert np.all(np.abs(orc.estimate_normals(flat, 0.5, 30)[0][:, 2]) > 1 - 1e-12)
+    lonely, c1, _ = orc.estimate_normals(S, 1e-3, 30)
+    assert np.all(c1 == 1) and np.all(lonely == [0.0, 0.0, 1.0])     # fewer than 3 neighbours
+    kept = orc.estimate_normals(S, 12.0, 30, normals=-S)[0]
+    assert np.all((kept * S).sum(1) < 0.0)                            # existing normals keep their side
+    assert orc.fast_eigen3x3(np.zeros((3, 3))) == (0.0, 0.0, 0.0)
+    assert orc.fast_eigen3x3(np.diag([3.0, 1.0, 2.0])) == (0.0, 1.0, 0.0)
