@@ -733,7 +733,17 @@ int dp_align_to_surface(dp_ctx *ctx, const double *query, int stride, int64_t n,
         dal = aligned_points ? ctx->tmp[4].as<double>() : nullptr;
         di = idx ? ctx->tmp[5].as<int32_t>() : nullptr;
     }
-    CK(launch_nearest(dq, stride, n, dt, m, dn, offset, di, dal, doff, s), "dp_align_to_surface: launch");
+    // Large searches go through the uniform grid over the target (built per call; ring search, same result bit for
+    // bit); DP_NN_GRID=0 keeps the tiled scan of the whole target for A/B measurements.
+    const char *knob = getenv("DP_NN_GRID");
+    IcpGridView gv;
+    gv.tps = nullptr;
+    if ((knob ? atoi(knob) : 1) && m >= 4096 && m < (int64_t)1 << 31 && (double)n * (double)m >= 134217728.0) {
+        CK(ctx->tmp[6].ensure(icp_grid_bytes(m)), "dp_align_to_surface: grid");
+        CK(icp_grid_build(dt, dn, m, 0.0, 1, ctx->tmp[6].p, &gv, s), "dp_align_to_surface: grid build");
+    }
+    if (gv.tps) CK(launch_nearest_grid(dq, stride, n, gv, dn != nullptr, offset, di, dal, doff, s), "dp_align_to_surface: launch");
+    else CK(launch_nearest(dq, stride, n, dt, m, dn, offset, di, dal, doff, s), "dp_align_to_surface: launch");
     if (mem == DP_HOST) {
         if (offset_points) CK(cudaMemcpyAsync(offset_points, doff, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_align_to_surface: D2H");
         if (aligned_points) CK(cudaMemcpyAsync(aligned_points, dal, (size_t)n * 24, cudaMemcpyDeviceToHost, s), "dp_align_to_surface: D2H");

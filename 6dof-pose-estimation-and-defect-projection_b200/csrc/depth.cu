@@ -182,6 +182,76 @@ k_nearest(const double *__restrict__ q, int stride, long long n, const double *_
     }
 }
 
+// The same search on the uniform grid of icp.cu (cells sized by the point density): the query's cell, then the shells
+// of cells around it, until the best distance found is smaller than the distance to everything not yet visited.
+// Same distance arithmetic, ties to the smaller ORIGINAL index: the result equals the scan's bit for bit.
+__global__ void __launch_bounds__(NN_THREADS)
+k_nearest_grid(const double *__restrict__ q, int stride, long long n, const double *__restrict__ tps,
+               const double *__restrict__ tns, const uint32_t *__restrict__ orig, const int32_t *__restrict__ cell_start,
+               const int32_t *__restrict__ cell_end, IcpGrid g, double offset, int32_t *__restrict__ idx_out,
+               double *__restrict__ aligned, double *__restrict__ offset_pts)
+{
+    const long long i = blockIdx.x * (long long)NN_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const double qp[3] = {q[i * stride], q[i * stride + 1], q[i * stride + 2]};
+    double best = INFINITY;
+    int bk = -1;
+    uint32_t bo = 0xffffffffu;
+    if (qp[0] == qp[0] && qp[1] == qp[1] && qp[2] == qp[2]) {
+        int c[3];
+        double slack = 1e-9 * g.cell;                    // cell coordinates are rounded: keep the bound on the safe side
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            c[k] = grid_coord(qp[k], g.lo[k], g.inv_cell, g.dim[k]);
+            slack += 1e-12 * (fabs(qp[k]) + fabs(g.lo[k]) + g.cell * g.dim[k]);
+        }
+        const int rmax = max(max(g.dim[0], g.dim[1]), g.dim[2]);
+        for (int r = 0; r < rmax; ++r) {
+            const int z0 = max(c[2] - r, 0), z1 = min(c[2] + r, g.dim[2] - 1);
+            const int y0 = max(c[1] - r, 0), y1 = min(c[1] + r, g.dim[1] - 1);
+            const int x0 = max(c[0] - r, 0), x1 = min(c[0] + r, g.dim[0] - 1);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    // inside the shell only the two end cells of the row are new
+                    const bool whole = (z == c[2] - r) || (z == c[2] + r) || (y == c[1] - r) || (y == c[1] + r);
+                    const int step = (whole || r == 0) ? 1 : 2 * r;
+                    for (int x = c[0] - r; x <= c[0] + r; x += step) {
+                        if (x < x0 || x > x1) continue;
+                        const int cell = (z * g.dim[1] + y) * g.dim[0] + x;
+                        const int k0 = cell_start[cell], k1 = cell_end[cell];
+                        for (int k = k0; k < k1; ++k) {
+                            const double dx = __dsub_rn(qp[0], tps[3 * k]), dy = __dsub_rn(qp[1], tps[3 * k + 1]),
+                                         dz = __dsub_rn(qp[2], tps[3 * k + 2]);
+                            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                            const uint32_t o = orig[k];
+                            if (d2 < best || (d2 == best && o < bo)) { best = d2; bk = k; bo = o; }
+                        }
+                    }
+                }
+            // distance from the query to everything outside the block of cells visited so far (faces at the rim of
+            // the grid are open: no target lies beyond them)
+            double bound = INFINITY;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (c[k] - r > 0) bound = fmin(bound, qp[k] - (g.lo[k] + (double)(c[k] - r) * g.cell));
+                if (c[k] + r + 1 < g.dim[k]) bound = fmin(bound, g.lo[k] + (double)(c[k] + r + 1) * g.cell - qp[k]);
+            }
+            if (bound == INFINITY) break;                // the whole grid has been visited
+            bound -= slack;
+            if (bound > 0.0 && best < bound * bound) break;
+        }
+    }
+    if (idx_out) idx_out[i] = bk >= 0 ? (int32_t)bo : -1;
+    if (bk >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double p = tps[3 * bk + k];
+            if (aligned) aligned[3 * i + k] = p;
+            if (offset_pts) offset_pts[3 * i + k] = __dadd_rn(p, __dmul_rn(tns[3 * bk + k], offset));
+        }
+    }
+}
+
 }  // namespace
 
 size_t depth_select_scratch_bytes(int64_t n_elems)
@@ -230,6 +300,16 @@ cudaError_t launch_nearest(const double *q, int stride, int64_t n, const double 
     if (n <= 0) return cudaSuccess;
     k_nearest<<<(unsigned)((n + NN_THREADS - 1) / NN_THREADS), NN_THREADS, 0, s>>>(q, stride, n, target, m, normals, offset, idx,
                                                                                  aligned, offset_pts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nearest_grid(const double *q, int stride, int64_t n, const IcpGridView &gv, bool has_normals, double offset,
+                                int32_t *idx, double *aligned, double *offset_pts, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_nearest_grid<<<(unsigned)((n + NN_THREADS - 1) / NN_THREADS), NN_THREADS, 0, s>>>(
+        q, stride, n, gv.tps, has_normals ? gv.tns : nullptr, gv.orig, gv.cell_start, gv.cell_end, gv.grid, offset, idx, aligned,
+        has_normals ? offset_pts : nullptr);
     return cudaGetLastError();
 }
 

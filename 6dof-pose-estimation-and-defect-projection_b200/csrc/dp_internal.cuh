@@ -152,6 +152,9 @@ cudaError_t launch_calc_coordinates(const int32_t *xs, const int32_t *ys, int64_
                                     const double *K, double *out3, unsigned char *valid, cudaStream_t s);
 cudaError_t launch_nearest(const double *q, int stride, int64_t n, const double *target, int64_t m, const double *normals,
                            double offset, int32_t *idx, double *aligned, double *offset_pts, cudaStream_t s);
+struct IcpGridView;
+cudaError_t launch_nearest_grid(const double *q, int stride, int64_t n, const IcpGridView &gv, bool has_normals, double offset,
+                                int32_t *idx, double *aligned, double *offset_pts, cudaStream_t s);
 
 // ---- prep.cu -------------------------------------------------------------------------------
 // mm: 4 device long longs (ordered max, ordered min, NaN flag, count)
@@ -171,7 +174,7 @@ constexpr int ICP_GRID_MIN_CELLS = 216;
 constexpr int ICP_GRID_MAX_DIM = 96;   // cells per axis of the target grid (2 x 3.5 MB of cell ranges at most)
 struct IcpGrid {
     double lo[3];
-    double inv_cell;
+    double inv_cell, cell;
     int dim[3];
 };
 struct IcpGridView {

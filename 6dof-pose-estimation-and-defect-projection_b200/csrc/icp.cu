@@ -303,8 +303,17 @@ cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double
         ext = hi - lo > ext ? hi - lo : ext;
     }
     out->tps = nullptr;                                              // "no grid": the caller scans the target instead
-    double cell = max_dist * (1.0 + 1e-9);                           // >= the search radius, with room for rounding
-    if (ext / ICP_GRID_MAX_DIM > cell) cell = ext / ICP_GRID_MAX_DIM;
+    double cell;
+    if (max_dist > 0.0) {
+        cell = max_dist * (1.0 + 1e-9);                              // >= the search radius, with room for rounding
+        if (ext / ICP_GRID_MAX_DIM > cell) cell = ext / ICP_GRID_MAX_DIM;
+    } else {
+        // no radius (unbounded nearest neighbour, searched ring by ring): a handful of points per occupied cell of
+        // a surface-like cloud, which fills about d^2 of the d^3 cells
+        double d = ceil(sqrt((double)m / 16.0));
+        d = d < 1.0 ? 1.0 : (d > ICP_GRID_MAX_DIM ? (double)ICP_GRID_MAX_DIM : d);
+        cell = ext > 0.0 ? ext / d : 1.0;
+    }
     if (!(cell > 0.0) || !(cell < 1e300)) return cudaSuccess;        // infinite coordinates
     g.inv_cell = 1.0 / cell;
     for (int k = 0; k < 3; ++k) {
@@ -320,6 +329,7 @@ cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double
     if ((e = cudaMemsetAsync(cell_start, 0, cells * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(cell_end, 0, cells * 4, s)) != cudaSuccess) return e;
     k_icp_grid_gather<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(tp, tn, keys, vals, m, tps, tns, cell_start, cell_end);
+    g.cell = cell;
     out->grid = g;
     out->tps = tps; out->tns = tns; out->orig = vals; out->cell_start = cell_start; out->cell_end = cell_end;
     return cudaGetLastError();

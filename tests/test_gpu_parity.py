@@ -736,3 +736,37 @@ def test_depth_path_full_size_properties(ctx, orc):
     _, ali, idx = ctx.align_to_surface(q, tp, None, 0.0)
     ridx = orc.nearest_points(q, tp)
     assert np.array_equal(idx, ridx) and np.array_equal(ali, tp[ridx])
+
+
+def test_align_to_surface_grid_search_equals_the_scan(ctx, monkeypatch):
+    """dp_align_to_surface on large inputs walks a uniform grid over the target ring by ring; DP_NN_GRID=0 keeps the
+    tiled scan.  Same indices, aligned and offset points bit for bit -- for queries on the surface, in the hollow of
+    the torus, far outside the target's box, on duplicated target points (ties to the smaller index) and NaN."""
+    rng = np.random.default_rng(5)
+    V, F = synth.param_mesh(300, 200, seed=3)
+    tp = V.astype(np.float64)
+    tp = np.concatenate([tp, tp[:1000]])                             # duplicates: equal distances
+    tn = rng.normal(size=tp.shape)
+    tn /= np.linalg.norm(tn, axis=1, keepdims=True)
+    q = np.concatenate([tp[::9] + rng.normal(scale=0.4, size=tp[::9].shape),      # near the surface
+                        tp[:1000],                                                # exactly on duplicated points
+                        rng.uniform(-15.0, 15.0, (500, 3)),                       # the hollow around the axis
+                        rng.uniform(-1.0, 1.0, (500, 3)) * 5000.0,                # far outside the box
+                        np.zeros((1, 3))])
+    q = np.c_[q, np.ones(len(q))]                                    # [x, y, z, intensity] like heatmap_to_point3d
+    q[17, :3] = np.nan
+    assert len(q) * len(tp) >= 2 ** 27
+    monkeypatch.setenv("DP_NN_GRID", "1")
+    o1, a1, i1 = ctx.align_to_surface(q, tp, tn, 0.5)
+    monkeypatch.setenv("DP_NN_GRID", "0")
+    o0, a0, i0 = ctx.align_to_surface(q, tp, tn, 0.5)
+    assert np.array_equal(i1, i0) and i1[17] == -1 and (np.delete(i1, 17) >= 0).all()
+    ok = i1 >= 0
+    assert np.array_equal(a1[ok], a0[ok]) and np.array_equal(o1[ok], o0[ok])
+    assert np.array_equal(a1[ok], tp[i1[ok]])
+    on_dup = slice(len(tp[::9]), len(tp[::9]) + 1000)
+    assert np.array_equal(i1[on_dup], np.arange(1000))               # the smaller of the two equal indices
+    # without normals only the nearest points come back
+    monkeypatch.setenv("DP_NN_GRID", "1")
+    _, a2, i2 = ctx.align_to_surface(q, tp, None, 0.0)
+    assert np.array_equal(i2, i1) and np.array_equal(a2[ok], a1[ok])
