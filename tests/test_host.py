@@ -136,3 +136,21 @@ def test_load_extrinsics_schema(tmp_path):
     synth.write_scene_dir(str(tmp_path), K, (H, W), color_to_depth=c2d)
     a, b = dpj.load_extrinsics(str(tmp_path))
     assert np.array_equal(a, c2d) and np.allclose(a @ b, np.eye(4), atol=1e-12)
+
+
+def test_normals_facade_rejects_what_it_does_not_implement_before_touching_the_gpu():
+    """Only the hybrid search the reference uses (and Open3D's default fast eigen solver) is implemented; anything
+    else raises instead of silently doing something different.  Empty clouds never reach the device."""
+    from defectproj import defect_projection as dpj
+    from defectproj import pose_estimation as pe
+    pcd = dpj.PointCloud(np.zeros((4, 3)))
+    with pytest.raises(NotImplementedError):
+        pcd.estimate_normals()
+    with pytest.raises(NotImplementedError):
+        pcd.estimate_normals(search_param=dpj.KDTreeSearchParamHybrid(1.0, 5), fast_normal_computation=False)
+    empty = dpj.PointCloud()
+    assert empty.estimate_normals(search_param=dpj.KDTreeSearchParamHybrid(radius=2, max_nn=5)) is empty
+    assert not empty.has_normals()
+    assert pe.estimate_normals(dpj.PointCloud(), {"any": 1}).normals.shape == (0, 3)
+    p = dpj.KDTreeSearchParamHybrid(radius=10, max_nn=30)
+    assert (p.radius, p.max_nn) == (10.0, 30)
