@@ -319,10 +319,138 @@ __device__ __forceinline__ float distribute_cost(const float cl[7], const float 
     return best;
 }
 
+// C(id, 1..7) of a node from its children (tables of internal children from ctab, read past L1: another thread may
+// have written them; a single triangle costs A * c_prim for every i)
+__device__ __forceinline__ void load_table(long long id, long long n, const float *ctab, const float *blo, const float *bhi,
+                                           float c_prim, float out[7])
+{
+    if (id >= n - 1) {
+        float lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = __ldcg(&blo[3 * id + k]); hi[k] = __ldcg(&bhi[3 * id + k]); }
+        const float c = half_area(lo, hi) * c_prim;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) out[i] = c;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) out[i] = __ldcg(&ctab[8 * id + i]);
+    }
+}
+
+__device__ __forceinline__ void node_table(const float cl[7], const float cr[7], float A, int P, float c_prim, float C[7])
+{
+    const float c_leaf = P <= LEAF_MAX ? A * (float)P * c_prim : INFINITY;
+    C[0] = fminf(c_leaf, distribute_cost(cl, cr, 8, nullptr) + A * C_NODE);
+#pragma unroll
+    for (int i = 2; i <= 7; ++i) C[i - 1] = fminf(distribute_cost(cl, cr, i, nullptr), C[i - 2]);
+}
+
+// Tree rotations at `cur` (Kensler 2008), applied by the thread that completes the node on the way up.  With
+// children L = (l0, l1) and R = (r0, r1) the candidates are
+//   child <-> grandchild:       L changes places with r_j (R keeps the other one), or R with l_i;
+//   grandchild <-> grandchild:  l_i changes places with r_j  (DP_ROTATE_GG, untangles two interleaved children);
+// the one that shrinks the summed surface area of the restructured children most is applied.  The node's own box
+// and triangle set do not change, so nothing above is affected, and both subtrees are complete, so nobody else is
+// reading them.  A restructured child's triangles stop being one interval of the sorted order: its last[] is
+// rewritten so that last - first + 1 stays its triangle count (the only use of the interval of a node with more
+// than LEAF_MAX triangles); candidates that would leave such a child with LEAF_MAX triangles or fewer are skipped.
+struct RotBox { float lo[3], hi[3]; };
+__device__ __forceinline__ RotBox rot_union(const RotBox &a, const RotBox &b)
+{
+    RotBox r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.lo[k] = fminf(a.lo[k], b.lo[k]); r.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+    return r;
+}
+
+__device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *left, int32_t *right, int32_t *parent,
+                                           const int32_t *first, int32_t *last, float *blo, float *bhi, float *ctab,
+                                           float c_prim, int gg)
+{
+    auto count = [&](long long id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
+    auto box = [&](long long id) -> RotBox {
+        RotBox r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r.lo[k] = __ldcg(&blo[3 * id + k]); r.hi[k] = __ldcg(&bhi[3 * id + k]); }
+        return r;
+    };
+    // make node `id` the parent of (c0, c1) with the given box and count, and refresh its cost table
+    auto rebuild = [&](long long id, long long c0, long long c1, const RotBox &bx, int cnt) {
+        left[id] = (int32_t)c0; right[id] = (int32_t)c1;
+        parent[c0] = (int32_t)id; parent[c1] = (int32_t)id;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { blo[3 * id + k] = bx.lo[k]; bhi[3 * id + k] = bx.hi[k]; }
+        last[id] = first[id] + cnt - 1;
+        if (ctab) {
+            float cl[7], cr[7], C[7];
+            load_table(c0, n, ctab, blo, bhi, c_prim, cl);
+            load_table(c1, n, ctab, blo, bhi, c_prim, cr);
+            node_table(cl, cr, half_area(bx.lo, bx.hi), cnt, c_prim, C);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) ctab[8 * id + i] = C[i];
+        }
+    };
+    const long long ch[2] = {left[cur], right[cur]};
+    const bool inner[2] = {ch[0] < n - 1, ch[1] < n - 1};
+    if (!inner[0] && !inner[1]) return;
+    RotBox cb[2] = {box(ch[0]), box(ch[1])};
+    long long g[2][2] = {{-1, -1}, {-1, -1}};
+    RotBox gb[2][2];
+    int gc[2][2] = {{0, 0}, {0, 0}};
+    float area[2];
+    int cc[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        area[s] = half_area(cb[s].lo, cb[s].hi);
+        cc[s] = count(ch[s]);
+        if (!inner[s]) continue;
+        g[s][0] = left[ch[s]]; g[s][1] = right[ch[s]];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) { gb[s][w] = box(g[s][w]); gc[s][w] = count(g[s][w]); }
+    }
+    float best_gain = 0.0f;
+    int best = -1;                       // 0..3: child 1-s <-> g[s][w] (code 2*s + w);  4..7: g[0][i] <-> g[1][j] (code 4 + 2*i + j)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (!inner[s]) continue;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            if (cc[1 - s] + gc[s][1 - w] <= LEAF_MAX) continue;
+            const RotBox nb = rot_union(cb[1 - s], gb[s][1 - w]);
+            const float gain = area[s] - half_area(nb.lo, nb.hi);
+            if (gain > best_gain && gain > 1e-6f * area[s]) { best_gain = gain; best = 2 * s + w; }
+        }
+    }
+    if (gg && inner[0] && inner[1]) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (gc[1][j] + gc[0][1 - i] <= LEAF_MAX || gc[0][i] + gc[1][1 - j] <= LEAF_MAX) continue;
+                const RotBox n0 = rot_union(gb[1][j], gb[0][1 - i]), n1 = rot_union(gb[0][i], gb[1][1 - j]);
+                const float gain = area[0] + area[1] - half_area(n0.lo, n0.hi) - half_area(n1.lo, n1.hi);
+                if (gain > best_gain && gain > 1e-6f * (area[0] + area[1])) { best_gain = gain; best = 4 + 2 * i + j; }
+            }
+    }
+    if (best < 0) return;
+    if (best < 4) {
+        const int s = best >> 1, w = best & 1;
+        const long long B = ch[s], A = ch[1 - s], moved = g[s][w], stay = g[s][1 - w];
+        if (left[cur] == (int32_t)A) left[cur] = (int32_t)moved; else right[cur] = (int32_t)moved;
+        parent[moved] = (int32_t)cur;
+        rebuild(B, A, stay, rot_union(cb[1 - s], gb[s][1 - w]), cc[1 - s] + gc[s][1 - w]);
+    } else {
+        const int i = (best >> 1) & 1, j = best & 1;
+        rebuild(ch[0], g[1][j], g[0][1 - i], rot_union(gb[1][j], gb[0][1 - i]), gc[1][j] + gc[0][1 - i]);
+        rebuild(ch[1], g[0][i], g[1][1 - j], rot_union(gb[0][i], gb[1][1 - j]), gc[0][i] + gc[1][1 - j]);
+    }
+}
+
+// Bottom-up pass over the binary tree, one thread per triangle walking towards the root; the second thread to arrive
+// at a node completes it: box, optional rotation (nodes of at most rot_max triangles), cost table of the collapse.
 __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict__ F, const uint32_t *__restrict__ sorted_tri,
-                         long long n, const int32_t *__restrict__ parent, const int32_t *__restrict__ left,
-                         const int32_t *__restrict__ right, const int32_t *__restrict__ first,
-                         const int32_t *__restrict__ last, float *blo, float *bhi, int *flags, float *ctab, float c_prim)
+                         long long n, int32_t *parent, int32_t *left, int32_t *right, const int32_t *first, int32_t *last,
+                         float *blo, float *bhi, int *flags, float *ctab, float c_prim, int rot_min, int rot_max, int rot_gg)
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -332,51 +460,29 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
 #pragma unroll
     for (int k = 0; k < 3; ++k) { blo[3 * id + k] = lo[k]; bhi[3 * id + k] = hi[k]; }
     if (n == 1) return;
-    float mine[7];                                        // C(id, 1..7) of the subtree this thread carries upwards
-    {
-        const float c = half_area(lo, hi) * c_prim;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) mine[i] = c;
-    }
     long long cur = parent[id];
     for (;;) {
         __threadfence();
         if (atomicAdd(&flags[cur], 1) == 0) return;       // the sibling subtree is not done yet
-        const bool id_is_left = left[cur] == id;
-        const long long sib = id_is_left ? right[cur] : left[cur];
-        float slo[3], shi[3];
+        const int P = last[cur] - first[cur] + 1;
+        if (rot_max > 0 && P <= rot_max && P >= rot_min && P > 2 * LEAF_MAX) try_rotate(cur, n, left, right, parent, first, last, blo, bhi, ctab, c_prim, rot_gg);
+        const long long L = left[cur], R = right[cur];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            slo[k] = __ldcg(&blo[3 * sib + k]);
-            shi[k] = __ldcg(&bhi[3 * sib + k]);
-            lo[k] = fminf(lo[k], slo[k]);
-            hi[k] = fmaxf(hi[k], shi[k]);
+            lo[k] = fminf(__ldcg(&blo[3 * L + k]), __ldcg(&blo[3 * R + k]));
+            hi[k] = fmaxf(__ldcg(&bhi[3 * L + k]), __ldcg(&bhi[3 * R + k]));
             blo[3 * cur + k] = lo[k];
             bhi[3 * cur + k] = hi[k];
         }
         if (ctab) {
-            float other[7];
-            if (sib >= n - 1) {
-                const float c = half_area(slo, shi) * c_prim;
+            float cl[7], cr[7], C[7];
+            load_table(L, n, ctab, blo, bhi, c_prim, cl);
+            load_table(R, n, ctab, blo, bhi, c_prim, cr);
+            node_table(cl, cr, half_area(lo, hi), P, c_prim, C);
 #pragma unroll
-                for (int i = 0; i < 7; ++i) other[i] = c;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 7; ++i) other[i] = __ldcg(&ctab[8 * sib + i]);
-            }
-            const float *cl = id_is_left ? mine : other, *cr = id_is_left ? other : mine;
-            const float A = half_area(lo, hi);
-            const int P = last[cur] - first[cur] + 1;
-            float C[7];
-            const float c_leaf = P <= LEAF_MAX ? A * (float)P * c_prim : INFINITY;
-            C[0] = fminf(c_leaf, distribute_cost(cl, cr, 8, nullptr) + A * C_NODE);
-#pragma unroll
-            for (int i = 2; i <= 7; ++i) C[i - 1] = fminf(distribute_cost(cl, cr, i, nullptr), C[i - 2]);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) { mine[i] = C[i]; ctab[8 * cur + i] = C[i]; }
+            for (int i = 0; i < 7; ++i) ctab[8 * cur + i] = C[i];
         }
         if (cur == 0) return;
-        id = cur;
         cur = parent[cur];
     }
 }
@@ -863,6 +969,37 @@ static int knob_dp_max_count()
     if (v < 0) { const char *e = getenv("DP_HYBRID_COUNT"); v = e ? atoi(e) : 512; }
     return v;
 }
+// Tree rotations in k_binfit: subtrees of DP_ROTATE_MIN .. DP_ROTATE_MAX triangles may rotate (MAX = 0: none).
+// Measured on B200 (1024^2 dense rays; profiles/r1d_sweep_rotations*.log): the gain sits at the top of the tree --
+// rotating only subtrees of >= 1024 triangles gives 500k triangles 12.79 -> 12.63 nodes per ray (0.297 -> 0.293 ms)
+// and 5M triangles 14.80 -> 14.57 (0.439 -> 0.421 ms) at no build cost; rotating everything adds 0.1 / 0.7 ms to the
+// build for another 0.1 nodes per ray.  Grandchild <-> grandchild candidates (DP_ROTATE_GG) lower the surface area
+// further but not the node visits (12.73 / 14.97), further passes (DP_ROTATE_PASSES) cost a k_binfit each for
+// 0.1 nodes per ray: both stay off.
+static int knob_rotate_max()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DP_ROTATE_MAX"); v = e ? atoi(e) : 0x7fffffff; }
+    return v;
+}
+static int knob_rotate_min()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DP_ROTATE_MIN"); v = e ? atoi(e) : 1024; }
+    return v;
+}
+static int knob_rotate_gg()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DP_ROTATE_GG"); v = e ? atoi(e) : 0; }
+    return v;
+}
+static int knob_rotate_passes()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DP_ROTATE_PASSES"); v = e ? atoi(e) : 1; }
+    return v;
+}
 static float knob_c_prim()
 {
     static float v = -1.0f;
@@ -933,7 +1070,14 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     if ((e = cudaMemsetAsync(parent, 0xff, 2 * N * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
     if (n > 1) k_karras<<<blocks_for(n - 1, 256), 256, 0, s>>>(keys, n, left, right, parent, first, last);
-    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab, c_prim);
+    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab, c_prim,
+                                                knob_rotate_min(), knob_rotate_max(), knob_rotate_gg());
+    // further rotation passes over the rotated tree (each node looks at its new grandchildren once more)
+    for (int pass = 1; pass < knob_rotate_passes() && knob_rotate_max() > 0; ++pass) {
+        if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
+        k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab,
+                                                    c_prim, knob_rotate_min(), knob_rotate_max(), knob_rotate_gg());
+    }
 
     // top-down collapse, one launch per level of the wide tree
     {
