@@ -125,6 +125,10 @@ r = ctx.icp_point_to_plane(src, Vi, vn, 3.0)
 ms = wall(lambda: ctx.icp_point_to_plane(src, Vi, vn, 3.0), reps=2)
 fr["icp_20k_x_60k"] = {"ms_total": ms, "iterations": r["iterations"], "ms_per_iteration": ms / (r["iterations"] + 1),
                        "fitness": r["fitness"], "inlier_rmse": r["inlier_rmse"], "max_abs_error_vs_applied_pose": float(np.abs(r["transformation"] - Ti).max())}
+fr["estimate_normals_60k_radius2_nn5_ms"] = wall(lambda: ctx.estimate_normals(Vi, 2.0, 5), reps=3)
+fr["estimate_normals_60k_radius10_nn30_ms"] = wall(lambda: ctx.estimate_normals(Vi, 10.0, 30), reps=3)
+q_ = Vi[rng.integers(0, len(Vi), 20000)] + rng.normal(scale=0.5, size=(20000, 3))
+fr["align_to_surface_20k_x_60k_ms"] = wall(lambda: ctx.align_to_surface(q_, Vi, vn, 0.5), reps=3)
 out["f_rows"] = fr
 print("f_rows", json.dumps(fr), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
