@@ -298,6 +298,33 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
     return DP_OK;
 }
 
+int dp_update_vertices(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_update_vertices: no mesh (call dp_set_mesh first)");
+    if (nV != ctx->nV || vdtype != ctx->vdtype || (nV > 0 && !V))
+        return fail(ctx, DP_E_ARG, "dp_update_vertices: vertex count and type must be those of dp_set_mesh");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const cudaMemcpyKind kind = mem == DP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (nV) {
+        if (vdtype == DP_F64) CK(cudaMemcpyAsync(ctx->V64.p, V, (size_t)nV * 24, kind, s), "dp_update_vertices: copy V");
+        else CK(cudaMemcpyAsync(ctx->V.p, V, (size_t)nV * 12, kind, s), "dp_update_vertices: copy V");
+    }
+    ctx->has_cam = false;
+    if (ctx->has_bvh) {
+        // the object-frame hierarchy keeps its topology and is fitted again, in place, to the new vertices (the
+        // "no transform" pose pass rewrites the float32 vertex copy and the scene scale)
+        CK(pose_and_refit(vdtype == DP_F64 ? ctx->V64.p : ctx->V.p, vdtype, nV, ctx->F.as<int32_t>(), ctx->nF, nullptr,
+                          ctx->V.as<float>(), nullptr, ctx->obj, ctx->obj, ctx->topo, s),
+           "dp_update_vertices: refit");
+    } else if (nV && vdtype == DP_F64) {
+        CK(convert_f64_to_f32(ctx->V64.as<double>(), ctx->V.as<float>(), nV * 3, s), "dp_update_vertices: convert V");
+    }
+    if (mem == DP_HOST) CK(cudaStreamSynchronize(s), "dp_update_vertices: sync");
+    return DP_OK;
+}
+
 int dp_pose_mesh(dp_ctx *ctx, const double *T, void *stream)
 {
     if (!ctx || !T) return fail(ctx, DP_E_ARG, "dp_pose_mesh: bad arguments");

@@ -872,18 +872,20 @@ struct Mat34 {
 // v' = float32(((T0*x + T1*y) + T2*z) + T3) in float64: TriangleMesh.transform (:550) then the
 // float32 cast of from_legacy (:245).  Also reduces max |v'| into scale_bits.
 template <typename TV>
-__global__ void k_pose_vertices(const TV *__restrict__ V, long long nV, Mat34 T, float *out, double *out64,
+__global__ void k_pose_vertices(const TV *V, long long nV, Mat34 T, int identity, float *out, double *out64,
                                 unsigned *scale_bits)
 {
+    // `identity`: no arithmetic at all (the vertices as they are, even non-finite ones); V may then be `out` itself
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (i < nV) {
         const double x = V[3 * i], y = V[3 * i + 1], z = V[3 * i + 2];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double r = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.m[4 * k], x), __dmul_rn(T.m[4 * k + 1], y)),
-                                                 __dmul_rn(T.m[4 * k + 2], z)),
-                                       T.m[4 * k + 3]);
+            const double r = identity ? (k == 0 ? x : (k == 1 ? y : z))
+                                      : __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.m[4 * k], x), __dmul_rn(T.m[4 * k + 1], y)),
+                                                            __dmul_rn(T.m[4 * k + 2], z)),
+                                                  T.m[4 * k + 3]);
             const float f = (float)r;
             out[3 * i + k] = f;
             if (out64) out64[3 * i + k] = r;
@@ -1130,15 +1132,17 @@ cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t 
                            const Topology &topo, cudaStream_t s)
 {
     cudaError_t e;
+    // T_host == nullptr: the vertices as they are (in-place refit of `src` after dp_update_vertices)
     Mat34 T;
-    for (int k = 0; k < 12; ++k) T.m[k] = T_host[k];
+    for (int k = 0; k < 12; ++k) T.m[k] = T_host ? T_host[k] : (k % 5 == 0 ? 1.0 : 0.0);
+    const int identity = T_host == nullptr;
     if ((e = cudaMemsetAsync(dst.d_scale, 0, 4, s)) != cudaSuccess) return e;
     if (nV > 0) {
         if (vdtype == 1)
-            k_pose_vertices<double><<<blocks_for(nV, 256), 256, 0, s>>>(static_cast<const double *>(V), nV, T, Vposed,
+            k_pose_vertices<double><<<blocks_for(nV, 256), 256, 0, s>>>(static_cast<const double *>(V), nV, T, identity, Vposed,
                                                                         Vposed64, reinterpret_cast<unsigned *>(dst.d_scale));
         else
-            k_pose_vertices<float><<<blocks_for(nV, 256), 256, 0, s>>>(static_cast<const float *>(V), nV, T, Vposed,
+            k_pose_vertices<float><<<blocks_for(nV, 256), 256, 0, s>>>(static_cast<const float *>(V), nV, T, identity, Vposed,
                                                                        Vposed64, reinterpret_cast<unsigned *>(dst.d_scale));
     }
     dst.n_nodes = src.n_nodes;

@@ -40,6 +40,7 @@ SYMBOLS = {
     "dp_synchronize": (i32, [vp, vp]),
     "dp_set_mesh": (i32, [vp, vp, i32, i64, vp, i64, i32, vp]),
     "dp_build_bvh": (i32, [vp, vp]),
+    "dp_update_vertices": (i32, [vp, vp, i32, i64, i32, vp]),
     "dp_pose_mesh": (i32, [vp, vp, vp]),
     "dp_get_posed_vertices": (i32, [vp, vp, i32, i32, vp]),
     "dp_compact": (i32, [vp, vp, i32, i64, i32, i32, f64, vp, vp, i64, C.POINTER(i64), vp, i32, vp]),

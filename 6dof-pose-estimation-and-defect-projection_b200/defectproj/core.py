@@ -126,6 +126,23 @@ class Context:
         self._check(self._L.dp_build_bvh(self._h, self._stream(stream)))
         return self
 
+    def update_vertices(self, V, stream=None):
+        """New positions for the vertices of set_mesh (same count, dtype and faces): refit instead of a rebuild."""
+        if _is_torch(V):
+            import torch
+            if not V.is_cuda or V.dtype not in (torch.float32, torch.float64):
+                raise ValueError("vertex tensors must be float32/float64 CUDA tensors")
+            V = V.contiguous()
+            vd, n, mem = (DP_F64 if V.dtype == torch.float64 else DP_F32), V.shape[0], DP_DEVICE
+        else:
+            V = np.ascontiguousarray(V)
+            if V.dtype not in (np.float32, np.float64):
+                V = V.astype(np.float64)
+            V = V.reshape(-1, 3)
+            vd, n, mem = (DP_F64 if V.dtype == np.float64 else DP_F32), len(V), DP_HOST
+        self._check(self._L.dp_update_vertices(self._h, _ptr(V), vd, n, mem, self._stream(stream)))
+        return self
+
     def pose_mesh(self, T, stream=None):
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
         self._check(self._L.dp_pose_mesh(self._h, _ptr(T), self._stream(stream)))

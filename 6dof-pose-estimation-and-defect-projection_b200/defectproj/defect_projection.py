@@ -139,11 +139,19 @@ def _K(intrinsic):
 
 
 def _scene(V, F):
-    """Upload + BVH build, skipped when the same arrays were used by the previous call."""
+    """Upload + BVH build, skipped when the same arrays were used by the previous call.  The same model at new
+    vertex positions -- what run.py:109-110 hands over on every capture: the mesh moved by the current pose -- keeps
+    the hierarchy's topology and is refitted (dp_update_vertices) instead of rebuilt."""
     ctx = get_context()
     s = _SCENE
-    if not (s["V"] is not None and s["V"].shape == V.shape and s["V"].dtype == V.dtype and s["F"].shape == F.shape
-            and np.array_equal(s["V"], V) and np.array_equal(s["F"], F)):
+    same_faces = s["F"] is not None and s["F"].shape == F.shape and np.array_equal(s["F"], F)
+    same_layout = same_faces and s["V"].shape == V.shape and s["V"].dtype == V.dtype
+    if same_layout and np.array_equal(s["V"], V):
+        return ctx
+    if same_layout and len(F):
+        ctx.update_vertices(V)
+        s["V"] = V.copy()
+    else:
         ctx.set_mesh(V, F)
         ctx.build_bvh()
         s["V"], s["F"] = V.copy(), F.copy()

@@ -103,6 +103,11 @@ DP_API int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const
  * surface-area-guided collapse into compressed 8-wide nodes.  Asynchronous apart from one
  * 8-byte read-back per tree level. */
 DP_API int dp_build_bvh(dp_ctx *ctx, void *stream);
+/* New vertex positions for the mesh of dp_set_mesh (same count, type and faces): the reference hands ray_tracing a
+ * freshly transformed copy of the same model on every call (run.py:109-110) and rebuilds its scene from it
+ * (:253-254); here the hierarchy keeps its topology and is refitted in place to the new vertices (any valid
+ * hierarchy gives the same closest hits; the Morton order is that of the vertices dp_build_bvh saw). */
+DP_API int dp_update_vertices(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, int mem, void *stream);
 /* Camera-frame copy of the mesh: v' = float32(T * (double)v) (:549-550 then :245), followed by
  * a bottom-up refit of a second set of wide nodes that shares the object-frame topology.
  * T: 16 doubles on the HOST, row-major. */

@@ -48,6 +48,28 @@ with tempfile.TemporaryDirectory() as d:
                    "cpu_port_ms": cpu_ms, "cpu_cores": orc.num_threads()}
             out.append(row)
             print(json.dumps(row), flush=True)
+        # the production pattern: the same model at a new pose on every call (run.py:109-110) -> refit, not rebuild
+        moved = []
+        for k in range(12):
+            Tk = np.eye(4)
+            Tk[:3, :3] = synth.rot_z(3.0 * k)
+            moved.append(dpj.TriangleMesh(orc.transform_points(Vd, Tk), F))
+        dpj.ray_tracing(d, moved[0], heat, K, 0.75)
+        ts = []
+        for m in moved[1:]:
+            t0 = time.perf_counter()
+            dpj.ray_tracing(d, m, heat, K, 0.75)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts_rebuild = []
+        for m in moved[1:]:
+            dpj._SCENE["F"] = None                                   # what the call cost when every new pose meant a rebuild
+            t0 = time.perf_counter()
+            dpj.ray_tracing(d, m, heat, K, 0.75)
+            ts_rebuild.append((time.perf_counter() - t0) * 1e3)
+        row = {"mesh": mesh, "threshold": 0.75, "moving_mesh_refit_ms_median": float(np.median(ts)),
+               "moving_mesh_rebuild_ms_median": float(np.median(ts_rebuild))}
+        out.append(row)
+        print(json.dumps(row), flush=True)
         pr = cProfile.Profile()
         pr.enable()
         for _ in range(5):

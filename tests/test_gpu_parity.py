@@ -770,3 +770,66 @@ def test_align_to_surface_grid_search_equals_the_scan(ctx, monkeypatch):
     monkeypatch.setenv("DP_NN_GRID", "1")
     _, a2, i2 = ctx.align_to_surface(q, tp, None, 0.0)
     assert np.array_equal(i2, i1) and np.array_equal(a2[ok], a1[ok])
+
+
+def _moved(V, rz, t):
+    R = synth.rot_z(rz) @ synth.rot_x(0.4 * rz)
+    return V.astype(np.float64) @ R.T + np.asarray(t, dtype=np.float64)
+
+
+def test_update_vertices_refit_equals_a_rebuild(ctx):
+    """dp_update_vertices keeps the hierarchy's topology and refits it to the new vertex positions; the closest hits
+    do not depend on the hierarchy, so both frames give the bits of a fresh build on the moved mesh."""
+    V, F = synth.param_mesh(60, 40, seed=11)
+    K, H, W = synth.camera_720p()
+    pose = synth.fixed_pose()
+    heat = synth.gaussian_heatmap((H, W), dtype=np.float32)
+    Tc = np.eye(4)
+    Tc[:3, :3] = synth.rot_y(12.0)
+    Tc[:3, 3] = [5.0, -3.0, 560.0]
+    for dtype in (np.float32, np.float64):
+        Va, Vb = V.astype(dtype), _moved(V, 25.0, [4.0, -6.0, 9.0]).astype(dtype)
+
+        def both_frames():
+            o = ctx.project(heat, K, pose[None], 0.5, frame="object", want=("t_hit", "face"))
+            ctx.pose_mesh(Tc)
+            c = ctx.project(heat, K, None, 0.5, frame="camera", want=("t_hit", "face"))
+            return o, c, ctx.posed_vertices(dtype)
+
+        ctx.set_mesh(Va, F).build_bvh()
+        ctx.pose_mesh(Tc)
+        ctx.update_vertices(Vb)
+        with pytest.raises(Exception):
+            ctx.project(heat, K, None, 0.5, frame="camera")         # the camera-frame copy is stale until posed again
+        o1, c1, p1 = both_frames()
+        ctx.set_mesh(Vb, F).build_bvh()
+        o2, c2, p2 = both_frames()
+        assert o1["hits"] == o2["hits"] > 0 and c1["hits"] == c2["hits"] > 0
+        for a, b in ((o1, o2), (c1, c2)):
+            assert np.array_equal(a["face"], b["face"])
+            assert np.array_equal(a["t_hit"].view(np.uint32), b["t_hit"].view(np.uint32))
+        assert np.array_equal(p1, p2)
+        with pytest.raises(ValueError):
+            ctx.update_vertices(Vb[:-1])
+        with pytest.raises(ValueError):
+            ctx.update_vertices(Vb.astype(np.float64 if dtype == np.float32 else np.float32))
+
+
+def test_ray_tracing_facade_refits_a_moved_mesh(tmp_path):
+    """The reference hands ray_tracing the same model at a new pose on every capture (run.py:109-110): the facade
+    refits instead of rebuilding, with the outputs of a rebuild."""
+    from defectproj import defect_projection as dpj
+    K, H, W = synth.camera_720p()
+    d = synth.write_scene_dir(str(tmp_path), K, (H, W))
+    heat = synth.gaussian_heatmap((H, W), dtype=np.float64)
+    V, F = synth.param_mesh(60, 40, seed=11)
+    P = synth.fixed_pose()
+    V1 = V.astype(np.float64) @ P[:3, :3].T + P[:3, 3]
+    V2 = _moved(V, 15.0, [2.0, 1.0, -3.0]) @ P[:3, :3].T + P[:3, 3]
+    dpj.ray_tracing(d, dpj.TriangleMesh(V1, F), heat, K, 0.5)
+    a, ma = dpj.ray_tracing(d, dpj.TriangleMesh(V2, F), heat, K, 0.5)           # refit
+    dpj._SCENE["F"] = None
+    b, mb = dpj.ray_tracing(d, dpj.TriangleMesh(V2, F), heat, K, 0.5)           # rebuild
+    assert len(a.points) == len(b.points) > 0
+    assert np.array_equal(a.points, b.points) and np.array_equal(a.colors, b.colors)
+    assert np.array_equal(a.face_ids, b.face_ids) and np.array_equal(ma.vertices, mb.vertices)
