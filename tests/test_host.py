@@ -154,3 +154,49 @@ def test_normals_facade_rejects_what_it_does_not_implement_before_touching_the_g
     assert pe.estimate_normals(dpj.PointCloud(), {"any": 1}).normals.shape == (0, 3)
     p = dpj.KDTreeSearchParamHybrid(radius=10, max_nn=30)
     assert (p.radius, p.max_nn) == (10.0, 30)
+
+
+def test_scene_cache_decides_between_skip_refit_and_rebuild(monkeypatch):
+    """ray_tracing's scene cache: the same arrays -> nothing; the same faces at new vertex positions (what
+    run.py:109-110 hands over on every capture) -> dp_update_vertices; anything else -> set_mesh + build."""
+    from defectproj import defect_projection as dpj
+
+    class Fake:
+        def __init__(self):
+            self.calls = []
+
+        def set_mesh(self, V, F):
+            self.calls.append("set_mesh")
+            return self
+
+        def build_bvh(self):
+            self.calls.append("build")
+            return self
+
+        def update_vertices(self, V):
+            self.calls.append("update")
+            return self
+
+    fake = Fake()
+    monkeypatch.setattr(dpj, "get_context", lambda device=0: fake)
+    monkeypatch.setattr(dpj, "_SCENE", {"V": None, "F": None})
+    V, F = synth.param_mesh(12, 8, seed=1)
+    V = V.astype(np.float64)
+    dpj._scene(V, F)
+    assert fake.calls == ["set_mesh", "build"]
+    dpj._scene(V.copy(), F.copy())
+    assert fake.calls == ["set_mesh", "build"]                       # equal contents: nothing to do
+    V2 = V + 1.0
+    dpj._scene(V2, F)
+    assert fake.calls[-1] == "update" and len(fake.calls) == 3
+    V2[0, 0] += 1.0                                                  # the caller's array mutated in place is seen
+    dpj._scene(V2, F)
+    assert fake.calls[-1] == "update" and len(fake.calls) == 4
+    dpj._scene(V2.astype(np.float32), F)                             # another vertex type: a new mesh
+    assert fake.calls[-2:] == ["set_mesh", "build"]
+    F2 = F.copy()
+    F2[0] = F2[0][::-1]
+    dpj._scene(V2.astype(np.float32), F2)                            # other faces: a new mesh
+    assert fake.calls[-2:] == ["set_mesh", "build"] and len(fake.calls) == 8
+    dpj._scene(V2[:-1].astype(np.float32), F2 % (len(V2) - 1))       # other vertex count
+    assert fake.calls[-2:] == ["set_mesh", "build"] and len(fake.calls) == 10
