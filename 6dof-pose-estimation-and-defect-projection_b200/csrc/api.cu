@@ -57,7 +57,7 @@ struct dp_ctx {
     bool has_mesh = false, has_bvh = false, has_cam = false;
 
     BvhStorage obj, cam;
-    DevBuf obj_nodes, obj_tris, obj_wlo, obj_whi, cam_nodes, cam_tris, cam_wlo, cam_whi, scales, tri_face, wparent, arrived;
+    DevBuf obj_nodes, obj_tris, obj_wlo, obj_whi, cam_nodes, cam_tris, cam_wlo, cam_whi, scales, tri_face, wparent, arrived, obj_fat, cam_fat;
     Topology topo;
     void *build_scratch = nullptr;
     size_t build_scratch_bytes = 0;
@@ -117,7 +117,10 @@ struct DeviceGuard {
 
 BvhView view_of(const BvhStorage &b)
 {
-    return BvhView{b.nodes, b.tris, b.d_scale, (size_t)b.n_nodes * sizeof(WideNode) + (size_t)b.n_tris * sizeof(TriRec)};
+    // the uncompressed twin is traced while it and the records fit L2 together
+    const bool fat_ok = b.fat != nullptr && (size_t)b.n_nodes * FAT_NODE_BYTES + (size_t)b.n_tris * sizeof(TriRec) <= FAT_MAX_BYTES;
+    return BvhView{b.nodes, b.tris, b.d_scale, (size_t)b.n_nodes * sizeof(WideNode) + (size_t)b.n_tris * sizeof(TriRec),
+                   fat_ok ? b.fat : nullptr};
 }
 
 }  // namespace
@@ -185,7 +188,7 @@ void dp_destroy(dp_ctx *ctx)
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
-                      &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
+                      &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->obj_fat, &ctx->cam_fat, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
                       &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
                       &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats, &ctx->jet};
@@ -272,6 +275,14 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
         CK(ctx->tri_face.ensure(nf * 4), "dp_build_bvh: tri_face");
         CK(ctx->wparent.ensure(cap_nodes * 4), "dp_build_bvh: topology");
         CK(ctx->arrived.ensure(cap_nodes * 4), "dp_build_bvh: topology");
+        // uncompressed twin of the node set: only meshes whose records leave room for it in L2 (a wide node per ~8.5
+        // triangles: the twin of a 1.3M-triangle mesh is ~32 MB next to 62 MB of records)
+        const bool want_fat = nf * sizeof(TriRec) + (nf / 8) * FAT_NODE_BYTES <= FAT_MAX_BYTES;
+        ctx->obj.fat = nullptr;
+        if (want_fat) {
+            CK(ctx->obj_fat.ensure(cap_nodes * FAT_NODE_BYTES), "dp_build_bvh: uncompressed nodes");
+            ctx->obj.fat = ctx->obj_fat.as<uint4>();
+        }
         ctx->obj.nodes = ctx->obj_nodes.as<WideNode>();
         ctx->obj.tris = ctx->obj_tris.as<TriRec>();
         ctx->obj.wlo = ctx->obj_wlo.as<float>();
@@ -340,6 +351,11 @@ int dp_pose_mesh(dp_ctx *ctx, const double *T, void *stream)
     CK(ctx->cam_wlo.ensure((size_t)(ctx->obj.n_nodes + 1) * 12), "dp_pose_mesh: boxes");
     CK(ctx->cam_whi.ensure((size_t)(ctx->obj.n_nodes + 1) * 12), "dp_pose_mesh: boxes");
     (void)cap_nodes;
+    ctx->cam.fat = nullptr;
+    if (ctx->obj.fat) {
+        CK(ctx->cam_fat.ensure((size_t)(ctx->obj.n_nodes + 1) * FAT_NODE_BYTES), "dp_pose_mesh: uncompressed nodes");
+        ctx->cam.fat = ctx->cam_fat.as<uint4>();
+    }
     ctx->cam.nodes = ctx->cam_nodes.as<WideNode>();
     ctx->cam.tris = ctx->cam_tris.as<TriRec>();
     ctx->cam.wlo = ctx->cam_wlo.as<float>();

@@ -732,7 +732,7 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
 // in float64 (all products with 2^e and 2^-e are exact) with an explicit containment check, plus 1/128 of a step.
 __device__ __forceinline__ void fit_node8(long long w, int s, unsigned gmask, const WideNode *src, WideNode *dst,
                                           TriRec *tris, float *wlo, float *whi, float pad, const float *__restrict__ V,
-                                          const int32_t *__restrict__ F, const int32_t *__restrict__ tri_face)
+                                          const int32_t *__restrict__ F, const int32_t *__restrict__ tri_face, uint4 *fat)
 {
     const uint4 w1 = src[w].w[1];
     const unsigned imask = src[w].w[0].w >> 24;
@@ -765,6 +765,17 @@ __device__ __forceinline__ void fit_node8(long long w, int s, unsigned gmask, co
 #pragma unroll
             for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
         }
+    }
+    if (fat) {
+        // uncompressed twin: this slot's six planes (an empty slot keeps +inf / -inf: never hit) and the header
+        float *fp = reinterpret_cast<float *>(fat + w * FAT_QUADS);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { fp[4 + 8 * k + s] = lo[k]; fp[28 + 8 * k + s] = hi[k]; }
+        unsigned vb = 0;
+        if (valid) vb = ((meta & 0x18u) == 0x18u) ? (0x01000000u << s) : ((meta >> 5) << (3 * s));
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) vb |= __shfl_xor_sync(gmask, vb, d);
+        if (s == 0) fat[w * FAT_QUADS] = make_uint4(w1.x, w1.y, vb, 0u);
     }
     // node box over the eight slots
     float nlo[3], nhi[3];
@@ -836,7 +847,7 @@ __device__ __forceinline__ void fit_node8(long long w, int s, unsigned gmask, co
 __global__ void __launch_bounds__(256)
 k_fit_all(long long n_nodes, const WideNode *src, WideNode *dst, TriRec *tris, float *wlo, float *whi,
           const float *__restrict__ d_scale, const float *__restrict__ V, const int32_t *__restrict__ F,
-          const int32_t *__restrict__ tri_face, const int32_t *__restrict__ wparent, unsigned *arrived)
+          const int32_t *__restrict__ tri_face, const int32_t *__restrict__ wparent, unsigned *arrived, uint4 *fat)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long w = t >> 3;
@@ -847,7 +858,7 @@ k_fit_all(long long n_nodes, const WideNode *src, WideNode *dst, TriRec *tris, f
     if (src[w].w[0].w >> 24) return;                     // has inner children: fitted by the last of them
     const float pad = 3.8146973e-6f * (*d_scale);        // 2^-18 * max |coordinate|
     for (;;) {
-        fit_node8(w, s, gmask, src, dst, tris, wlo, whi, pad, V, F, tri_face);
+        fit_node8(w, s, gmask, src, dst, tris, wlo, whi, pad, V, F, tri_face, fat);
         if (w == 0) return;
         const long long p = wparent[w];
         const unsigned need = __popc(src[p].w[0].w >> 24);
@@ -1055,6 +1066,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         root.w[3] = make_uint4(0xffffffffu, 0xffffffffu, 0, 0);
         root.w[4] = make_uint4(0, 0, 0, 0);
         if ((e = cudaMemcpyAsync(out.nodes, &root, sizeof(root), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+        if (out.fat && (e = cudaMemsetAsync(out.fat, 0, FAT_NODE_BYTES, s)) != cudaSuccess) return e;   // valid = 0
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         out.n_nodes = 1;
         topo.n_levels = 1;
@@ -1117,7 +1129,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     out.n_nodes = end;
     if ((e = cudaMemsetAsync(topo.arrived, 0, (size_t)out.n_nodes * 4, s)) != cudaSuccess) return e;
     k_fit_all<<<blocks_for(out.n_nodes * 8, 256), 256, 0, s>>>(out.n_nodes, out.nodes, out.nodes, out.tris, out.wlo, out.whi,
-                                                           out.d_scale, V, F, topo.tri_face, topo.wparent, topo.arrived);
+                                                           out.d_scale, V, F, topo.tri_face, topo.wparent, topo.arrived, out.fat);
     return cudaGetLastError();
 }
 
@@ -1151,7 +1163,7 @@ cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t 
         return cudaMemcpyAsync(dst.nodes, src.nodes, sizeof(WideNode), cudaMemcpyDeviceToDevice, s);
     }
     k_fit_all<<<blocks_for(src.n_nodes * 8, 256), 256, 0, s>>>(src.n_nodes, src.nodes, dst.nodes, dst.tris, dst.wlo, dst.whi,
-                                                           dst.d_scale, Vposed, F, topo.tri_face, topo.wparent, topo.arrived);
+                                                           dst.d_scale, Vposed, F, topo.tri_face, topo.wparent, topo.arrived, dst.fat);
     return cudaGetLastError();
 }
 

@@ -36,11 +36,27 @@ constexpr int STACK_LOCAL = 64 - STACK_SMEM; // overflow entries in local memory
 constexpr int MAX_WIDE_DEPTH = STACK_SMEM + STACK_LOCAL - 2;
 constexpr float T_SLACK = 1.0001f;    // culling bound = best * T_SLACK (same as oracle.c)
 
+// ------------------------------------------------------------------------------------------
+// Uncompressed twin of the wide node for hierarchies that stay resident in L2: 208 bytes = thirteen 16-byte words.
+//   q0      : child_base, tri_base, valid, 0
+//             valid bits 3s..3s+2 = the (<= 3) triangle records of leaf slot s (record = tri_base + number of valid
+//             bits below), bits 24+s = inner children (child = child_base + number of inner bits below)
+//   q1..q6  : lo_x[0..7], lo_y[0..7], lo_z[0..7]   (float32 child planes, empty slot = +inf)
+//   q7..q12 : hi_x[0..7], hi_y[0..7], hi_z[0..7]   (empty slot = -inf)
+// Same node numbering, same record array, same topology as the compressed set (both are written by fit_node8).  A
+// visit needs no byte->float conversion (48 quarter-rate I2F per visit in the compressed format), no per-node scale
+// and a constant hit word per slot; the price is 2.6x the bytes per node, paid in L1/L2 hits while the set fits L2.
+// ------------------------------------------------------------------------------------------
+constexpr int FAT_QUADS = 13;
+constexpr size_t FAT_NODE_BYTES = FAT_QUADS * 16;
+constexpr size_t FAT_MAX_BYTES = 96u << 20;   // fat nodes + records above this: the compressed set is traced instead
+
 struct BvhView {
     const WideNode *nodes;
     const TriRec *tris;
     const float *d_scale;  // device: max |vertex coordinate| of the mesh the BVH was fitted to
     size_t bytes;          // nodes + triangle records
+    const uint4 *fat;      // uncompressed node set (nullptr: not kept for this hierarchy)
 };
 
 // per-frame ray generation constants: fx fy cx cy | Rinv (row-major) | tinv
@@ -214,6 +230,7 @@ struct BvhStorage {
     TriRec *tris = nullptr;        // [nF]
     float *wlo = nullptr;          // [cap_nodes*3] exact wide-node boxes (refit)
     float *whi = nullptr;
+    uint4 *fat = nullptr;          // [cap_nodes*FAT_QUADS] uncompressed twin (optional)
     int64_t cap_nodes = 0;
     int64_t n_nodes = 0;
     int64_t n_tris = 0;

@@ -98,6 +98,8 @@ struct RayState {
     float ox, oy, oz;         // origin
     float ix, iy, iz;         // clamped reciprocal direction
     float px, py, pz;         // slab padding in t
+    float anx, any, anz;      // uncompressed nodes: near plane t = plane * i + an  (an = -o*i - pad)
+    float afx, afy, afz;      //                     far plane  t = plane * i + af  (af = -o*i + pad)
     unsigned order;           // three 8-bit slot masks (bytes 0..2 = bit 2, 1, 0 of the slot index): the slots a ray
                               // prefers on that bit, nearest child = the hit slot s that maximises s ^ (7 ^ octant)
     uint2 ng;                 // current node group: (child base, hit bits | imask)
@@ -129,6 +131,10 @@ __device__ __forceinline__ void ray_setup(RayState &r, float ox, float oy, float
     // every slab plane is moved outwards by pad_abs (in space), i.e. pad_abs*|1/d| in t
     const float pad_abs = 1.9073486e-6f * (scale + fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))));
     r.px = pad_abs * fabsf(r.ix); r.py = pad_abs * fabsf(r.iy); r.pz = pad_abs * fabsf(r.iz);
+    // the padding (2^-19 of the scene) exceeds the rounding of o*i and of the fused plane*i + a by a factor of 16
+    const float cx = -(ox * r.ix), cy = -(oy * r.iy), cz = -(oz * r.iz);
+    r.anx = cx - r.px; r.any = cy - r.py; r.anz = cz - r.pz;
+    r.afx = cx + r.px; r.afy = cy + r.py; r.afz = cz + r.pz;
     const unsigned oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
     const unsigned octinv = 7u ^ oct;
     r.order = ((octinv & 4u) ? 0x0fu : 0xf0u) | (((octinv & 2u) ? 0x33u : 0xccu) << 8) | (((octinv & 1u) ? 0x55u : 0xaau) << 16);
@@ -287,6 +293,78 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
     }
     r.ng = ng;
     node_select(r, nodes, stack, lstack, pf);
+    return true;
+}
+
+// Selection half for the uncompressed set: as node_select, without the prefetch (the set is L2-resident by construction).
+__device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2 *lstack)
+{
+    uint2 ng = r.ng;
+    const unsigned hits = ng.y;
+    unsigned c = hits >> 24, t;
+    t = c & r.order;          c = t ? t : c;
+    t = c & (r.order >> 8);   c = t ? t : c;
+    t = c & (r.order >> 16);  c = t ? t : c;
+    const unsigned slot = (unsigned)__ffs((int)c) - 1u;
+    ng.y &= ~(0x01000000u << slot);
+    if (ng.y & 0xff000000u) {
+        if (r.sp < STACK_SMEM) stack[r.sp * TR_THREADS] = ng; else lstack[r.sp - STACK_SMEM] = ng;
+        ++r.sp;
+    }
+    r.next = ng.x + __popc(hits & 0xffu & ((1u << slot) - 1u));
+}
+
+// Visit half for the uncompressed 208-byte node (dp_internal.cuh): thirteen 16-byte loads, per child six FMAs on the
+// float planes (near/far chosen by the sign of the ray: compile-time plane blocks when OCT >= 0, per-lane block
+// indices otherwise), one compare and ONE predicated OR of the slot's constant hit word (three triangle bits + the
+// inner bit); a single AND with the node's valid word then leaves the triangles and inner children that exist.
+// No byte->float conversions, no per-node scale, no per-child shifts.
+template <bool STATS, int OCT>
+__device__ __forceinline__ bool node_step_fat(RayState &r, const uint4 *__restrict__ fat, uint2 *stack, uint2 *lstack,
+                                              float tlimit, unsigned &tbase, unsigned &tmask, unsigned &tvalid,
+                                              unsigned &n_nodes)
+{
+    const uint4 *np = fat + (size_t)r.next * FAT_QUADS;
+    const uint4 h = __ldg(np);
+    if (STATS) ++n_nodes;
+    // first 16-byte word of the near block per axis (lo: 1, 3, 5; hi: 7, 9, 11); the far block is the other one
+    int bnx, bny, bnz;
+    if (OCT >= 0) { bnx = (OCT & 1) ? 7 : 1; bny = (OCT & 2) ? 9 : 3; bnz = (OCT & 4) ? 11 : 5; }
+    else { bnx = r.ix < 0.0f ? 7 : 1; bny = r.iy < 0.0f ? 9 : 3; bnz = r.iz < 0.0f ? 11 : 5; }
+    const int bfx = 8 - bnx, bfy = 12 - bny, bfz = 16 - bnz;
+    unsigned m = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const float4 nx = __ldg(reinterpret_cast<const float4 *>(np + bnx + half));
+        const float4 ny = __ldg(reinterpret_cast<const float4 *>(np + bny + half));
+        const float4 nz = __ldg(reinterpret_cast<const float4 *>(np + bnz + half));
+        const float4 fx = __ldg(reinterpret_cast<const float4 *>(np + bfx + half));
+        const float4 fy = __ldg(reinterpret_cast<const float4 *>(np + bfy + half));
+        const float4 fz = __ldg(reinterpret_cast<const float4 *>(np + bfz + half));
+        const float pnx[4] = {nx.x, nx.y, nx.z, nx.w}, pny[4] = {ny.x, ny.y, ny.z, ny.w}, pnz[4] = {nz.x, nz.y, nz.z, nz.w};
+        const float pfx[4] = {fx.x, fx.y, fx.z, fx.w}, pfy[4] = {fy.x, fy.y, fy.z, fy.w}, pfz[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int slot = 4 * half + j;
+            const float tnx = fmaf(pnx[j], r.ix, r.anx), tny = fmaf(pny[j], r.iy, r.any), tnz = fmaf(pnz[j], r.iz, r.anz);
+            const float tfx = fmaf(pfx[j], r.ix, r.afx), tfy = fmaf(pfy[j], r.iy, r.afy), tfz = fmaf(pfz[j], r.iz, r.afz);
+            const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
+            if (tmin <= tmax) m |= (7u << (3 * slot)) | (0x01000000u << slot);
+        }
+    }
+    m &= h.z;
+    uint2 ng = make_uint2(h.x, (m & 0xff000000u) | (h.z >> 24));
+    tmask = m & 0x00ffffffu;
+    tvalid = h.z;
+    tbase = h.y;
+    if (!(ng.y & 0xff000000u)) {
+        if (r.sp == 0) return false;
+        --r.sp;
+        ng = (r.sp < STACK_SMEM) ? stack[r.sp * TR_THREADS] : lstack[r.sp - STACK_SMEM];
+    }
+    r.ng = ng;
+    node_select_fat(r, stack, lstack);
     return true;
 }
 
@@ -528,9 +606,14 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
 #ifndef DP_MIN_BLOCKS_BIG
 #define DP_MIN_BLOCKS_BIG 5  // hierarchies beyond L2 (5M triangles: 0.511 -> 0.49 ms): fewer packets share an SM's L1
 #endif
-template <bool STATS, int SRC, int MINB>
+// FMT = 0: compressed 80-byte nodes; FMT = 1: the uncompressed 208-byte twin `fat` (L2-resident hierarchies), visited
+// by the instantiation of node_step_fat for the packet's octant (its rays disagree on a sign: per-lane plane blocks).
+#ifndef DP_FAT_OCT
+#define DP_FAT_OCT 1
+#endif
+template <bool STATS, int SRC, int MINB, int FMT>
 __global__ void __launch_bounds__(TR_THREADS, MINB)
-k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
+k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
         const float4 *__restrict__ dir4, const float *__restrict__ rays6, const float *__restrict__ intensity,
         const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
         const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
@@ -610,23 +693,41 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
             ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
         }
         best[lane] = KEY_MISS;
-        if (alive) node_select(r, nodes, stack, lstack, pf);
+        if (alive) { if (FMT == 1) node_select_fat(r, stack, lstack); else node_select(r, nodes, stack, lstack, pf); }
         __syncwarp();
-#if DP_OCT_SPECIALISE
         // the packet's octant, from the signs the slab test itself uses; -1 when its rays disagree
-        const int so = (r.ix < 0.0f ? 1 : 0) | (r.iy < 0.0f ? 2 : 0) | (r.iz < 0.0f ? 4 : 0);
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        const int so0 = __shfl_sync(0xffffffffu, so, vm ? __ffs((int)vm) - 1 : 0);
-        const int poct = __all_sync(0xffffffffu, !valid || so == so0) ? so0 : -1;
-#endif
+        int poct = -1;
+        if (DP_OCT_SPECIALISE || (FMT == 1 && DP_FAT_OCT)) {
+            const int so = (r.ix < 0.0f ? 1 : 0) | (r.iy < 0.0f ? 2 : 0) | (r.iz < 0.0f ? 4 : 0);
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            const int so0 = __shfl_sync(0xffffffffu, so, vm ? __ffs((int)vm) - 1 : 0);
+            poct = __all_sync(0xffffffffu, !valid || so == so0) ? so0 : -1;
+        }
         int qhead = 0, qcount = 0;              // warp-uniform
         const unsigned nn_start = nn;
         unsigned steps = 0;
 
         while (__any_sync(0xffffffffu, alive)) {
-            unsigned tmask = 0, tbase = 0;
+            unsigned tmask = 0, tbase = 0, tvalid = 0xffffffffu;
             if (alive) {
                 const float tlimit = __uint_as_float((unsigned)(best[lane] >> 32)) * T_SLACK;
+                if (FMT == 1) {
+#if DP_FAT_OCT
+                    switch (poct) {
+                    case 0: alive = node_step_fat<STATS, 0>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 1: alive = node_step_fat<STATS, 1>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 2: alive = node_step_fat<STATS, 2>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 3: alive = node_step_fat<STATS, 3>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 4: alive = node_step_fat<STATS, 4>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 5: alive = node_step_fat<STATS, 5>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 6: alive = node_step_fat<STATS, 6>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    case 7: alive = node_step_fat<STATS, 7>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    default: alive = node_step_fat<STATS, -1>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn); break;
+                    }
+#else
+                    alive = node_step_fat<STATS, -1>(r, fat, stack, lstack, tlimit, tbase, tmask, tvalid, nn);
+#endif
+                } else {
 #if DP_OCT_SPECIALISE
                 switch (poct) {
                 case 0: alive = node_step<STATS, 0>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn, pf); break;
@@ -642,6 +743,7 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
 #else
                 alive = node_step<STATS>(r, nodes, stack, lstack, tlimit, tbase, tmask, nn, pf);
 #endif
+                }
                 ++steps;
             }
             // queue this step's triangles: one warp prefix sum gives every lane the slots of all its triangles, which
@@ -669,8 +771,9 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
                     while (tmask) {
                         const int b = __ffs(tmask) - 1;
                         tmask &= tmask - 1u;
-                        queue[pos++ & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
-                        prefetch_l1(tris + (tbase + b), pf);
+                        const unsigned rec = FMT == 1 ? tbase + __popc(tvalid & ((1u << b) - 1u)) : tbase + b;
+                        queue[pos++ & (TQ_CAP - 1)] = ((unsigned)lane << 27) | rec;
+                        prefetch_l1(tris + rec, pf);
                     }
                     qcount += total;
                     __syncwarp();
@@ -687,7 +790,8 @@ k_trace(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, con
                         if (tmask) {
                             const int b = __ffs(tmask) - 1;
                             tmask &= tmask - 1u;
-                            queue[(qhead + qcount + __popc(contrib & lt)) & (TQ_CAP - 1)] = ((unsigned)lane << 27) | (tbase + b);
+                            const unsigned rec = FMT == 1 ? tbase + __popc(tvalid & ((1u << b) - 1u)) : tbase + b;
+                            queue[(qhead + qcount + __popc(contrib & lt)) & (TQ_CAP - 1)] = ((unsigned)lane << 27) | rec;
                         }
                         qcount += __popc(contrib);
                         __syncwarp();
@@ -885,24 +989,43 @@ int knob_tiled()
     return g_tiled;
 }
 
-int g_trace_grid[2] = {0, 0};     // persistent grid (CTAs resident on the device at once) of the two occupancy variants
-
-cudaError_t trace_grid(int big, int *grid)
+#ifndef DP_MIN_BLOCKS_FAT
+#define DP_MIN_BLOCKS_FAT 7
+#endif
+// DP_FAT=0: trace the compressed set even when the uncompressed twin exists (read per launch: tests flip it)
+int knob_fat()
 {
-    if (g_trace_grid[big] == 0) {
+    const char *e = getenv("DP_FAT");
+    return e ? atoi(e) : 1;
+}
+
+// persistent grid (CTAs resident on the device at once) of the three variants:
+// 0 = compressed nodes, hierarchy within L2; 1 = compressed, beyond L2 (fewer CTAs, L1 prefetch); 2 = uncompressed twin
+int g_trace_grid[3] = {0, 0, 0};
+
+cudaError_t trace_grid(int variant, int *grid)
+{
+    if (g_trace_grid[variant] == 0) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaError_t e;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if (big) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS_BIG>, TR_THREADS, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS>, TR_THREADS, 0);
+        if (variant == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS_BIG, 0>, TR_THREADS, 0);
+        else if (variant == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS_FAT, 1>, TR_THREADS, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0, DP_MIN_BLOCKS, 0>, TR_THREADS, 0);
         if (e != cudaSuccess) return e;
-        const int target = big ? DP_MIN_BLOCKS_BIG : DP_MIN_BLOCKS;
+        const int target = variant == 1 ? DP_MIN_BLOCKS_BIG : (variant == 2 ? DP_MIN_BLOCKS_FAT : DP_MIN_BLOCKS);
         if (per_sm > target) per_sm = target;       // the variant's point is its residency, not just its registers
-        g_trace_grid[big] = sms * (per_sm > 0 ? per_sm : 1);
+        g_trace_grid[variant] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    *grid = g_trace_grid[big];
+    *grid = g_trace_grid[variant];
     return cudaSuccess;
+}
+
+int trace_variant(const BvhView &bvh)
+{
+    if (bvh.fat != nullptr && knob_fat()) return 2;
+    return bvh.bytes > PREFETCH_MIN_BYTES ? 1 : 0;
 }
 
 }  // namespace
@@ -947,20 +1070,28 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
     int grid = 0;
-    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
-    if ((e = trace_grid(pf, &grid)) != cudaSuccess) return e;
+    const int variant = trace_variant(bvh);
+    const int pf = variant == 1;
+    if ((e = trace_grid(variant, &grid)) != cudaSuccess) return e;
     const long long want = (n_max + TR_THREADS - 1) / TR_THREADS;
     if (want < grid) grid = (int)want;
     if (!counter_zeroed && (e = cudaMemsetAsync(work_counter, 0, 2 * sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a = acc ? *acc : Accum{nullptr, nullptr, nullptr, nullptr};
     if (knob_order() == 0) { ord_prev = nullptr; ord_next = nullptr; }
     const int narrow = knob_narrow() && d_n != nullptr;
-#define DP_LAUNCH_TRACE0(ST, MB)                                                                                        \
-    k_trace<ST, 0, MB><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, n_max,   \
-                                                   total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, d_hits, \
-                                                   stats, knob_tiled(), ord_prev, ord_next, pf, narrow)
-    if (stats) { if (pf) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS); }
-    else       { if (pf) DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS); }
+#define DP_LAUNCH_TRACE0(ST, MB, FMT)                                                                                        \
+    k_trace<ST, 0, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, \
+                                                        n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, \
+                                                        d_hits, stats, knob_tiled(), ord_prev, ord_next, pf, narrow)
+    if (stats) {
+        if (variant == 2) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_FAT, 1);
+        else if (variant == 1) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG, 0);
+        else DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS, 0);
+    } else {
+        if (variant == 2) DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS_FAT, 1);
+        else if (variant == 1) DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS_BIG, 0);
+        else DP_LAUNCH_TRACE0(false, DP_MIN_BLOCKS, 0);
+    }
 #undef DP_LAUNCH_TRACE0
     return cudaGetLastError();
 }
@@ -971,17 +1102,26 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
     if (n <= 0) return cudaSuccess;
     cudaError_t e;
     int grid = 0;
-    const int pf = bvh.bytes > PREFETCH_MIN_BYTES;
-    if ((e = trace_grid(pf, &grid)) != cudaSuccess) return e;
+    const int variant = trace_variant(bvh);
+    const int pf = variant == 1;
+    if ((e = trace_grid(variant, &grid)) != cudaSuccess) return e;
     const long long want = (n + TR_THREADS - 1) / TR_THREADS;
     if (want < grid) grid = (int)want;
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
     Accum a{nullptr, nullptr, nullptr, nullptr};
-#define DP_LAUNCH_TRACE1(ST, MB)                                                                                          \
-    k_trace<ST, 1, MB><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, n, 0, 0, 0, \
-                                                   nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, nullptr, nullptr, pf, 0)
-    if (stats) { if (pf) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS); }
-    else       { if (pf) DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS_BIG); else DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS); }
+#define DP_LAUNCH_TRACE1(ST, MB, FMT)                                                                                          \
+    k_trace<ST, 1, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, \
+                                                        n, 0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, \
+                                                        nullptr, nullptr, pf, 0)
+    if (stats) {
+        if (variant == 2) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_FAT, 1);
+        else if (variant == 1) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG, 0);
+        else DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS, 0);
+    } else {
+        if (variant == 2) DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS_FAT, 1);
+        else if (variant == 1) DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS_BIG, 0);
+        else DP_LAUNCH_TRACE1(false, DP_MIN_BLOCKS, 0);
+    }
 #undef DP_LAUNCH_TRACE1
     return cudaGetLastError();
 }

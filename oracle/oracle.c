@@ -710,6 +710,17 @@ ORC_API int orc_num_threads(void)
 #endif
 }
 
+/* Thread count of the following parallel regions.  A launcher may export OMP_NUM_THREADS=1 to every rank
+ * (torch.distributed.run does); the CPU arm of bench.py sets the count it measured from its affinity mask instead. */
+ORC_API void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------- */
 /* DataReader.get_heatmap  (datareader.py:639-675)  -- SURVEY.md 8f #3         */
 /*   heatmap = data - np.min(data); heatmap = heatmap / np.max(heatmap)  :658   */

@@ -80,6 +80,8 @@ def lib():
         L.orc_prepare_heatmap_f32.argtypes = [vp, i64, i64, i64, i64, vp]
         L.orc_prepare_heatmap_f32.restype = None
         L.orc_num_threads.argtypes = []
+        L.orc_set_num_threads.restype = None
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -256,6 +258,15 @@ def accumulate(face, I, F, nV):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n=None):
+    """OpenMP threads of the following calls; default = the CPUs this process may run on (a launcher's
+    OMP_NUM_THREADS=1 would otherwise make the CPU arm single-threaded).  Returns the count in effect."""
+    if n is None:
+        n = len(os.sched_getaffinity(0))
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 # ------------------------------------------------------------------ independent numpy check

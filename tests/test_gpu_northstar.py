@@ -1,0 +1,172 @@
+"""The north_star criterion at BASELINE.json's full sizes.
+
+"face ids and per-face hit counts must be bit-exact except rays the reference also classifies as edge/grazing
+ties, and hit points must agree within 1e-5 of the mesh bounding-box diagonal."
+
+The comparator here is NOT the float32 contract the kernel and the oracle share (tests/test_gpu_parity.py does that,
+bit for bit): it is the oracle's independent float64 Moeller-Trumbore closest hit on the float32-rounded inputs the
+reference hands to Embree (oracle.c orc_cast_f64), plus its tie classifier.  Covered: the dense 1024x1024 frame
+(every ray, packet traversal), blob heatmaps at thresholds 0.5 / 0.75 (sparse frames: eight lanes per ray), both the
+uncompressed and the compressed node set, object frame and the reference-literal camera frame
+(/root/reference/src/defect_projection.py:549-550, :245-251), and configs[2] (64 views, per-frame LBVH refit).
+"""
+import numpy as np
+import pytest
+
+from defectproj import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_FRAC = 1e-5      # north_star: hit points within 1e-5 of the mesh bounding-box diagonal
+
+
+def check_north_star(orc, bvh, V, rays6, d_cam, face, point64, min_clean=0.9, min_hits=1000):
+    """face / point64: the GPU's per-ray results; rays6: the float32 rays the reference would cast; d_cam: float64
+    camera-frame unit directions (hit point = d_cam * t, :261-263).  Returns (tie mask, float64 truth faces)."""
+    t64, f64, tie = bvh.cast_f64(rays6)
+    clean = tie == 0
+    assert clean.mean() > min_clean, f"only {clean.mean():.3f} of the rays are off ties"
+    bad = clean & (face != f64)
+    assert not bad.any(), f"{bad.sum()} of {clean.sum()} non-tie rays differ from the float64 truth (first: {np.nonzero(bad)[0][:5]})"
+    hit = clean & (f64 >= 0)
+    assert hit.sum() >= min_hits
+    diag = float(np.linalg.norm(V.max(0).astype(np.float64) - V.min(0).astype(np.float64)))
+    p64 = d_cam[hit] * t64[hit][:, None]
+    err = np.linalg.norm(point64[hit] - p64, axis=1).max()
+    assert err <= TOL_FRAC * diag, f"hit points off by {err:.3g} > {TOL_FRAC * diag:.3g}"
+    # on tie rays the GPU's face must be a genuine candidate: inside its triangle up to the tie margin and, when the
+    # truth also hits, at the truth's distance up to the distance margin
+    tie_hit = (~clean) & (face >= 0)
+    if tie_hit.any():
+        tt, margin, _ = bvh.eval_face(rays6[tie_hit], face[tie_hit])
+        tau, tau_t = bvh.margins(rays6)
+        assert (margin >= -tau).all(), "a tie ray's face is not a candidate (outside its triangle beyond the margin)"
+        f_t = f64[tie_hit]
+        ok = (f_t < 0) | (np.abs(tt - np.where(f_t >= 0, t64[tie_hit], tt)) <= 4 * tau_t)
+        assert ok.all(), "a tie ray's face is not at the closest distance"
+    return ~clean, f64
+
+
+def _project_and_check(ctx, orc, bvh, V, K, H, W, pose, heat, thr, accumulate=False):
+    res = ctx.project(heat, K, pose[None], thr, "object", accumulate, want=("pixel", "face", "point64"))
+    xs, ys, _ = orc.heatmap_to_points(heat, thr)
+    assert res["n"] == len(xs) and np.array_equal(res["pixel"], (ys * W + xs).astype(np.uint32))
+    rays6 = orc.rays_object_frame(xs, ys, orc.frame_xform(K, pose))
+    d = orc.compute_rays(xs, ys, K)
+    tie, f64 = check_north_star(orc, bvh, V, rays6, d, res["face"], res["point64"])
+    return res, tie, f64
+
+
+@pytest.mark.parametrize("cfg", ["c2_500k", "ns_1m", "c4_5m"])
+def test_full_size_object_frame_vs_float64_truth(ctx, orc, cfg, monkeypatch):
+    """configs[1], the north-star 1M-triangle mesh and configs[3]: the dense WFOV frame (all 1 048 576 rays) and two
+    blob heatmaps at thresholds 0.5 / 0.75, GPU vs the float64 truth off ties; per-face hit counts equal the truth's
+    after the tie rays are removed from both sides."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS[cfg], seed=0, scale=6.0)
+    K, H, W = synth.camera_wfov()
+    pose = synth.fill_frame_pose()
+    bvh = orc.Bvh(V, F)
+    ctx.set_mesh(V, F).build_bvh()
+    dense = np.ones((H, W), np.float32)
+    node_sets = ("1", "0") if cfg != "c4_5m" else ("1",)          # 5M triangles: only the compressed set exists
+    for fat in node_sets:
+        monkeypatch.setenv("DP_FAT", fat)
+        res, tie, f64 = _project_and_check(ctx, orc, bvh, V, K, H, W, pose, dense, 0.5)
+        keep = ~tie
+        h_gpu = np.bincount(res["face"][keep & (res["face"] >= 0)], minlength=len(F))
+        h_ref = np.bincount(f64[keep & (f64 >= 0)], minlength=len(F))
+        assert np.array_equal(h_gpu, h_ref)                        # per-face hit counts, tie rays removed
+        assert (res["face"] >= 0).mean() > 0.9
+    monkeypatch.setenv("DP_FAT", "1")
+    for seed, thr in ((3, 0.5), (3, 0.75), (8, 0.5)):
+        heat = synth.blob_heatmap((H, W), seed=seed)
+        res, _, _ = _project_and_check(ctx, orc, bvh, V, K, H, W, pose, heat, thr)
+        assert 3000 < res["n"] < 131072                            # a sparse frame: the eight-lanes-per-ray traversal
+
+
+def test_full_size_camera_frame_is_reference_literal(ctx, orc):
+    """The arithmetic the reference performs (:549-550 then :245-251): vertices posed in float64, cast to float32, BVH
+    refitted to them, rays from the origin -- at configs[1] size, against the float64 truth on the posed mesh."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c2_500k"], seed=0, scale=6.0)
+    K, H, W = synth.camera_wfov()
+    pose = synth.fill_frame_pose()
+    V64 = V.astype(np.float64)
+    ctx.set_mesh(V64, F).build_bvh()
+    ctx.pose_mesh(pose)
+    Vref = orc.pose_vertices(V64, pose)
+    assert np.array_equal(ctx.posed_vertices(), Vref)              # float32 vertices == the reference's, bit for bit
+    bvh = orc.Bvh(Vref, F)
+    for heat, thr in ((np.ones((H, W), np.float32), 0.5), (synth.blob_heatmap((H, W), seed=3), 0.5),
+                      (synth.blob_heatmap((H, W), seed=3), 0.75)):
+        res = ctx.project(heat, K, None, thr, "camera", False, want=("face", "t_hit", "point64"))
+        xs, ys, _ = orc.heatmap_to_points(heat, thr)
+        d = orc.compute_rays(xs, ys, K)
+        rays6 = orc.rays6_camera(d)
+        check_north_star(orc, bvh, Vref, rays6, d, res["face"], res["point64"])
+        t32, f32 = bvh.cast_f32(rays6)                             # and the float32 contract, bit for bit
+        assert np.array_equal(res["face"], f32)
+        assert np.array_equal(res["t_hit"].view(np.uint32), t32.view(np.uint32))
+
+
+def test_config3_64_views_refit_vs_object_frame(ctx, orc):
+    """configs[2]: 64 Fibonacci views x 720p blob heatmaps on the 500k-triangle mesh.  Object frame: ONE launch for
+    the 64 views.  Camera frame: per-frame float64 posing + LBVH refit (dp_pose_mesh) + launch.  Every ray on which the
+    two disagree must be a tie-classified ray, the histograms agree once those rays are removed, and off ties both
+    equal the float64 truth."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c2_500k"], seed=0)
+    K, H, W = synth.camera_720p()
+    B = 64
+    poses = synth.fibonacci_poses(B, radius=600.0)
+    heats = np.stack([synth.blob_heatmap((H, W), seed=200 + i) for i in range(B)])
+    thr = 0.5
+    V64 = V.astype(np.float64)
+    ctx.set_mesh(V64, F).build_bvh()
+    ctx.accum_reset()
+    obj = ctx.project(heats, K, poses, thr, "object", True, want=("pixel", "face", "point64"))
+    hist_obj = ctx.accum_get()[0]
+    assert hist_obj.sum() == obj["hits"] > 100000
+    bvh = orc.Bvh(V, F)
+    ctx.accum_reset()
+    lo = 0
+    differing = 0
+    hist_clean_obj = np.zeros(len(F), np.int64)
+    hist_clean_cam = np.zeros(len(F), np.int64)
+    for b in range(B):
+        ctx.pose_mesh(poses[b])
+        cam = ctx.project(heats[b], K, None, thr, "camera", True, want=("face", "point64"))
+        n = cam["n"]
+        xs, ys, _ = orc.heatmap_to_points(heats[b], thr)
+        assert n == len(xs)
+        assert np.array_equal(obj["pixel"][lo:lo + n], (b * H * W + ys * W + xs).astype(np.uint32))
+        f_obj, p_obj = obj["face"][lo:lo + n], obj["point64"][lo:lo + n]
+        lo += n
+        d = orc.compute_rays(xs, ys, K)
+        rays_o = orc.rays_object_frame(xs, ys, orc.frame_xform(K, poses[b]))
+        # object frame vs the float64 truth on the model
+        tie_o, f64 = check_north_star(orc, bvh, V, rays_o, d, f_obj, p_obj, min_hits=0)
+        # camera frame: the float64 classifier on the posed mesh (4 of the 64 views, the BVH build dominates) ...
+        diff = f_obj != cam["face"]
+        differing += int(diff.sum())
+        if b % 16 == 3:
+            Vref = orc.pose_vertices(V64, poses[b])
+            tie_c, _ = check_north_star(orc, orc.Bvh(Vref, F), Vref, orc.rays6_camera(d), d, cam["face"], cam["point64"],
+                                        min_hits=0)
+            assert not (diff & ~(tie_o | tie_c)).any()
+        # ... and for every view: a ray on which the frames disagree is a tie of the object-frame classifier or lies
+        # within the tie margin of the camera-frame face (same candidate set, rigid invariance)
+        und = diff & ~tie_o
+        if und.any():
+            idx = np.nonzero(und & (cam["face"] >= 0))[0]
+            _, margin, _ = bvh.eval_face(rays_o[idx], cam["face"][idx])
+            tau, _ = bvh.margins(rays_o)
+            assert (margin >= -tau).all()
+            assert (np.abs(margin) <= 64 * tau).all(), "frames disagree on a ray that is not near an edge"
+        keep = ~(tie_o | diff)
+        hist_clean_obj += np.bincount(f_obj[keep & (f_obj >= 0)], minlength=len(F))
+        hist_clean_cam += np.bincount(cam["face"][keep & (cam["face"] >= 0)], minlength=len(F))
+    assert lo == obj["n"]
+    hist_cam = ctx.accum_get()[0]
+    assert hist_cam.sum() == hist_obj.sum() or differing > 0
+    assert np.array_equal(hist_clean_obj, hist_clean_cam)
+    # the raw histograms differ at most on the faces of the disagreeing rays
+    assert (hist_cam != hist_obj).sum() <= 2 * differing
