@@ -62,8 +62,16 @@ struct dp_ctx {
     void *build_scratch = nullptr;
     size_t build_scratch_bytes = 0;
 
-    // accumulators
-    DevBuf hist, fmax, vmax;
+    // accumulators: ONE allocation, hist | fmax | vmax with 256-byte aligned starts (the gaps stay zero), so that a
+    // caller can combine fmax and vmax of several contexts with one MAX reduction over [fmax, vmax + nV)
+    DevBuf accum;
+    struct View {
+        void *p = nullptr;
+        template <typename T>
+        T *as() const { return static_cast<T *>(p); }
+    } hist, fmax, vmax;
+    size_t accum_bytes = 0;
+    RayShard shard;                  // dp_set_ray_shard
 
     // per-call scratch
     DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, counts, fcounts, xf, stats, jet;
@@ -189,7 +197,7 @@ void dp_destroy(dp_ctx *ctx)
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->obj_fat, &ctx->cam_fat, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
-                      &ctx->hist, &ctx->fmax, &ctx->vmax, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
+                      &ctx->accum, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
                       &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats, &ctx->jet};
     for (DevBuf *b : bufs) b->release();
@@ -216,7 +224,8 @@ int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const int32_
     if (!ctx) return DP_E_ARG;
     if (nV < 0 || nF < 0 || (nV > 0 && !V) || (nF > 0 && !F) || (vdtype != DP_F32 && vdtype != DP_F64))
         return fail(ctx, DP_E_ARG, "dp_set_mesh: bad arguments");
-    if (nF > 0x7fffffffLL / 4 || nV > 0x7fffffffLL / 4) return fail(ctx, DP_E_ARG, "dp_set_mesh: mesh too large");
+    // the traversal's triangle queue packs (owner lane << 27 | record index): 2^27 - 1 triangles at most
+    if (nF >= (1LL << 27) || nV > 0x7fffffffLL / 4) return fail(ctx, DP_E_ARG, "dp_set_mesh: mesh too large (at most 2^27 - 1 triangles)");
     if (mem == DP_HOST) {
         for (int64_t i = 0; i < 3 * nF; ++i)
             if (F[i] < 0 || F[i] >= nV) return fail(ctx, DP_E_ARG, "dp_set_mesh: face index out of range");
@@ -231,9 +240,14 @@ int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const int32_
         CK(ctx->V64.ensure(nv * 24), "dp_set_mesh: V64");
         CK(ctx->Vposed64.ensure(nv * 24), "dp_set_mesh: Vposed64");
     }
-    CK(ctx->hist.ensure(nf * 4), "dp_set_mesh: hist");
-    CK(ctx->fmax.ensure(nf * 4), "dp_set_mesh: fmax");
-    CK(ctx->vmax.ensure(nv * 4), "dp_set_mesh: vmax");
+    {
+        const size_t af = (nf * 4 + 255) & ~size_t(255), av = (nv * 4 + 255) & ~size_t(255);
+        CK(ctx->accum.ensure(2 * af + av), "dp_set_mesh: accumulators");
+        ctx->hist.p = ctx->accum.p;
+        ctx->fmax.p = ctx->accum.as<char>() + af;
+        ctx->vmax.p = ctx->accum.as<char>() + 2 * af;
+        ctx->accum_bytes = 2 * af + av;
+    }
     const cudaMemcpyKind kind = mem == DP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (nV) {
         if (vdtype == DP_F64) {
@@ -244,10 +258,19 @@ int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const int32_
         }
     }
     if (nF) CK(cudaMemcpyAsync(ctx->F.p, F, (size_t)nF * 12, kind, s), "dp_set_mesh: copy F");
-    CK(cudaMemsetAsync(ctx->hist.p, 0, nf * 4, s), "dp_set_mesh: zero");
-    CK(cudaMemsetAsync(ctx->fmax.p, 0, nf * 4, s), "dp_set_mesh: zero");
-    CK(cudaMemsetAsync(ctx->vmax.p, 0, nv * 4, s), "dp_set_mesh: zero");
+    CK(cudaMemsetAsync(ctx->accum.p, 0, ctx->accum_bytes, s), "dp_set_mesh: zero");
     if (mem == DP_HOST) CK(cudaStreamSynchronize(s), "dp_set_mesh: sync");
+    else if (nF) {
+        // a device-resident mesh cannot be validated on the host: one pass over the indices, one 4-byte read-back
+        int *d_flag = reinterpret_cast<int *>(ctx->counts.as<long long>() + 5);
+        CK(check_faces(ctx->F.as<int32_t>(), nF, nV, d_flag, s), "dp_set_mesh: index check");
+        CK(cudaMemcpyAsync(ctx->h_counts + 5, d_flag, 4, cudaMemcpyDeviceToHost, s), "dp_set_mesh: index check");
+        CK(cudaStreamSynchronize(s), "dp_set_mesh: index check");
+        if (*reinterpret_cast<int *>(ctx->h_counts + 5)) {
+            ctx->has_mesh = false;
+            return fail(ctx, DP_E_ARG, "dp_set_mesh: face index out of range");
+        }
+    }
     ctx->nV = nV;
     ctx->nF = nF;
     ctx->vdtype = vdtype;
@@ -299,8 +322,8 @@ int dp_build_bvh(dp_ctx *ctx, void *stream)
         if (e != cudaErrorMemoryAllocation) break;
         cudaGetLastError();
     }
-    if (e == cudaErrorInvalidValue) return fail(ctx, DP_E_STATE, "dp_build_bvh: hierarchy deeper than 126 levels");
     CK(e, "dp_build_bvh");
+    if (ctx->topo.n_levels < 0) return fail(ctx, DP_E_STATE, "dp_build_bvh: hierarchy deeper than 126 levels");
     CK(cudaEventRecord(ctx->ev[9], s), "dp_build_bvh");
     CK(cudaEventSynchronize(ctx->ev[9]), "dp_build_bvh: kernels");
     cudaEventElapsedTime(&ctx->build_ms, ctx->ev[8], ctx->ev[9]);
@@ -569,7 +592,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     OrderState *ord_next = nullptr;
     {
         const size_t np = (size_t)(cap / 32 + 2);
-        const size_t per = np * 4 * 2 + ((np + 15) & ~size_t(15));
+        const size_t per = np * 4 * 3 + ((np + 15) & ~size_t(15));
         const void *before = ctx->order.p;
         CK(ctx->order.ensure(2 * per + 256), "dp_project: schedule");
         char *basep = ctx->order.as<char>();
@@ -578,10 +601,11 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
             OrderState h[2];
             for (int k = 0; k < 2; ++k) {
                 char *p = basep + 256 + k * per;
-                h[k].n_valid = -1; h[k].cost_sum = 0; h[k].cnt[0] = h[k].cnt[1] = 0;
+                h[k].n_valid = -1; h[k].cost_sum = 0; h[k].cnt[0] = h[k].cnt[1] = h[k].cnt[2] = 0; h[k].pad_ = 0;
                 h[k].list0 = reinterpret_cast<uint32_t *>(p);
                 h[k].list1 = reinterpret_cast<uint32_t *>(p + np * 4);
-                h[k].flags = reinterpret_cast<unsigned char *>(p + np * 8);
+                h[k].list2 = reinterpret_cast<uint32_t *>(p + np * 8);
+                h[k].flags = reinterpret_cast<unsigned char *>(p + np * 12);
             }
             CK(cudaMemcpyAsync(dstate, h, sizeof(h), cudaMemcpyHostToDevice, s), "dp_project: schedule");   // (re)allocation only
             ctx->order_parity = 0;
@@ -617,15 +641,15 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     // t_hit is needed by the hit-point kernel even when the caller does not want it
     if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
     CK(ctx->dir4.ensure((size_t)cap * 32 + 32), "dp_project: rays");
-    CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s),
+    CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s, n_elems, ctx->shard),
        "dp_project: ray generation");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
     CK(launch_trace_pixels(view_of(b), ctx->dir4.as<float4>(), d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
-                           d_counts + 1, st, ord_prev, ord_next, s, true),
+                           d_counts + 1, st, ord_prev, ord_next, s, true, ctx->shard),
        "dp_project: traversal");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
-    CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s),
+    CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s, n_elems, ctx->shard),
        "dp_project: hit points");
     if (out && out->counts) {
         // device memory: plain store; pinned host memory: zero-copy store through its device alias
@@ -968,17 +992,74 @@ int dp_pack_hits(dp_ctx *ctx, const void *intensity, int dtype, const int32_t *f
     return DP_OK;
 }
 
+int dp_set_ray_shard(dp_ctx *ctx, int rank, int world)
+{
+    if (!ctx) return DP_E_ARG;
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, DP_E_ARG, "dp_set_ray_shard: need 0 <= rank < world");
+    if (rank != ctx->shard.rank || world != ctx->shard.world) ctx->order_np = 0;   // the learnt packet lists are per shard
+    ctx->shard.rank = rank;
+    ctx->shard.world = world;
+    return DP_OK;
+}
+
+int dp_shard_slots(int rank, int world, int64_t n_rays, int64_t nframes, int H, int W, int64_t *lo, int64_t *hi)
+{
+    if (!lo || !hi || n_rays < 0 || nframes < 0 || H < 0 || W < 0 || world < 1 || rank < 0 || rank >= world) return DP_E_ARG;
+    RayShard sh;
+    sh.rank = rank;
+    sh.world = world;
+    shard_slots_host(n_rays, nframes * (int64_t)H * W, H, W, sh, lo, hi);
+    return DP_OK;
+}
+
+int dp_pack_records(dp_ctx *ctx, const uint32_t *pixel, const float *t_hit, const int32_t *face, const float *point,
+                    int64_t n, int64_t first, uint32_t *records, int64_t cap, int64_t *m, int64_t *m_async, int mem, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (n < 0 || first < 0 || cap < 0 || (n > 0 && (!face || !t_hit)) || (cap > 0 && !records) || (!m && !m_async))
+        return fail(ctx, DP_E_ARG, "dp_pack_records: bad arguments");
+    if (mem != DP_DEVICE) return fail(ctx, DP_E_ARG, "dp_pack_records: device buffers only (the per-ray outputs of dp_project)");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(ctx->tmp[7].ensure(pack_scratch_bytes(n) + 64), "dp_pack_records: scratch");
+    long long *d_count = ctx->counts.as<long long>() + 4;
+    long long *d_async = nullptr;
+    if (m_async) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, m_async) == cudaSuccess && at.devicePointer) d_async = static_cast<long long *>(at.devicePointer);
+        else { cudaGetLastError(); return fail(ctx, DP_E_ARG, "dp_pack_records: m_async must be device or pinned host memory"); }
+    }
+    CK(launch_pack_records(pixel, t_hit, face, point, n, first, records, cap, ctx->tmp[7].as<unsigned long long>(), d_count,
+                           d_async, s),
+       "dp_pack_records: launch");
+    if (m) {
+        CK(cudaMemcpyAsync(ctx->h_counts + 4, d_count, 8, cudaMemcpyDeviceToHost, s), "dp_pack_records: count");
+        CK(cudaStreamSynchronize(s), "dp_pack_records: kernel");
+        *m = ctx->h_counts[4];
+        if (*m > cap) return fail(ctx, DP_E_NOMEM, "dp_pack_records: capacity too small for the hits");
+    }
+    return DP_OK;
+}
+
+int dp_accum_layout(dp_ctx *ctx, void **base, int64_t *hist_off, int64_t *fmax_off, int64_t *vmax_off, int64_t *bytes)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_layout: no mesh");
+    if (base) *base = ctx->accum.p;
+    if (hist_off) *hist_off = 0;
+    if (fmax_off) *fmax_off = (int64_t)(ctx->fmax.as<char>() - ctx->accum.as<char>());
+    if (vmax_off) *vmax_off = (int64_t)(ctx->vmax.as<char>() - ctx->accum.as<char>());
+    if (bytes) *bytes = (int64_t)ctx->accum_bytes;
+    return DP_OK;
+}
+
 int dp_accum_reset(dp_ctx *ctx, void *stream)
 {
     if (!ctx) return DP_E_ARG;
     if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_accum_reset: no mesh");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (ctx->nF) {
-        CK(cudaMemsetAsync(ctx->hist.p, 0, (size_t)ctx->nF * 4, s), "dp_accum_reset");
-        CK(cudaMemsetAsync(ctx->fmax.p, 0, (size_t)ctx->nF * 4, s), "dp_accum_reset");
-    }
-    if (ctx->nV) CK(cudaMemsetAsync(ctx->vmax.p, 0, (size_t)ctx->nV * 4, s), "dp_accum_reset");
+    CK(cudaMemsetAsync(ctx->accum.p, 0, ctx->accum_bytes, s), "dp_accum_reset");
     return DP_OK;
 }
 

@@ -503,7 +503,7 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
                            const int32_t *__restrict__ last, const float *__restrict__ blo,
                            const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
                            WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
-                           float c_prim, int greedy_mode, int32_t *wparent, int dp_max_count, int32_t *sel)
+                           float c_prim, int greedy_mode, int32_t *wparent, int dp_max_count, int32_t *sel, long long cap_nodes)
 {
     const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long w = begin + (MODE == 1 ? gt : (gt >> 3));
@@ -701,8 +701,12 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
         if (my_inner) {
             ibit = 1u << my_slot;
             meta = 0x20u | (24u + (unsigned)my_slot);
-            if (wparent) wparent[cbase + k_inner] = (int32_t)w;
-            wroot[cbase + k_inner] = my;
+            // beyond the node capacity nothing is written: counters[0] still reports the overflow and the host retries
+            // with the larger capacity (build_lbvh)
+            if ((long long)cbase + k_inner < cap_nodes) {
+                if (wparent) wparent[cbase + k_inner] = (int32_t)w;
+                wroot[cbase + k_inner] = my;
+            }
         } else {
             const long long f0 = my < n - 1 ? first[my] : my - (n - 1);
             meta = (((1u << my_cnt) - 1u) << 5) | (unsigned)toff;
@@ -907,6 +911,13 @@ __global__ void k_pose_vertices(const TV *V, long long nV, Mat34 T, int identity
     if ((threadIdx.x & 31) == 0 && mx) atomicMax(scale_bits, mx);
 }
 
+// face indices of a device-resident mesh: any index outside [0, nV) raises the flag (dp_set_mesh checks host meshes itself)
+__global__ void k_check_faces(const int32_t *__restrict__ F, long long n3, int32_t nV, int *flag)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n3 && (F[i] < 0 || F[i] >= nV)) *flag = 1;
+}
+
 __global__ void k_f64_to_f32(const double *__restrict__ a, float *__restrict__ b, long long n)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1103,19 +1114,19 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     long long begin = 0, end = 1;
     int L = 0;
     while (begin < end) {
-        if (L + 1 >= 127) return cudaErrorInvalidValue;
+        if (L + 1 >= 127) { topo.n_levels = -1; return cudaSuccess; }      // deeper than any ray stack: reported by the caller
         const long long lvl = end - begin;
         if (lvl < 2048 || lvl > (long long)(N / 2 + 64)) {
             k_collapse<0><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
                                                                out.nodes, topo.tri_face, counters, ctab, c_prim,
-                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf);
+                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes);
         } else {
             k_collapse<1><<<blocks_for(lvl, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
                                                                out.nodes, topo.tri_face, counters, ctab, c_prim,
-                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf);
+                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes);
             k_collapse<2><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
                                                                out.nodes, topo.tri_face, counters, ctab, c_prim,
-                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf);
+                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes);
         }
         unsigned cnt[2];
         if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -1130,6 +1141,14 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     if ((e = cudaMemsetAsync(topo.arrived, 0, (size_t)out.n_nodes * 4, s)) != cudaSuccess) return e;
     k_fit_all<<<blocks_for(out.n_nodes * 8, 256), 256, 0, s>>>(out.n_nodes, out.nodes, out.nodes, out.tris, out.wlo, out.whi,
                                                            out.d_scale, V, F, topo.tri_face, topo.wparent, topo.arrived, out.fat);
+    return cudaGetLastError();
+}
+
+cudaError_t check_faces(const int32_t *F, int64_t nF, int64_t nV, int *d_flag, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), s);
+    if (e != cudaSuccess || nF <= 0) return e;
+    k_check_faces<<<blocks_for(3 * nF, 256), 256, 0, s>>>(F, 3 * nF, (int32_t)nV, d_flag);
     return cudaGetLastError();
 }
 

@@ -164,7 +164,7 @@ k_project_prologue(unsigned long long *scratch, long long scratch_words, long lo
     for (long long i = threadIdx.x; i < scratch_words; i += blockDim.x) scratch[i] = 0ull;
     if (threadIdx.x < 4) counts[threadIdx.x] = 0;                 // rays, hits, the two traversal work counters
     if (threadIdx.x == 3 && ord_next) {
-        ord_next->n_valid = -1; ord_next->cost_sum = 0; ord_next->cnt[0] = 0; ord_next->cnt[1] = 0;
+        ord_next->n_valid = -1; ord_next->cost_sum = 0; ord_next->cnt[0] = 0; ord_next->cnt[1] = 0; ord_next->cnt[2] = 0;
     }
     if ((int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + 16 * n_xf) {
         const int k = threadIdx.x - 32;

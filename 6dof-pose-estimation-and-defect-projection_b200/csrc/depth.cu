@@ -77,7 +77,10 @@ k_depth_select(const T *__restrict__ heat, int H, int W, const uint16_t *__restr
         if (e < n) {
             const int y = (int)(e / W), x = (int)(e - (long long)y * W);
             if (y < Hd && x < Wd) {
-                const double v = __ddiv_rn((double)heat[e], maxv);
+                // a float32 map divides in float32 (:384: np.float32 / np.float32); the rounded quotient, widened, is what
+                // the reference compares with the threshold (numpy 1.26.4: in float64) and stores in column 3
+                const double v = sizeof(T) == 4 ? (double)__fdiv_rn((float)heat[e], (float)maxv)
+                                                : __ddiv_rn((double)heat[e], maxv);
                 if (v > thr) {
                     const unsigned short d = depth[(long long)y * Wd + x];
                     if (d > 0) { m |= 1u << j; inten[j] = v; dep[j] = d; }

@@ -75,8 +75,11 @@ struct Accum {
 struct OrderState {
     long long n_valid;               // ray count the lists were built for (-1 = none)
     unsigned long long cost_sum;     // sum over packets of the longest ray (node steps)
-    unsigned cnt[2];                 // entries in list0 / list1
-    uint32_t *list0, *list1;         // packets above 2.5x / 1.5x the mean cost
+    unsigned cnt[3];                 // entries in list0 / list1 / list2
+    unsigned pad_;
+    uint32_t *list0, *list1;         // packets above 2.5x / 1.5x the mean cost: traced first
+    uint32_t *list2;                 // packets below 0.75x the mean cost: traced last (the tail of the launch is made of
+                                     // short packets: simulated on the benchmark frame's measured costs, SM-busy 0.90 -> 0.96)
     unsigned char *flags;            // [packets] 1 = the packet is in one of the lists
 };
 
@@ -141,17 +144,24 @@ cudaError_t launch_project_prologue(unsigned long long *scratch, int64_t n_elems
 cudaError_t launch_publish_counts(const long long *counts, long long *dst, cudaStream_t s);
 
 // ---- trace.cu ------------------------------------------------------------------------------
+// single-frame ray sharding: this context traces block `rank` of `world` of every frame's compacted ray list
+struct RayShard {
+    int rank = 0, world = 1;
+};
+// output slots [lo, hi) of the shard for a frame of n selected pixels (same partition as the kernels)
+void shard_slots_host(int64_t n, int64_t total_px, int H, int W, RayShard shard, int64_t *lo, int64_t *hi);
 // rays from pixels: pixel[i] = frame*HW + y*W + x ; xf[frame] ; n read from *d_n (<= n_max)
 cudaError_t launch_raygen(const uint32_t *pixel, const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
-                          int64_t n_xf, float4 *dir4, cudaStream_t s);
+                          int64_t n_xf, float4 *dir4, cudaStream_t s, int64_t total_px = 0, RayShard shard = RayShard());
 cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long long *d_n, int64_t n_max, int H, int W,
-                          const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s);
+                          const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s,
+                          int64_t total_px = 0, RayShard shard = RayShard());
 // dir4[2i] = origin (object frame), dir4[2i+1] = (direction, frame index bits) of compacted ray i, written by launch_raygen
 cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const float *intensity, const long long *d_n,
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
-                                bool counter_zeroed = false);
+                                bool counter_zeroed = false, RayShard shard = RayShard());
 // per-vertex maxima from the per-face maxima (run when the accumulators are read, not per hit)
 cudaError_t launch_vertex_max(const uint32_t *fmax, const int32_t *F, int64_t nF, uint32_t *vmax, cudaStream_t s);
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,
@@ -183,6 +193,10 @@ cudaError_t launch_pack_hits(const void *inten, int dtype, const int32_t *face, 
                              int64_t n, const double *T_host, const double *lut, long long *mm, double *points, double *colors,
                              int32_t *face_out, uint32_t *pixel_out, double *inten_out, int64_t cap,
                              unsigned long long *scratch, long long *d_count, cudaStream_t s);
+
+cudaError_t launch_pack_records(const uint32_t *pixel, const float *t_hit, const int32_t *face, const float *point, int64_t n,
+                                int64_t first, uint32_t *rec, int64_t cap, unsigned long long *scratch, long long *d_count,
+                                long long *m_async, cudaStream_t s);
 
 // ---- icp.cu --------------------------------------------------------------------------------
 constexpr int ICP_GRID_MIN_POINTS = 256;   // smaller targets are scanned (one shared-memory tile)
@@ -255,6 +269,7 @@ cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t 
                            float *Vposed, double *Vposed64, const BvhStorage &src, BvhStorage &dst,
                            const Topology &topo, cudaStream_t s);
 cudaError_t convert_f64_to_f32(const double *src, float *dst, int64_t n, cudaStream_t s);
+cudaError_t check_faces(const int32_t *F, int64_t nF, int64_t nV, int *d_flag, cudaStream_t s);
 cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
                              uint32_t *table, cudaStream_t s, bool *result_in_tmp);
 size_t radix_table_entries(int64_t n);

@@ -234,6 +234,70 @@ k_pack_hits(const T *__restrict__ inten, const int32_t *__restrict__ face, const
     }
 }
 
+
+// Lean hit records for the multi-GPU gather: the rays of [first, first + n) that hit, in ray order,
+// as rows of 3 words (pixel, t_hit bits, face) or 6 words (+ float32 hit point).  Same ballot ranks + decoupled
+// look-back as k_pack_hits; the count also goes to `m_async` (device or mapped pinned-host memory) when given.
+__global__ void __launch_bounds__(PK_THREADS)
+k_pack_records(const uint32_t *__restrict__ pixel, const float *__restrict__ t_hit, const int32_t *__restrict__ face,
+               const float *__restrict__ point, long long n, long long first, uint32_t *__restrict__ rec, long long cap,
+               unsigned long long *scratch, long long *d_count, long long *m_async)
+{
+    __shared__ unsigned s_tile, s_warp_tot[PK_THREADS / 32], s_warp_off[PK_THREADS / 32];
+    __shared__ long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned *>(scratch), 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    unsigned long long *state = scratch + 1;
+    const long long e0 = (long long)tile * PK_TILE + (long long)tid * PK_ITEMS;
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < PK_ITEMS; ++j) {
+        const long long e = e0 + j;
+        if (e < n && face[first + e] >= 0) m |= 1u << j;
+    }
+    const unsigned cnt = __popc(m);
+    unsigned inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    if (lane == 31) s_warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned run = 0;
+        for (int w = 0; w < PK_THREADS / 32; ++w) { const unsigned c = s_warp_tot[w]; if (lane == 0) s_warp_off[w] = run; run += c; }
+        const unsigned long long total = run;
+        const unsigned long long prefix = lookback_exclusive_prefix(state, tile, total, lane);
+        if (lane == 0) {
+            s_base = (long long)prefix;
+            if ((long long)(tile + 1) * PK_TILE >= n) {
+                *d_count = (long long)(prefix + total);
+                if (m_async) *m_async = (long long)(prefix + total);
+            }
+        }
+    }
+    __syncthreads();
+    if (!m) return;
+    const int stride = point ? 6 : 3;
+    long long off = s_base + s_warp_off[warp] + (inc - cnt);
+#pragma unroll
+    for (int j = 0; j < PK_ITEMS; ++j) {
+        if (!((m >> j) & 1u)) continue;
+        if (off < cap) {
+            const long long e = first + e0 + j;
+            uint32_t *o = rec + off * stride;
+            o[0] = pixel ? pixel[e] : (uint32_t)e;
+            o[1] = __float_as_uint(t_hit[e]);
+            o[2] = (uint32_t)face[e];
+            if (point) { o[3] = __float_as_uint(point[3 * e]); o[4] = __float_as_uint(point[3 * e + 1]); o[5] = __float_as_uint(point[3 * e + 2]); }
+        }
+        ++off;
+    }
+}
+
 }  // namespace
 
 // matplotlib's LinearSegmentedColormap('jet', N=256) table (colors._create_lookup_table), float64, RGB.
@@ -340,6 +404,18 @@ cudaError_t launch_pack_hits(const void *inten, int dtype, const int32_t *face, 
         k_pack_hits<float><<<tiles, PK_THREADS, 0, s>>>(static_cast<const float *>(inten), face, pixel, point64, n, mm, lut,
                                                         T_host != nullptr, T, points, colors, face_out, pixel_out, inten_out,
                                                         cap, scratch, d_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_records(const uint32_t *pixel, const float *t_hit, const int32_t *face, const float *point, int64_t n,
+                                int64_t first, uint32_t *rec, int64_t cap, unsigned long long *scratch, long long *d_count,
+                                long long *m_async, cudaStream_t s)
+{
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(scratch, 0, pack_scratch_bytes(n > 0 ? n : 1), s)) != cudaSuccess) return e;
+    // n == 0 still launches one tile: it publishes the zero count
+    const unsigned tiles = (unsigned)((n + PK_TILE - 1) / PK_TILE);
+    k_pack_records<<<tiles ? tiles : 1, PK_THREADS, 0, s>>>(pixel, t_hit, face, point, n, first, rec, cap, scratch, d_count, m_async);
     return cudaGetLastError();
 }
 

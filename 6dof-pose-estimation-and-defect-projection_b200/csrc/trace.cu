@@ -451,25 +451,62 @@ constexpr int NR_STACK = 64;                          // stack entries per ray (
                                                       // 16-23 % faster than packets at 35k-110k rays, 30-35 % at 9k-16k)
 #endif
 
+// ------------------------------------------------------------------------------------------
+// Single-frame ray sharding: with `world` > 1 a launch traces only rank `rank`'s contiguous block of
+// the compacted ray list, in units of 32-ray packets -- whole tile rows (4 image rows) when the dense frame is walked in
+// 8x4 tiles, so that the block is also a contiguous range of row-major output slots [s_lo, s_hi).
+// dp_shard_slots (api.cu) evaluates the same partition on the host.
+// ------------------------------------------------------------------------------------------
+struct Shard {
+    long long p_lo, p_hi;     // packets of the work order
+    long long s_lo, s_hi;     // output slots
+    bool tiled;
+};
+__host__ __device__ inline Shard shard_of(long long n, long long total_px, int H, int W, int allow_tiled, int narrow, int rank,
+                                          int world)
+{
+    Shard sh;
+    sh.tiled = allow_tiled && n == total_px && (W & 7) == 0 && (H & 3) == 0 && W > 0 && !(narrow && n <= DP_NARROW_MAX_RAYS);
+    const long long np = (n + 31) >> 5;
+    sh.p_lo = 0; sh.p_hi = np;
+    if (world > 1) {
+        const long long unit = sh.tiled ? (long long)(W >> 3) : 1;
+        const long long units = (np + unit - 1) / unit;
+        sh.p_lo = (units * rank / world) * unit;
+        sh.p_hi = (units * (rank + 1) / world) * unit;
+        if (sh.p_lo > np) sh.p_lo = np;
+        if (sh.p_hi > np) sh.p_hi = np;
+    }
+    // a packet of the tiled order covers 8x4 pixels; W/8 packets = four full image rows
+    sh.s_lo = sh.tiled ? (sh.p_lo / (W >> 3)) * 4ll * W : sh.p_lo * 32;
+    sh.s_hi = sh.tiled ? (sh.p_hi / (W >> 3)) * 4ll * W : sh.p_hi * 32;
+    if (sh.s_lo > n) sh.s_lo = n;
+    if (sh.s_hi > n) sh.s_hi = n;
+    return sh;
+}
+
 template <bool STATS>
 __device__ __noinline__ void
 trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
              const float4 *__restrict__ dir4, const float *__restrict__ intensity, long long n,
              float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
-             unsigned long long *work_counter, long long *d_hits, TraceStats *stats, uint2 *s_stack)
+             unsigned long long *work_counter, long long *d_hits, TraceStats *stats, uint2 *s_stack, long long s_lo,
+             long long s_hi)
 {
     const int lane = threadIdx.x & 31, c = lane & 7, g = lane >> 3;
     const unsigned gmask = 0xffu << (8 * g);
     uint2 *stack = s_stack + (threadIdx.x >> 3) * NR_STACK;
     const float scale = __ldg(d_scale);
-    const long long nitems = (n + 3) >> 2;                        // one work item = four consecutive rays = one warp
+    // one work item = four consecutive rays = one warp; a shard's slots start on a packet (32-ray) boundary
+    const long long item0 = s_lo >> 2, nitems = ((s_hi + 3) >> 2) - item0;
+    n = s_hi;
     unsigned long long nn = 0, nt = 0, nhit = 0, nray = 0;
     for (;;) {
         unsigned long long wv = 0;
         if (lane == 0) wv = atomicAdd(work_counter, 1ull);
         const long long w = (long long)__shfl_sync(0xffffffffu, wv, 0);
         if (w >= nitems) break;
-        const long long i = w * 4 + g;
+        const long long i = (item0 + w) * 4 + g;
         const bool valid = i < n;
         bool alive = valid;
         RayState r;
@@ -603,6 +640,9 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
     }
 }
 
+#ifndef DP_LIGHT_FRAC
+#define DP_LIGHT_FRAC 0.75f  // packets cheaper than this fraction of the mean are traced last
+#endif
 #ifndef DP_MIN_BLOCKS_BIG
 #define DP_MIN_BLOCKS_BIG 5  // hierarchies beyond L2 (5M triangles: 0.511 -> 0.49 ms): fewer packets share an SM's L1
 #endif
@@ -618,8 +658,10 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         const long long *__restrict__ d_n, long long n_max, long long total_px, int H, int W,
         const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
         unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
-        const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch, int narrow_enabled)
+        const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch, int narrow_enabled, int shard_rank,
+        int shard_world)
 {
+    // (the learnt packet lists hold packets of the previous launch over the same shard: dp_set_ray_shard drops them)
     const bool pf = prefetch != 0;
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
     __shared__ unsigned s_queue[(TR_THREADS / 32) * TQ_CAP];
@@ -632,25 +674,28 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
     const unsigned lt = (1u << lane) - 1u;
     long long n = d_n ? *d_n : n_max;
     if (n > n_max) n = n_max;
+    const Shard sh = shard_of(n, total_px, H, W, SRC == 0 && allow_tiled, SRC == 0 && narrow_enabled, shard_rank, shard_world);
     if (SRC == 0 && narrow_enabled && n <= DP_NARROW_MAX_RAYS) {
         // sparse frame: eight lanes per ray (work items come from the second counter)
         static_assert(STACK_SMEM * TR_THREADS >= (NR_THREADS / 8) * NR_STACK, "the narrow path borrows the packet stack");
-        trace_narrow<STATS>(nodes, tris, d_scale, dir4, intensity, n, t_hit, face, acc, has_acc, work_counter + 1, d_hits, stats, s_stack);
+        trace_narrow<STATS>(nodes, tris, d_scale, dir4, intensity, n, t_hit, face, acc, has_acc, work_counter + 1, d_hits, stats,
+                            s_stack, sh.s_lo, sh.s_hi);
         return;
     }
-    const bool tiled = SRC == 0 && allow_tiled && n == total_px && (W & 7) == 0 && (H & 3) == 0 && W > 0;
+    const bool tiled = sh.tiled;
     const float scale = __ldg(d_scale);
     unsigned nn = 0, nt = 0, n_hit_local = 0, n_ray_local = 0;
     // Packets the previous launch over the same rays found expensive (longest ray, in node steps,
     // above 2.5x / 1.5x the mean) are walked first, so that their long dependent chains overlap with
     // the bulk of the work instead of forming the tail of the kernel; the rest follows in natural order.
-    const long long np = (n + 31) >> 5;
+    const long long np = sh.p_hi - sh.p_lo;                 // packets of this launch (all of them unless sharded)
     const bool use_order = ord_prev != nullptr && ord_prev->n_valid == n;
-    const long long c0 = use_order ? (long long)ord_prev->cnt[0] : 0, c1 = use_order ? (long long)ord_prev->cnt[1] : 0;
-    float thr0 = __int_as_float(0x7f800000), thr1 = thr0;
+    const long long c0 = use_order ? (long long)ord_prev->cnt[0] : 0, c1 = use_order ? (long long)ord_prev->cnt[1] : 0,
+                    c2 = use_order ? (long long)ord_prev->cnt[2] : 0;
+    float thr0 = __int_as_float(0x7f800000), thr1 = thr0, thr2 = -1.0f;
     if (ord_prev != nullptr && ord_prev->n_valid == n && np > 0) {
         const float mean = (float)ord_prev->cost_sum / (float)np;
-        thr0 = 2.5f * mean; thr1 = 1.5f * mean;
+        thr0 = 2.5f * mean; thr1 = 1.5f * mean; thr2 = DP_LIGHT_FRAC * mean;
     }
     if (ord_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ord_next->n_valid = n;
     unsigned long long cost_local = 0;
@@ -660,15 +705,15 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
     if (lane == 0) nextw = atomicAdd(work_counter, 1ull);
     for (;;) {
         const long long w = (long long)__shfl_sync(0xffffffffu, nextw, 0);
-        if (w >= np + c0 + c1) break;
+        if (w >= np + c0 + c1 + c2) break;
         if (lane == 0) nextw = atomicAdd(work_counter, 1ull);
         long long packet;
         if (w < c0) packet = ord_prev->list0[w];
         else if (w < c0 + c1) packet = ord_prev->list1[w - c0];
-        else {
-            packet = w - c0 - c1;
-            if (use_order && ord_prev->flags[packet]) continue;      // already done from a list
-        }
+        else if (w < c0 + c1 + np) {
+            packet = sh.p_lo + (w - c0 - c1);
+            if (use_order && ord_prev->flags[packet]) continue;      // traced from a list (before, or at the end)
+        } else packet = ord_prev->list2[w - c0 - c1 - np];
         const long long i = packet * 32 + lane;
         bool alive = i < n;
         const bool valid = alive;
@@ -811,11 +856,11 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             if (lane == 0) {
                 cost_local += c;
                 const float cf = (float)c;
-                const int cls = cf > thr0 ? 0 : (cf > thr1 ? 1 : 2);
-                ord_next->flags[packet] = cls < 2;
-                if (cls < 2) {
+                const int cls = cf > thr0 ? 0 : (cf > thr1 ? 1 : (cf < thr2 ? 2 : 3));
+                ord_next->flags[packet] = cls < 3;
+                if (cls < 3) {
                     const unsigned pos = atomicAdd(&ord_next->cnt[cls], 1u);
-                    (cls == 0 ? ord_next->list0 : ord_next->list1)[pos] = (uint32_t)packet;
+                    (cls == 0 ? ord_next->list0 : (cls == 1 ? ord_next->list1 : ord_next->list2))[pos] = (uint32_t)packet;
                 }
             }
         }
@@ -895,12 +940,17 @@ __device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const 
 
 __global__ void __launch_bounds__(256)
 k_raygen(const uint32_t *__restrict__ pixel, const long long *__restrict__ d_n, long long n_max, int H, int W,
-         const FrameXf *__restrict__ xf, long long n_xf, float4 *__restrict__ dir4)
+         const FrameXf *__restrict__ xf, long long n_xf, float4 *__restrict__ dir4, long long total_px, int allow_tiled,
+         int narrow, int shard_rank, int shard_world)
 {
     long long n = *d_n;
     if (n > n_max) n = n_max;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (shard_world > 1) {
+        const Shard sh = shard_of(n, total_px, H, W, allow_tiled, narrow, shard_rank, shard_world);
+        if (i < sh.s_lo || i >= sh.s_hi) return;
+    }
     uint32_t fr;
     double dcx, dcy, dcz;
     pixel_ray_f64(pixel[i], H, W, xf, n_xf, fr, dcx, dcy, dcz);
@@ -920,12 +970,16 @@ k_raygen(const uint32_t *__restrict__ pixel, const long long *__restrict__ d_n, 
 __global__ void __launch_bounds__(256)
 k_points(const uint32_t *__restrict__ pixel, const float *__restrict__ t_hit, const long long *__restrict__ d_n,
          long long n_max, int H, int W, const FrameXf *__restrict__ xf, long long n_xf, float *__restrict__ point,
-         double *__restrict__ point64)
+         double *__restrict__ point64, long long total_px, int allow_tiled, int narrow, int shard_rank, int shard_world)
 {
     long long n = *d_n;
     if (n > n_max) n = n_max;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (shard_world > 1) {
+        const Shard sh = shard_of(n, total_px, H, W, allow_tiled, narrow, shard_rank, shard_world);
+        if (i < sh.s_lo || i >= sh.s_hi) return;
+    }
     const float tf = t_hit[i];
     const bool hit = tf < __int_as_float(0x7f800000);
     double px, py, pz;
@@ -990,7 +1044,7 @@ int knob_tiled()
 }
 
 #ifndef DP_MIN_BLOCKS_FAT
-#define DP_MIN_BLOCKS_FAT 7
+#define DP_MIN_BLOCKS_FAT 6  // 80 registers, 6 CTAs per SM: 0.228 ms against 0.234 (7 CTAs, 72 registers, spills) and 0.264 (8 CTAs)
 #endif
 // DP_FAT=0: trace the compressed set even when the uncompressed twin exists (read per launch: tests flip it)
 int knob_fat()
@@ -1046,18 +1100,28 @@ cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n,
 }
 
 cudaError_t launch_raygen(const uint32_t *pixel, const long long *d_n, int64_t n_max, int H, int W, const FrameXf *xf,
-                          int64_t n_xf, float4 *dir4, cudaStream_t s)
+                          int64_t n_xf, float4 *dir4, cudaStream_t s, int64_t total_px, RayShard shard)
 {
     if (n_max <= 0) return cudaSuccess;
-    k_raygen<<<(unsigned)((n_max + 255) / 256), 256, 0, s>>>(pixel, d_n, n_max, H, W, xf, n_xf, dir4);
+    k_raygen<<<(unsigned)((n_max + 255) / 256), 256, 0, s>>>(pixel, d_n, n_max, H, W, xf, n_xf, dir4, total_px, knob_tiled(),
+                                                             knob_narrow(), shard.rank, shard.world);
     return cudaGetLastError();
 }
 
+void shard_slots_host(int64_t n, int64_t total_px, int H, int W, RayShard shard, int64_t *lo, int64_t *hi)
+{
+    const Shard sh = shard_of(n, total_px, H, W, knob_tiled(), knob_narrow(), shard.rank, shard.world);
+    *lo = sh.s_lo;
+    *hi = sh.s_hi;
+}
+
 cudaError_t launch_points(const uint32_t *pixel, const float *t_hit, const long long *d_n, int64_t n_max, int H, int W,
-                          const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s)
+                          const FrameXf *xf, int64_t n_xf, float *point, double *point64, cudaStream_t s, int64_t total_px,
+                          RayShard shard)
 {
     if (n_max <= 0 || (!point && !point64)) return cudaSuccess;
-    k_points<<<(unsigned)((n_max + 255) / 256), 256, 0, s>>>(pixel, t_hit, d_n, n_max, H, W, xf, n_xf, point, point64);
+    k_points<<<(unsigned)((n_max + 255) / 256), 256, 0, s>>>(pixel, t_hit, d_n, n_max, H, W, xf, n_xf, point, point64, total_px,
+                                                             knob_tiled(), knob_narrow(), shard.rank, shard.world);
     return cudaGetLastError();
 }
 
@@ -1065,7 +1129,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
-                                bool counter_zeroed)
+                                bool counter_zeroed, RayShard shard)
 {
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
@@ -1082,7 +1146,8 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
 #define DP_LAUNCH_TRACE0(ST, MB, FMT)                                                                                        \
     k_trace<ST, 0, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, \
                                                         n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, \
-                                                        d_hits, stats, knob_tiled(), ord_prev, ord_next, pf, narrow)
+                                                        d_hits, stats, knob_tiled(), ord_prev, ord_next, pf, narrow, shard.rank, \
+                                                        shard.world)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG, 0);
@@ -1112,7 +1177,7 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
 #define DP_LAUNCH_TRACE1(ST, MB, FMT)                                                                                          \
     k_trace<ST, 1, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, \
                                                         n, 0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, \
-                                                        nullptr, nullptr, pf, 0)
+                                                        nullptr, nullptr, pf, 0, 0, 1)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG, 0);

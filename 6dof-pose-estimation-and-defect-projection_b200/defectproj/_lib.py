@@ -57,6 +57,10 @@ SYMBOLS = {
     "dp_transform_points": (i32, [vp, vp, i64, vp, i32, vp]),
     "dp_pack_hits": (i32, [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64), i32, vp]),
     "dp_jet_lut": (None, [vp]),
+    "dp_set_ray_shard": (i32, [vp, i32, i32]),
+    "dp_shard_slots": (i32, [i32, i32, i64, i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "dp_pack_records": (i32, [vp, vp, vp, vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp, i32, vp]),
+    "dp_accum_layout": (i32, [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "dp_icp_point_to_plane": (i32, [vp, vp, i64, vp, vp, i64, f64, vp, i32, f64, f64, vp, C.POINTER(f64), C.POINTER(f64),
                                     C.POINTER(i32), vp, i32, vp]),
     "dp_accum_reset": (i32, [vp, vp]),

@@ -544,6 +544,50 @@ class Context:
         self._check(self._L.dp_accum_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def accum_layout(self):
+        """(base address, hist offset, fmax offset, vmax offset, total bytes) of the one accumulator allocation."""
+        base = C.c_void_p()
+        a, b, c, n = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._L.dp_accum_layout(self._h, C.byref(base), C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return base.value, a.value, b.value, c.value, n.value
+
+    # ------------------------------------------------------------------ multi-GPU helpers (SURVEY.md 8e)
+    def set_ray_shard(self, rank: int = 0, world: int = 1):
+        """Trace only block `rank` of `world` of every frame's compacted ray list (single-frame ray sharding)."""
+        self._check(self._L.dp_set_ray_shard(self._h, int(rank), int(world)))
+        return self
+
+    @staticmethod
+    def shard_slots(rank: int, world: int, n_rays: int, H: int, W: int, nframes: int = 1):
+        """Output slots [lo, hi) of shard `rank` of `world` for a projection that selected n_rays pixels."""
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        rc = _lib.load().dp_shard_slots(int(rank), int(world), int(n_rays), int(nframes), int(H), int(W), C.byref(lo), C.byref(hi))
+        if rc != 0:
+            raise ValueError("shard_slots: bad arguments")
+        return lo.value, hi.value
+
+    def pack_records_device(self, t_hit, face, pixel=None, point=None, first=0, n=None, out=None, count_async=None,
+                            sync=True, stream=None):
+        """Hit records of the rays [first, first+n) of project_device's outputs: rows (pixel, t_hit bits, face[, x, y, z
+        bits]) of the rays that hit, in ray order, as an int32 CUDA tensor [m, 3|6].  `out` may be a preallocated
+        [>= n, 3|6] int32 tensor; `count_async`: pinned int64 tensor [1] that receives m on the stream (sync=False)."""
+        import torch
+        if n is None:
+            n = face.numel() - first
+        w = 6 if point is not None else 3
+        if out is None:
+            out = torch.empty((max(int(n), 1), w), dtype=torch.int32, device=face.device)
+        if out.shape[1] != w or out.dtype != torch.int32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous int32 [cap, {w}] tensor")
+        m = C.c_int64(0)
+        if stream is None:
+            stream = torch.cuda.current_stream(face.device)
+        self._check(self._L.dp_pack_records(self._h, _ptr(pixel), _ptr(t_hit), _ptr(face), _ptr(point), int(n), int(first),
+                                            _ptr(out), out.shape[0], C.byref(m) if sync else None,
+                                            _ptr(count_async) if count_async is not None else None, DP_DEVICE,
+                                            self._stream(stream)))
+        return out[:m.value] if sync else out
+
     # ------------------------------------------------------------------ instrumentation
     def set_stats(self, on: bool):
         self._check(self._L.dp_set_stats(self._h, int(bool(on))))

@@ -1,11 +1,13 @@
-"""Batched / multi-GPU surface: one process per GPU, frames sharded, mesh + BVH replicated.
+"""Batched / multi-GPU surface: one process per GPU, mesh + BVH replicated.
 
-The data path has no collective: every rank projects its own frames against its own copy of
-the BVH.  Only the results are combined:
-    hist  int32  [nF]  all-reduce SUM        fmax / vmax  float32  all-reduce MAX
-    hits  variable length -> all-gather of counts, then padded all-gather of the records
-Integer sums and float maxima do not depend on the order of combination, so an N-GPU result
-is bit-identical to the 1-GPU result.
+The data path has no collective: every rank projects its own frames (`Projector.project_batch`, frames sharded) or
+its own block of one frame's compacted ray list (`Projector.project_frame_sharded`, rays sharded) against its own
+copy of the BVH.  Only the results are combined, once per batch:
+    hist  int32  [nF]              all-reduce SUM   } on a SNAPSHOT of the accumulator block, on a side stream, while
+    fmax | vmax  float32 bits      ONE all-reduce MAX } the next batch's frames run; the live accumulators stay local
+    hits  variable length          counts exchanged once, then the records travel UNPADDED (to every rank, or to one)
+Integer sums and float maxima do not depend on the order of combination, so an N-GPU result is bit-identical to the
+1-GPU result.
 """
 from __future__ import annotations
 
@@ -13,7 +15,8 @@ import numpy as np
 
 from .core import Context
 
-__all__ = ["Projector", "FrameStream", "shard_range", "combine_accumulators", "gather_hits"]
+__all__ = ["Projector", "FrameStream", "BatchCombiner", "shard_range", "combine_accumulators", "combine_block", "fold_block",
+           "gather_hits", "gather_slices"]
 
 
 def shard_range(n_items: int, world: int, rank: int):
@@ -24,10 +27,23 @@ def shard_range(n_items: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def combine_accumulators(hist, fmax, vmax, group=None):
-    """In-place all-reduce of the three accumulators (torch tensors on any device)."""
+def _dist(group=None):
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist
+    return None
+
+
+def _global_rank(dist, group, r):
+    return dist.get_global_rank(group, r) if group is not None else r
+
+
+def combine_accumulators(hist, fmax, vmax, group=None):
+    """In-place all-reduce of three separate accumulator tensors (any device).  Callers that hold the library's live
+    accumulators should NOT use this on them (a following accumulation would count earlier batches `world` times):
+    use BatchCombiner, which reduces a snapshot."""
+    dist = _dist(group)
+    if dist is None:
         return hist, fmax, vmax
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(fmax, op=dist.ReduceOp.MAX, group=group)
@@ -35,29 +51,81 @@ def combine_accumulators(hist, fmax, vmax, group=None):
     return hist, fmax, vmax
 
 
-def gather_hits(records, group=None):
-    """All-gather variable-length per-rank records ([n_r, C] tensor) -> [sum n_r, C] in rank order."""
+def combine_block(block, max_from, group=None):
+    """In-place combination of one accumulator block (int32 tensor: hist | fmax bits | vmax bits, see
+    dp_accum_layout): SUM over the words [0, max_from), ONE MAX over [max_from, end) -- the bit patterns of
+    non-negative floats order like integers, so fmax and vmax share a single collective."""
+    dist = _dist(group)
+    if dist is None:
+        return block
+    dist.all_reduce(block[:max_from], op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(block[max_from:], op=dist.ReduceOp.MAX, group=group)
+    return block
+
+
+def fold_block(total, snapshot, max_from, group=None):
+    """One batch into the running totals: the snapshot (this rank's accumulator block since the previous snapshot)
+    is combined over the ranks in place, then total[:max_from] += it and total[max_from:] = max(., it)."""
     import torch
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    combine_block(snapshot, max_from, group)
+    total[:max_from].add_(snapshot[:max_from])
+    torch.maximum(total[max_from:], snapshot[max_from:], out=total[max_from:])
+    return total
+
+
+def gather_hits(records, group=None, dst=None, counts=None):
+    """Variable-length per-rank records ([n_r, C] tensor) -> [sum n_r, C] in rank order, UNPADDED: the counts are
+    exchanged once (one small all-gather and one host read), then every rank's rows travel exactly once into their
+    slice of the result.  dst=None: every rank receives the whole; dst=r: only rank r does (the viewer's rank),
+    the others return None.  `counts` (list of ints) skips the exchange when the caller already knows them."""
+    import torch
+    dist = _dist(group)
+    if dist is None:
         return records
-    world = dist.get_world_size(group)
-    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
-    counts_t = torch.empty(world, dtype=torch.int64, device=records.device)
-    dist.all_gather_into_tensor(counts_t, n, group=group)
-    counts = counts_t.tolist()                                  # the one host synchronisation of the gather
-    m = max(counts) if counts else 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    records = records.contiguous()
+    if counts is None:
+        n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+        counts_t = torch.empty(world, dtype=torch.int64, device=records.device)
+        dist.all_gather_into_tensor(counts_t, n, group=group)
+        counts = counts_t.tolist()                              # the one host synchronisation of the gather
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     tail = tuple(records.shape[1:])
-    if records.shape[0] == m:
-        pad = records.contiguous()
-    else:
-        pad = torch.zeros((m,) + tail, dtype=records.dtype, device=records.device)
-        pad[:records.shape[0]] = records
-    buf = torch.empty((world * m,) + tail, dtype=records.dtype, device=records.device)
-    dist.all_gather_into_tensor(buf, pad, group=group)          # one flat collective, no per-rank staging copies
-    if all(c == m for c in counts):
-        return buf
-    return torch.cat([buf[r * m:r * m + c] for r, c in enumerate(counts)], dim=0)
+    if dst is None:
+        out = torch.empty((int(offs[-1]),) + tail, dtype=records.dtype, device=records.device)
+        return gather_slices(out, [(int(offs[r]), int(offs[r + 1])) for r in range(world)], group=group, mine=records)
+    if rank != dst:
+        if counts[rank]:
+            dist.send(records, _global_rank(dist, group, dst), group=group)
+        return None
+    out = torch.empty((int(offs[-1]),) + tail, dtype=records.dtype, device=records.device)
+    ops = []
+    for r in range(world):
+        if r == rank:
+            out[offs[r]:offs[r + 1]].copy_(records)
+        elif counts[r]:
+            ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], _global_rank(dist, group, r), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
+
+
+def gather_slices(full, ranges, group=None, mine=None):
+    """`full`: a tensor every rank holds at full length; rank r owns rows ranges[r] = (lo, hi) of it (already filled,
+    or given as `mine`).  After the call every rank holds every slice: one broadcast per non-empty slice, in place."""
+    dist = _dist(group)
+    if dist is None:
+        if mine is not None:
+            full[ranges[0][0]:ranges[0][1]].copy_(mine)
+        return full
+    rank = dist.get_rank(group)
+    if mine is not None:
+        full[ranges[rank][0]:ranges[rank][1]].copy_(mine)
+    for r, (lo, hi) in enumerate(ranges):
+        if hi > lo:
+            dist.broadcast(full[lo:hi], _global_rank(dist, group, r), group=group)
+    return full
 
 
 class _DevView:
@@ -68,8 +136,72 @@ class _DevView:
                                          "version": 2, "strides": None}
 
 
+class BatchCombiner:
+    """Per-batch combination of the accumulators without touching the live ones.
+
+    submit(): on the compute stream the per-vertex maxima are brought up to date, the whole accumulator block
+    (hist | fmax | vmax, ONE allocation) is copied into a staging buffer and -- by default -- zeroed for the next
+    batch; a side stream then all-reduces the snapshot (one SUM, one MAX) and folds it into the running totals
+    (hist += , fmax/vmax = max).  The next batch's kernels run meanwhile.  result() waits for the side stream and
+    returns the totals over every submitted batch and every rank.  Because only snapshots (deltas) are reduced, a
+    histogram accumulated over several batches counts every hit exactly once.
+    """
+
+    def __init__(self, ctx: Context, group=None):
+        import torch
+        self.ctx, self.group = ctx, group
+        self.dev = torch.device(f"cuda:{ctx.device}")
+        base, h_off, f_off, v_off, nbytes = ctx.accum_layout()
+        self.words, self.max_from = nbytes // 4, f_off // 4
+        self.f_off, self.v_off = f_off // 4, v_off // 4
+        self.live = torch.as_tensor(_DevView(base, self.words, "<i4"), device=self.dev)
+        self.stage = [torch.empty(self.words, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        self.total = torch.zeros(self.words, dtype=torch.int32, device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.ev_snap = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.busy = [False, False]
+        self.k = 0
+
+    def reset_totals(self, stream=None):
+        import torch
+        stream = stream or torch.cuda.current_stream(self.dev)
+        stream.wait_stream(self.side)
+        with torch.cuda.stream(stream):
+            self.total.zero_()
+
+    def submit(self, stream=None, reset=True):
+        import torch
+        stream = stream or torch.cuda.current_stream(self.dev)
+        k = self.k
+        self.k ^= 1
+        if self.busy[k]:
+            stream.wait_event(self.ev_done[k])              # the staging buffer's previous reduction has finished
+        self.ctx.accum_flush(stream)                        # vmax derived from fmax (one small kernel)
+        with torch.cuda.stream(stream):
+            self.stage[k].copy_(self.live)
+            if reset:
+                self.live.zero_()
+            self.ev_snap[k].record(stream)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_snap[k])
+            fold_block(self.total, self.stage[k], self.max_from, self.group)
+            self.ev_done[k].record(self.side)
+        self.busy[k] = True
+        return self
+
+    def result(self, stream=None):
+        """(hist int32 [nF], fmax float32 [nF], vmax float32 [nV]) totals; the caller's stream waits for the side stream."""
+        import torch
+        stream = stream or torch.cuda.current_stream(self.dev)
+        stream.wait_stream(self.side)
+        nF, nV = self.ctx.nF, self.ctx.nV
+        t = self.total
+        return (t[:nF], t[self.f_off:self.f_off + nF].view(torch.float32), t[self.v_off:self.v_off + nV].view(torch.float32))
+
+
 class Projector:
-    """Mesh + BVH on this process's GPU, frames of a batch sharded over the process group."""
+    """Mesh + BVH on this process's GPU; frames of a batch, or the rays of one frame, sharded over the process group."""
 
     def __init__(self, V, F, device=None, group=None):
         import torch
@@ -85,9 +217,10 @@ class Projector:
         self.ctx.set_mesh(V, F)
         self.ctx.build_bvh()          # deterministic: every rank builds the identical BVH
         self.nV, self.nF = self.ctx.nV, self.ctx.nF
+        self.combiner = BatchCombiner(self.ctx, group)
 
     def accumulators(self):
-        """Torch views (no copy) of hist int32 [nF], fmax float32 [nF], vmax float32 [nV]."""
+        """Torch views (no copy) of THIS rank's live hist int32 [nF], fmax float32 [nF], vmax float32 [nV]."""
         import torch
         self.ctx.accum_flush(torch.cuda.current_stream(self.device))
         h, f, v = self.ctx.accum_device_ptrs()
@@ -96,14 +229,21 @@ class Projector:
                 torch.as_tensor(_DevView(f, max(self.nF, 1), "<f4"), device=dev)[:self.nF],
                 torch.as_tensor(_DevView(v, max(self.nV, 1), "<f4"), device=dev)[:self.nV])
 
+    def combined(self):
+        """(hist, fmax, vmax) over every batch submitted since the last reset and over all ranks."""
+        return self.combiner.result()
+
     def project_batch(self, heat, K, poses, thr=0.5, mode="object", out=None, reduce=True, reset=True):
         """heat: CUDA tensor [B_local,H,W] holding THIS rank's frames (see shard_range);
         poses: [B_local,4,4] model->camera.  mode 'object' = one launch for the whole batch,
         'camera' = per-frame dp_pose_mesh (refit) + launch, the reference-literal arithmetic.
-        Returns (n_rays, n_hits) of this rank after synchronising."""
+        reduce: the batch's accumulators are snapshotted, zeroed and combined over the ranks into the running
+        totals (`combined()`), asynchronously; reset: the totals start from zero with this batch (False: they keep
+        accumulating -- every hit is still counted once).  Returns (n_rays, n_hits) of this rank."""
         import torch
         if reset:
             self.ctx.accum_reset(torch.cuda.current_stream())
+            self.combiner.reset_totals()
         K = np.asarray(K, np.float64).reshape(-1, 9)
         poses = np.asarray(poses, np.float64).reshape(-1, 4, 4)
         if mode == "object":
@@ -116,9 +256,43 @@ class Projector:
                 a, c = self.ctx.project_device(heat[b:b + 1], kb, None, thr, "camera", True, out=None, sync=True)
                 n += a
                 h += c
-        if reduce and self.world > 1:
-            combine_accumulators(*self.accumulators(), group=self.group)
+        if reduce:
+            self.combiner.submit(reset=True)
         return n, h
+
+    def project_frame_sharded(self, heat, K, pose, thr=0.5, out=None, gather=True, reduce=True, reset=True):
+        """ONE frame, its compacted ray list split over the ranks (the reference casts the frame's rays in
+        one call, /root/reference/src/defect_projection.py:247-256).  Every rank holds the same `heat` [H,W] (CUDA) and
+        pose, compacts the whole frame and traces block `rank` of `world`.  `out`: full-length per-ray CUDA tensors
+        ('t_hit', 'face', 'point', ...); with gather=True every rank ends up with every rank's slice (row-major order,
+        bit-identical to the 1-GPU arrays).  Returns (n_rays of the frame, n_hits of the frame, (lo, hi) of this rank)."""
+        import torch
+        ctx = self.ctx
+        if reset:
+            ctx.accum_reset(torch.cuda.current_stream())
+            self.combiner.reset_totals()
+        if heat.dim() == 2:
+            heat = heat[None]
+        H, W = heat.shape[-2:]
+        ctx.set_ray_shard(self.rank, self.world)
+        try:
+            n, h = ctx.project_device(heat, K, np.asarray(pose, np.float64).reshape(1, 4, 4), thr, "object", True, out=out,
+                                      sync=True)
+        finally:
+            ctx.set_ray_shard(0, 1)
+        ranges = [Context.shard_slots(r, self.world, n, H, W) for r in range(self.world)]
+        dist = _dist(self.group)
+        if dist is not None:
+            cnt = torch.tensor([h], dtype=torch.int64, device=heat.device)
+            dist.all_reduce(cnt, group=self.group)
+            if gather and out:
+                for k, t in out.items():
+                    if k not in ("counts", "pixel", "intensity"):      # the selection is replicated: only results travel
+                        gather_slices(t, ranges, group=self.group)
+            h = int(cnt.item())
+        if reduce:
+            self.combiner.submit(reset=True)
+        return n, h, ranges[self.rank]
 
 
 class FrameStream:

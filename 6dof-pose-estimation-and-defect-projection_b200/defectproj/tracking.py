@@ -35,7 +35,7 @@ class DefectTracker:
         self.threshold = heatmap_threshold
         self.intersection_pcds = []
         self.previous_transformation = None
-        self.mesh_in_camera = None
+        self.mesh_in_camera = None            # the posed model in the DEPTH camera's frame (what update_dash_data gets)
         # the tracker's own context: its device accumulators are never reset, so the per-face histogram and the
         # per-face / per-vertex maxima persist across detections without leaving the GPU
         from .core import Context
@@ -85,8 +85,10 @@ class DefectTracker:
         pcd.face_ids, pcd.pixels = pk["face"], pk["pixel"].astype(np.int64)
         self.intersection_pcds.append(pcd)
         self.previous_transformation = cur
-        self.mesh_in_camera = _dp.TriangleMesh(ctx.posed_vertices(np.float64 if self.V.dtype == np.float64 else np.float32),
-                                               self.F)
+        # the mesh the viewer gets is the caller's target_mesh_copy: the model posed by inv(current) ONLY, i.e. in the
+        # DEPTH camera's frame -- the frame the clouds were just moved into (run.py:109-110 / :179-181 and :205);
+        # the colour-camera copy that was traced stays inside the context
+        self.mesh_in_camera = _dp.TriangleMesh(ctx.transform_points(np.asarray(self.V, dtype=np.float64), T_depth), self.F)
         return pcd
 
     def payload(self):

@@ -229,6 +229,31 @@ DP_API int dp_accum_get(dp_ctx *ctx, int32_t *hist, float *fmax, float *vmax, in
 DP_API int dp_accum_flush(dp_ctx *ctx, void *stream);
 /* device addresses of the accumulators, for in-place NCCL reductions by the host layer */
 DP_API int dp_accum_device_ptrs(dp_ctx *ctx, int32_t **hist, float **fmax, float **vmax);
+/* The three accumulators live in ONE allocation (hist | fmax | vmax, 256-byte aligned starts, the gaps stay zero):
+ * `base` + offsets, `bytes` in total.  A host layer snapshots the whole block with one copy and combines
+ * [fmax_off, bytes) of several devices with ONE max-reduction (non-negative floats order like their bits). */
+DP_API int dp_accum_layout(dp_ctx *ctx, void **base, int64_t *hist_off, int64_t *fmax_off, int64_t *vmax_off, int64_t *bytes);
+
+/* ---- multi-GPU: single-frame ray sharding and hit records ------------------------------------
+ * The reference casts one frame's rays in one call (/root/reference/src/defect_projection.py:247-256); with the mesh
+ * and BVH replicated per GPU, that call splits by rays.  After dp_set_ray_shard(rank, world) every dp_project of this
+ * context still compacts the whole frame (the ray list and its order are global) but generates, traces and accumulates
+ * only block `rank` of `world` of the compacted list: a contiguous range of output slots [lo, hi) -- whole 4-row bands
+ * when the dense frame is walked in 8x4 tiles -- which dp_shard_slots returns for any (rank, world) and a frame of n_rays selected pixels.
+ * n_rays of dp_project stays the frame's total, n_hits counts the shard.  Slots outside the range are not written.
+ * Concatenating the ranks' ranges gives the 1-GPU arrays bit for bit; summing / maxing their accumulators likewise.
+ * (0, 1) restores whole frames. */
+DP_API int dp_set_ray_shard(dp_ctx *ctx, int rank, int world);
+DP_API int dp_shard_slots(int rank, int world, int64_t n_rays, int64_t nframes, int H, int W, int64_t *lo, int64_t *hi);
+/* Compacted hit records of the rays [first, first + n) of a projection's per-ray outputs (device memory): the rays with
+ * face >= 0, in ray order, as rows of 3 uint32 (pixel, t_hit bits, face) or -- when `point` (float32 [.,3]) is given --
+ * 6 uint32 (+ x, y, z bits): the unit a rank contributes to the hit gather, and the viewer's input
+ * (/root/reference/src/defect_projection.py:259-264 keeps exactly these rays).  pixel may be NULL (the ray index is
+ * stored).  *m receives the count (the call then synchronises); m_async (device or pinned host memory) receives it
+ * asynchronously on the stream.  DP_DEVICE only. */
+DP_API int dp_pack_records(dp_ctx *ctx, const uint32_t *pixel, const float *t_hit, const int32_t *face, const float *point,
+                           int64_t n, int64_t first, uint32_t *records, int64_t cap, int64_t *m, int64_t *m_async, int mem,
+                           void *stream);
 
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* enable != 0: the next traversal launches use the counting variant of the kernel */

@@ -310,11 +310,17 @@ def heatmap_to_point3d(heat, depth, K, thr=0.1):
     K = np.asarray(K, np.float64)
     H, W = heat.shape
     Hd, Wd = depth.shape
-    maxv = np.max(heat).astype(np.float64) if heat.size else np.float64(1.0)
     h = min(H, Hd)
     w = min(W, Wd)
     with np.errstate(divide="ignore", invalid="ignore"):
-        inten = heat[:h, :w].astype(np.float64) / maxv
+        if heat.dtype == np.float32:
+            # :384 on a float32 map is a float32 division; its rounded quotient is compared with the (float64) threshold
+            # the way numpy 1.26.4 compares an np.float32 scalar with a Python float -- in float64 -- and stored widened
+            maxv = np.max(heat) if heat.size else np.float32(1.0)
+            inten = (heat[:h, :w] / maxv).astype(np.float64)
+        else:
+            maxv = np.max(heat).astype(np.float64) if heat.size else np.float64(1.0)
+            inten = heat[:h, :w].astype(np.float64) / maxv
     d = depth[:h, :w]
     ys, xs = np.nonzero((inten > thr) & (d > 0))
     dd = d[ys, xs].astype(np.float64)

@@ -129,6 +129,14 @@ def main():
     dep["d_heat"], dep["d_depth"], dep["d_K"] = heat, depth, Kd
     for thr, tag in ((0.1, "010"), (0.5, "050")):
         dep[f"d_point3d_{tag}"] = ref["heatmap_to_point3d"](heat, depth, intr_d, threshold=thr)
+    # a float32 map: the quotient heatmap[y, x] / max_value is a float32 division (:384) whose float32-rounded value lands
+    # in column 3.  The threshold comparison np.float32 > python float is float64 under the reference's numpy 1.26.4 and
+    # float32 under numpy >= 2 (NEP 50); the fixture must not depend on that, so no quotient may sit between the two
+    heat32 = heat.astype(np.float32)
+    q32 = heat32 / np.max(heat32)
+    for thr, tag in ((0.1, "010"), (0.5, "050")):
+        assert not ((q32.astype(np.float64) > thr) ^ (q32 > np.float32(thr))).any()
+        dep[f"d_point3d_f32_{tag}"] = ref["heatmap_to_point3d"](heat32, depth, intr_d, threshold=thr)
     small_depth = depth[:50, :70]                                               # depth image smaller than the heatmap
     dep["d_point3d_small"] = ref["heatmap_to_point3d"](heat, small_depth, intr_d, threshold=0.3)
     picks = [(int(x), int(y)) for x, y in zip(rng.integers(0, Ww, 40), rng.integers(0, Hh, 40))]

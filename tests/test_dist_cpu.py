@@ -24,7 +24,7 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     from defectproj import synth
-    from defectproj.projector import combine_accumulators, gather_hits, shard_range
+    from defectproj.projector import combine_accumulators, fold_block, gather_hits, gather_slices, shard_range
     from oracle import oracle as orc
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -51,6 +51,11 @@ def _worker(rank, world, port, q):
             rec = np.concatenate(recs) if recs else np.zeros((0, 3))
             return orc.accumulate(f_all, I_all, F, len(V)), rec
 
+        def frames_one(b):
+            heat = synth.blob_heatmap((H, W), seed=b)
+            xs, ys, I = orc.heatmap_to_points(heat, 0.4)
+            return bvh.cast_f32(orc.rays_object_frame(xs, ys, orc.frame_xform(K, poses[b])))
+
         lo, hi = shard_range(B, world, rank)
         (h, fm, vm), rec = frames(lo, hi)
         h, fm, vm = torch.from_numpy(h), torch.from_numpy(fm), torch.from_numpy(vm)
@@ -59,6 +64,35 @@ def _worker(rank, world, port, q):
         (h1, f1, v1), rec1 = frames(0, B)
         ok = (np.array_equal(h.numpy(), h1) and np.array_equal(fm.numpy(), f1) and np.array_equal(vm.numpy(), v1)
               and np.array_equal(allrec.numpy(), rec1) and int(h1.sum()) == len(rec1) > 100)
+        # the records to one rank only (the viewer's), unpadded; an empty contribution from the other rank
+        only0 = gather_hits(torch.from_numpy(rec), dst=0)
+        ok = ok and ((only0 is None) if rank != 0 else np.array_equal(only0.numpy(), rec1))
+        part = torch.from_numpy(rec if rank == 0 else rec[:0])
+        both = gather_hits(part)
+        ok = ok and both.shape[0] == (len(rec) if rank == 0 else both.shape[0]) and both.shape[1] == 3
+
+        # two batches, accumulated: every rank snapshots its block per batch (hist | fmax bits | vmax bits, the layout of
+        # dp_accum_layout) and folds the combined snapshot into the totals -- each hit counted once (reducing
+        # the live accumulators in place counted earlier batches `world` times)
+        nF, nV = len(F), len(V)
+        total = torch.zeros(2 * nF + nV, dtype=torch.int32)
+        for b_lo, b_hi in ((0, 2), (2, B)):
+            lo2, hi2 = shard_range(b_hi - b_lo, world, rank)
+            (hb, fb, vb), _ = frames(b_lo + lo2, b_lo + hi2)
+            snap = torch.from_numpy(np.concatenate([hb, fb.view(np.int32), vb.view(np.int32)]))
+            fold_block(total, snap, nF)
+        tn = total.numpy()
+        ok = ok and (np.array_equal(tn[:nF], h1) and np.array_equal(tn[nF:2 * nF].view(np.float32), f1)
+                     and np.array_equal(tn[2 * nF:].view(np.float32), v1))
+
+        # single-frame ray sharding: each rank owns a slice of the frame's per-ray results, gathered in place
+        full_t, full_f = frames_one(0)
+        n = len(full_f)
+        ranges = [shard_range(n, world, r) for r in range(world)]
+        mine_f = torch.full((n,), -7, dtype=torch.int32)
+        mine_f[ranges[rank][0]:ranges[rank][1]] = torch.from_numpy(full_f[ranges[rank][0]:ranges[rank][1]])
+        gather_slices(mine_f, ranges)
+        ok = ok and np.array_equal(mine_f.numpy(), full_f)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -456,6 +456,10 @@ def test_error_behaviour(built_lib):
         bad[3, 1] = len(V)
         with pytest.raises(ValueError, match="out of range"):
             c.set_mesh(V, bad)
+        import torch
+        with pytest.raises(ValueError, match="out of range"):              # device-resident meshes are checked too
+            c.set_mesh(torch.from_numpy(V).cuda(), torch.from_numpy(bad).cuda())
+        c.set_mesh(torch.from_numpy(V).cuda(), torch.from_numpy(F).cuda()).build_bvh()
         with pytest.raises(ValueError):
             c.pose_mesh(np.ones((4, 4)))
     with pytest.raises(ValueError, match="out of range"):
@@ -700,6 +704,9 @@ def test_depth_projection_path_matches_reference(built_lib, orc):
     for thr, key in ((0.1, "d_point3d_010"), (0.5, "d_point3d_050")):
         assert np.array_equal(dpj.heatmap_to_point3d(heat, depth, K, threshold=thr), g[key])
     assert np.array_equal(dpj.heatmap_to_point3d(heat, depth[:50, :70], K, threshold=0.3), g["d_point3d_small"])
+    # float32 map: the reference divides in float32 and stores the rounded quotient (fixture from its own function)
+    for thr, key in ((0.1, "d_point3d_f32_010"), (0.5, "d_point3d_f32_050")):
+        assert np.array_equal(dpj.heatmap_to_point3d(heat.astype(np.float32), depth, K, threshold=thr), g[key])
     assert np.array_equal(dpj.heatmap_to_point3d(heat.astype(np.float32), depth, K, threshold=0.5),
                           orc.heatmap_to_point3d(heat.astype(np.float32), depth, K, 0.5))
     assert dpj.heatmap_to_point3d(np.zeros((8, 8)) + 1e-3, np.zeros((8, 8), np.uint16), K).shape == (0,)

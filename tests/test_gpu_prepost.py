@@ -269,3 +269,14 @@ def test_defect_tracker_follows_the_run_loop(ctx, orc):
     assert np.array_equal(trk.hist, hist_total)
     p = trk.payload()
     assert len(p["pcds"]) == 3 and p["face_hits"].sum() == sum(len(c) for c in ref_clouds)
+    # the payload's mesh is the model posed by inv(current) only -- the depth camera's frame, the frame of the clouds
+    # (run.py:179-181, :205) -- so the newest cloud's points lie ON the payload mesh: each in the plane and inside the
+    # triangle of its face
+    Vd = V @ np.linalg.inv(prev)[:3, :3].T + np.linalg.inv(prev)[:3, 3]
+    assert np.allclose(p["vertices"], Vd, rtol=0, atol=1e-9)
+    last = trk.intersection_pcds[-1]
+    tri = p["vertices"][F[last.face_ids]]                                   # [m, 3, 3]
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    dist = np.abs(np.einsum("ij,ij->i", last.points - tri[:, 0], nrm))
+    assert dist.max() < 1e-3                                                # mm; float32 t_hit at ~600 mm

@@ -122,6 +122,11 @@ def test_depth_path_oracle_vs_reference(orc, depth_golden):
     for thr, key in ((0.1, "d_point3d_010"), (0.5, "d_point3d_050")):
         assert np.array_equal(orc.heatmap_to_point3d(g["d_heat"], g["d_depth"], g["d_K"], thr), g[key])
     assert np.array_equal(orc.heatmap_to_point3d(g["d_heat"], g["d_depth"][:50, :70], g["d_K"], 0.3), g["d_point3d_small"])
+    # float32 map: float32 division, the rounded quotient in column 3 (fixture made by the reference's own function)
+    for thr, key in ((0.1, "d_point3d_f32_010"), (0.5, "d_point3d_f32_050")):
+        got = orc.heatmap_to_point3d(g["d_heat"].astype(np.float32), g["d_depth"], g["d_K"], thr)
+        assert np.array_equal(got, g[key])
+    assert not np.array_equal(g["d_point3d_f32_050"][:, 3], g["d_point3d_050"][:, 3])      # the float32 quotients differ
     offs, ali, idx = orc.align_to_surface(g["d_proj_point3d"], g["d_target_points"], g["d_target_normals"], 0.5)
     assert np.array_equal(offs, g["d_proj_offset"]) and np.array_equal(ali, g["d_proj_aligned"])
     offs, ali, _ = orc.align_to_surface(g["d_point3d_050"], g["d_target_points"], g["d_target_normals"], 0.1)
