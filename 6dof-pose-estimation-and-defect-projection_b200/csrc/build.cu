@@ -15,6 +15,7 @@
 // bytes, child and triangle bases, parent links) is shared, only boxes and triangle records are recomputed.
 #include "dp_internal.cuh"
 
+
 #include <math.h>
 
 #include <algorithm>
@@ -496,19 +497,41 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
 // MODE 0: selection and emission fused (small levels: one launch, lowest latency)
 // MODE 1: selection only, ONE THREAD per node, result to `sel` (large levels: all lanes busy with the serial walk)
 // MODE 2: emission only, eight lanes per node, selection read from `sel`
+struct CollapseArgs {
+    long long n;
+    const int32_t *left, *right, *first, *last;
+    const float *blo, *bhi;
+    const uint32_t *sorted_tri;
+    int32_t *wroot;
+    WideNode *nodes;
+    int32_t *tri_face;
+    unsigned *counters;
+    const float *ctab;
+    float c_prim;
+    int greedy_mode;
+    int32_t *wparent;
+    int dp_max_count;
+    int32_t *sel;
+    long long cap_nodes;
+};
+
+// one wide node `w` of the level that starts at `begin`; MODE 1: called by ONE thread (gl = 0), else by the eight lanes
+// gl = 0..7 of an aligned group
 template <int MODE>
-__global__ void __launch_bounds__(256)
-k_collapse(long long n, long long begin, long long end, const int32_t *__restrict__ left,
-                           const int32_t *__restrict__ right, const int32_t *__restrict__ first,
-                           const int32_t *__restrict__ last, const float *__restrict__ blo,
-                           const float *__restrict__ bhi, const uint32_t *__restrict__ sorted_tri, int32_t *wroot,
-                           WideNode *nodes, int32_t *tri_face, unsigned *counters, const float *__restrict__ ctab,
-                           float c_prim, int greedy_mode, int32_t *wparent, int dp_max_count, int32_t *sel, long long cap_nodes)
+__device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w, long long begin, int gl)
 {
-    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long w = begin + (MODE == 1 ? gt : (gt >> 3));
-    if (w >= end) return;                                   // whole groups leave together
-    const int gl = MODE == 1 ? 0 : (int)(gt & 7), lane32 = threadIdx.x & 31;
+    const long long n = A.n;
+    const int32_t *__restrict__ left = A.left, *__restrict__ right = A.right, *__restrict__ first = A.first,
+                  *__restrict__ last = A.last;
+    const float *__restrict__ blo = A.blo, *__restrict__ bhi = A.bhi, *__restrict__ ctab = A.ctab;
+    const uint32_t *__restrict__ sorted_tri = A.sorted_tri;
+    int32_t *wroot = A.wroot, *tri_face = A.tri_face, *wparent = A.wparent, *sel = A.sel;
+    WideNode *nodes = A.nodes;
+    unsigned *counters = A.counters;
+    const float c_prim = A.c_prim;
+    const int greedy_mode = A.greedy_mode, dp_max_count = A.dp_max_count;
+    const long long cap_nodes = A.cap_nodes;
+    const int lane32 = threadIdx.x & 31;
     const unsigned gmask = 0xffu << (lane32 & 24);
     const int gbase = lane32 & 24;
     const int32_t r = wroot[w];
@@ -725,6 +748,83 @@ k_collapse(long long n, long long begin, long long end, const int32_t *__restric
         nodes[w].w[0] = make_uint4(0u, 0u, 0u, ibit << 24);
         nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
     }
+}
+
+// one level per launch (the host reads the node counter back between levels): kept for A/B (DP_COLLAPSE_LAUNCHES=1)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_collapse(CollapseArgs A, long long begin, long long end)
+{
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long w = begin + (MODE == 1 ? gt : (gt >> 3));
+    if (w >= end) return;                                   // whole groups leave together
+    collapse_node<MODE>(A, w, begin, MODE == 1 ? 0 : (int)(gt & 7));
+}
+
+// The whole top-down collapse in ONE cooperative launch: the grid walks the levels itself, a grid-wide barrier where the
+// per-level version went back to the host (one stream synchronisation + an 8-byte read-back per level: ~25 us each,
+// 9-10 levels).  Small levels: eight lanes per node, selection and emission fused; levels of >= 2048 nodes: selection
+// with one thread per node, barrier, emission with eight lanes per node (as the per-level launches did).
+struct CollapseResult {
+    long long n_nodes;
+    int n_levels;              // -1: deeper than 126 levels; -2: node capacity exceeded (n_nodes = the demand)
+    int pad_;
+    long long level_begin[128];
+    unsigned bar_count, bar_phase;   // grid barrier (zeroed with the struct before the launch)
+    long long published;             // node counter as read by the LAST block to arrive at a barrier
+};
+
+// Grid-wide barrier of a cooperative launch (all blocks resident).  The last block to arrive reads the node counter --
+// every allocation of the level is complete, none of the next has started -- and publishes it before releasing the
+// others; the fence of the released thread invalidates its SM's L1, so that plain loads after the barrier see the
+// other blocks' stores (wroot, sel).
+__device__ __forceinline__ long long grid_barrier_publish(CollapseResult *res, const unsigned *counter, unsigned &phase)
+{
+    __shared__ long long s_pub;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ++phase;
+        const unsigned arrived = atomicAdd(&res->bar_count, 1u) + 1u;
+        if (arrived == phase * gridDim.x) {
+            res->published = (long long)__ldcg(counter);
+            __threadfence();
+            atomicExch(&res->bar_phase, phase);
+        } else {
+            while (*reinterpret_cast<volatile unsigned *>(&res->bar_phase) < phase) __nanosleep(32);
+        }
+        __threadfence();
+        s_pub = *reinterpret_cast<volatile long long *>(&res->published);
+    }
+    __syncthreads();
+    return s_pub;
+}
+
+__global__ void __launch_bounds__(256) k_collapse_all(CollapseArgs A, CollapseResult *res)
+{
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    long long begin = 0, end = 1;
+    int L = 0;
+    unsigned phase = 0;
+    if (gt == 0) res->level_begin[0] = 0;
+    while (begin < end) {
+        if (L + 1 >= 127) { if (gt == 0) { res->n_levels = -1; res->n_nodes = end; } return; }
+        const long long lvl = end - begin;
+        if (lvl < 2048) {
+            for (long long g = gt >> 3; g < lvl; g += nthreads >> 3) collapse_node<0>(A, begin + g, begin, (int)(gt & 7));
+        } else {
+            for (long long t = gt; t < lvl; t += nthreads) collapse_node<1>(A, begin + t, begin, 0);
+            grid_barrier_publish(res, A.counters, phase);
+            for (long long g = gt >> 3; g < lvl; g += nthreads >> 3) collapse_node<2>(A, begin + g, begin, (int)(gt & 7));
+        }
+        const long long next_end = grid_barrier_publish(res, A.counters, phase);
+        ++L;
+        if (gt == 0) res->level_begin[L] = end;
+        begin = end;
+        end = next_end;
+        if (end > A.cap_nodes) { if (gt == 0) { res->n_levels = -2; res->n_nodes = end; } return; }
+    }
+    if (gt == 0) { res->n_levels = L; res->n_nodes = end; }
 }
 
 // Fit of one wide node by EIGHT lanes, one per child slot: exact node box into wlo/whi, quantised child boxes into
@@ -980,6 +1080,13 @@ cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp,
 // the triangle/node cost ratio of the surface-area model; DP_HYBRID_COUNT is the largest subtree (in triangles) whose
 // cut is taken from the cost tables (0 = every subtree) -- above it the greedy expansion keeps the top of the tree
 // balanced and shallow, which is what the lock-step packets pay for.
+// DP_COLLAPSE_LAUNCHES=1: one launch + host read-back per level instead of the single cooperative launch (read per
+// build: tests flip it)
+static int knob_collapse_launches()
+{
+    const char *e = getenv("DP_COLLAPSE_LAUNCHES");
+    return e ? atoi(e) : 0;
+}
 static int knob_sah_collapse()
 {
     static int v = -1;
@@ -1037,13 +1144,14 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     cudaError_t e;
     const long long n = nF;
     const size_t N = (size_t)(n > 0 ? n : 1);
-    size_t need = 4096 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
+    size_t need = 4096 + sizeof(CollapseResult) + 256 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
                   (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + (9 * (N / 2 + 64) * 4 + 256) + 1024;
     if ((e = ensure_scratch(scratch, scratch_bytes, need)) != cudaSuccess) return e;
     Bump b{static_cast<char *>(*scratch)};
     unsigned *bounds_u = b.take<unsigned>(8);
     float *sbounds = b.take<float>(8);
     unsigned *counters = b.take<unsigned>(4);
+    CollapseResult *cres = b.take<CollapseResult>(1);
     uint32_t *keys = b.take<uint32_t>(N), *vals = b.take<uint32_t>(N);
     uint32_t *keys_t = b.take<uint32_t>(N), *vals_t = b.take<uint32_t>(N);
     uint32_t *table = b.take<uint32_t>(radix_table_entries(n));
@@ -1111,30 +1219,52 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         if ((e = cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(wroot, &root_id, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     }
+    CollapseArgs ca{n, left, right, first, last, blo, bhi, vals, wroot, out.nodes, topo.tri_face, counters, ctab, c_prim,
+                    knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes};
     long long begin = 0, end = 1;
     int L = 0;
-    while (begin < end) {
-        if (L + 1 >= 127) { topo.n_levels = -1; return cudaSuccess; }      // deeper than any ray stack: reported by the caller
-        const long long lvl = end - begin;
-        if (lvl < 2048 || lvl > (long long)(N / 2 + 64)) {
-            k_collapse<0><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
-                                                               out.nodes, topo.tri_face, counters, ctab, c_prim,
-                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes);
-        } else {
-            k_collapse<1><<<blocks_for(lvl, 128), 128, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
-                                                               out.nodes, topo.tri_face, counters, ctab, c_prim,
-                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes);
-            k_collapse<2><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(n, begin, end, left, right, first, last, blo, bhi, vals, wroot,
-                                                               out.nodes, topo.tri_face, counters, ctab, c_prim,
-                                                               knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes);
+    if (knob_collapse_launches() == 0) {
+        // one cooperative launch walks all levels (grid barriers instead of host round trips), one read-back at the end
+        static int coop_grid = 0;
+        if (coop_grid == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_all, 256, 0)) != cudaSuccess) return e;
+            coop_grid = sms * (per_sm > 0 ? per_sm : 1);
         }
-        unsigned cnt[2];
-        if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(cres, 0, sizeof(CollapseResult), s)) != cudaSuccess) return e;
+        void *kargs[] = {&ca, &cres};
+        if ((e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_collapse_all), dim3(coop_grid), dim3(256), kargs, 0, s)) !=
+            cudaSuccess)
+            return e;
+        CollapseResult hres;
+        if ((e = cudaMemcpyAsync(&hres, cres, sizeof(CollapseResult), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-        topo.level_begin[++L] = end;
-        begin = end;
-        end = cnt[0];
-        if (end > out.cap_nodes) return cudaErrorMemoryAllocation;
+        if (hres.n_levels == -1) { topo.n_levels = -1; return cudaSuccess; }      // deeper than any ray stack
+        if (hres.n_levels == -2) return cudaErrorMemoryAllocation;               // the caller retries with more nodes
+        L = hres.n_levels;
+        end = hres.n_nodes;
+        for (int l = 0; l <= L; ++l) topo.level_begin[l] = hres.level_begin[l];
+        topo.level_begin[L] = end;
+    } else {
+        while (begin < end) {
+            if (L + 1 >= 127) { topo.n_levels = -1; return cudaSuccess; }      // deeper than any ray stack: reported by the caller
+            const long long lvl = end - begin;
+            if (lvl < 2048 || lvl > (long long)(N / 2 + 64)) {
+                k_collapse<0><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(ca, begin, end);
+            } else {
+                k_collapse<1><<<blocks_for(lvl, 128), 128, 0, s>>>(ca, begin, end);
+                k_collapse<2><<<blocks_for(lvl * 8, 256), 256, 0, s>>>(ca, begin, end);
+            }
+            unsigned cnt[2];
+            if ((e = cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+            topo.level_begin[++L] = end;
+            begin = end;
+            end = cnt[0];
+            if (end > out.cap_nodes) return cudaErrorMemoryAllocation;
+        }
     }
     topo.n_levels = L;
     out.n_nodes = end;

@@ -296,8 +296,11 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
     return true;
 }
 
+#ifndef DP_FAT_PREFETCH
+#define DP_FAT_PREFETCH 0
+#endif
 // Selection half for the uncompressed set: as node_select, without the prefetch (the set is L2-resident by construction).
-__device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2 *lstack)
+__device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2 *lstack, const uint4 *__restrict__ fat)
 {
     uint2 ng = r.ng;
     const unsigned hits = ng.y;
@@ -312,6 +315,12 @@ __device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2
         ++r.sp;
     }
     r.next = ng.x + __popc(hits & 0xffu & ((1u << slot) - 1u));
+#if DP_FAT_PREFETCH
+    // the node is fetched at the start of the next step, after this step's triangle work: pull its lines into L1 now
+    const char *np = reinterpret_cast<const char *>(fat + (size_t)r.next * FAT_QUADS);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 128));
+#endif
 }
 
 // Visit half for the uncompressed 208-byte node (dp_internal.cuh): thirteen 16-byte loads, per child six FMAs on the
@@ -364,7 +373,7 @@ __device__ __forceinline__ bool node_step_fat(RayState &r, const uint4 *__restri
         ng = (r.sp < STACK_SMEM) ? stack[r.sp * TR_THREADS] : lstack[r.sp - STACK_SMEM];
     }
     r.ng = ng;
-    node_select_fat(r, stack, lstack);
+    node_select_fat(r, stack, lstack, fat);
     return true;
 }
 
@@ -651,6 +660,12 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
 #ifndef DP_FAT_OCT
 #define DP_FAT_OCT 1
 #endif
+#ifndef DP_TQ_ATOMIC
+#define DP_TQ_ATOMIC 0
+#endif
+#ifndef DP_BEST_ASM
+#define DP_BEST_ASM 0
+#endif
 template <bool STATS, int SRC, int MINB, int FMT>
 __global__ void __launch_bounds__(TR_THREADS, MINB)
 k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
@@ -666,11 +681,17 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
     __shared__ unsigned s_queue[(TR_THREADS / 32) * TQ_CAP];
     __shared__ unsigned long long s_best[TR_THREADS];
+#if DP_TQ_ATOMIC
+    __shared__ unsigned s_qn[TR_THREADS / 32];
+#endif
     uint2 lstack[STACK_LOCAL];
     uint2 *stack = s_stack + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *queue = s_queue + warp * TQ_CAP;
     unsigned long long *best = s_best + warp * 32;
+#if DP_BEST_ASM
+    const unsigned best_sa = (unsigned)__cvta_generic_to_shared(&s_best[threadIdx.x]);
+#endif
     const unsigned lt = (1u << lane) - 1u;
     long long n = d_n ? *d_n : n_max;
     if (n > n_max) n = n_max;
@@ -738,7 +759,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
         }
         best[lane] = KEY_MISS;
-        if (alive) { if (FMT == 1) node_select_fat(r, stack, lstack); else node_select(r, nodes, stack, lstack, pf); }
+        if (alive) { if (FMT == 1) node_select_fat(r, stack, lstack, fat); else node_select(r, nodes, stack, lstack, pf); }
         __syncwarp();
         // the packet's octant, from the signs the slab test itself uses; -1 when its rays disagree
         int poct = -1;
@@ -755,7 +776,13 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         while (__any_sync(0xffffffffu, alive)) {
             unsigned tmask = 0, tbase = 0, tvalid = 0xffffffffu;
             if (alive) {
+#if DP_BEST_ASM
+                unsigned best_hi;
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(best_hi) : "r"(best_sa));
+                const float tlimit = __uint_as_float(best_hi) * T_SLACK;
+#else
                 const float tlimit = __uint_as_float((unsigned)(best[lane] >> 32)) * T_SLACK;
+#endif
                 if (FMT == 1) {
 #if DP_FAT_OCT
                     switch (poct) {
@@ -795,6 +822,16 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             // it then fills in a short private loop; the queue is tested 32 pairs at a time
             if (__any_sync(0xffffffffu, tmask != 0u)) {
                 const unsigned k = __popc(tmask);
+#if DP_TQ_ATOMIC
+                // queue slots from a per-warp shared counter (the order of the pairs in the queue is irrelevant: the
+                // results meet in an atomicMin) instead of a five-round warp prefix sum
+                if (lane == 0) s_qn[warp] = 0u;
+                __syncwarp();
+                unsigned inc = k;
+                if (k) inc += atomicAdd(&s_qn[warp], k);
+                __syncwarp();
+                const int total = (int)s_qn[warp];
+#else
                 unsigned inc = k;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -802,6 +839,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
                     if (lane >= d) inc += y;
                 }
                 const int total = (int)__shfl_sync(0xffffffffu, inc, 31);
+#endif
                 if (qcount + total > TQ_CAP) {
                     // does not fit behind what is pending (at most 31 pairs): test those first; a step never yields
                     // more than 32 x 24 pairs, and more than TQ_CAP only on pathological nodes -> chunked below

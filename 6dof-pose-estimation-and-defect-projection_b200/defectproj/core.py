@@ -16,6 +16,7 @@ from ._lib import (DP_DEVICE, DP_E_ARG, DP_E_NOMEM, DP_E_STATE, DP_F32, DP_F64, 
 __all__ = ["Context", "DefectProjError", "FRAME_OBJECT", "FRAME_CAMERA"]
 
 FRAME_OBJECT, FRAME_CAMERA = DP_FRAME_OBJECT, DP_FRAME_CAMERA
+_PINNED_KEEPALIVE = []
 
 
 class DefectProjError(RuntimeError):
@@ -154,6 +155,27 @@ class Context:
         self._check(self._L.dp_get_posed_vertices(self._h, _ptr(out), DP_F64 if dtype == np.float64 else DP_F32,
                                                   DP_HOST, self._stream(stream)))
         return out
+
+    def posed_vertices_device(self, dtype=np.float32, stream=None):
+        """The posed vertices as a CUDA tensor [nV,3] owned by the caller (a device-to-device copy: nothing crosses PCIe)."""
+        import torch
+        dtype = np.dtype(dtype)
+        tdt = torch.float64 if dtype == np.float64 else torch.float32
+        out = torch.empty((self.nV, 3), dtype=tdt, device=f"cuda:{self.device}")
+        if stream is None:
+            stream = torch.cuda.current_stream(out.device)
+        self._check(self._L.dp_get_posed_vertices(self._h, _ptr(out), DP_F64 if dtype == np.float64 else DP_F32, DP_DEVICE,
+                                                  self._stream(stream)))
+        return out
+
+    @staticmethod
+    def pinned_array(shape, dtype):
+        """A page-locked numpy array (host staging for inputs that arrive in pageable memory)."""
+        import torch
+        t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+        a = t.numpy()
+        _PINNED_KEEPALIVE.append(t)
+        return a
 
     # ------------------------------------------------------------------ H1
     def compact(self, heat, thr, want_intensity=True, stream=None):

@@ -199,6 +199,28 @@ def test_wide_bvh_structure(ctx, cfg):
     _check_structure(nodes2, tris2, Vp, F)
 
 
+@pytest.mark.parametrize("cfg", ["small", "c1_30k", "c2_500k"])
+def test_single_launch_collapse_equals_per_level_launches(ctx, orc, cfg, monkeypatch):
+    """The cooperative single-launch collapse (grid barriers) and the per-level launches (host read-back per level) build
+    the same wide tree: same node and level counts, valid structure, identical hits."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS[cfg], seed=5)
+    K, H, W = synth.camera_720p()
+    rays6 = _grid_rays(orc, K, H, W, synth.fixed_pose(), 6)
+    got = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DP_COLLAPSE_LAUNCHES", mode)
+        ctx.set_mesh(V, F).build_bvh()
+        st = ctx.stats()
+        if cfg != "c2_500k":
+            nodes, tris = ctx.dump_bvh("object")
+            _check_structure(nodes, tris, V, F)
+        t, f = ctx.cast_rays(rays6)
+        got.append((st["n_wide_nodes"], st["wide_depth"], t, f))
+    assert got[0][0] == got[1][0] and got[0][1] == got[1][1]
+    assert np.array_equal(got[0][3], got[1][3]) and np.array_equal(_bits(got[0][2]), _bits(got[1][2]))
+    assert (got[0][3] >= 0).sum() > 100
+
+
 def test_duplicate_morton_codes_and_degenerate_triangles(ctx, orc):
     # 3000 triangles crammed into a few Morton cells + zero-area triangles: Karras must still build a tree
     rng = np.random.default_rng(9)
