@@ -640,17 +640,29 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
     // t_hit is needed by the hit-point kernel even when the caller does not want it
     if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
-    CK(ctx->dir4.ensure((size_t)cap * 32 + 32), "dp_project: rays");
-    CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, ctx->dir4.as<float4>(), s, n_elems, ctx->shard),
-       "dp_project: ray generation");
+    // DP_FUSE_RAYS=0: separate ray-generation and hit-point kernels around the traversal (the round-1 sequence, kept for
+    // A/B); default: the traversal generates its rays from the compacted pixels and writes the hit points itself --
+    // two launches and the 32-byte ray records (write + read) less per frame
+    static const int fuse_default = 1;
+    const char *fuse_env = getenv("DP_FUSE_RAYS");
+    const bool fuse = fuse_env ? atoi(fuse_env) != 0 : fuse_default != 0;
+    float4 *d_dir4 = nullptr;
+    if (!fuse) {
+        CK(ctx->dir4.ensure((size_t)cap * 32 + 32), "dp_project: rays");
+        d_dir4 = ctx->dir4.as<float4>();
+        CK(launch_raygen(d_pixel, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_dir4, s, n_elems, ctx->shard),
+           "dp_project: ray generation");
+    }
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[7], s), "dp_project");
-    CK(launch_trace_pixels(view_of(b), ctx->dir4.as<float4>(), d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
+    CK(launch_trace_pixels(view_of(b), d_dir4, d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
-                           d_counts + 1, st, ord_prev, ord_next, s, true, ctx->shard),
+                           d_counts + 1, st, ord_prev, ord_next, s, true, ctx->shard, d_pixel, nframes, fuse ? d_pt : nullptr,
+                           fuse ? d_p64 : nullptr),
        "dp_project: traversal");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
-    CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s, n_elems, ctx->shard),
-       "dp_project: hit points");
+    if (!fuse)
+        CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s, n_elems, ctx->shard),
+           "dp_project: hit points");
     if (out && out->counts) {
         // device memory: plain store; pinned host memory: zero-copy store through its device alias
         if (out->counts != ctx->counts_alias_src) {

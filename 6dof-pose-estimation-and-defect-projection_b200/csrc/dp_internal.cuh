@@ -161,7 +161,9 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
-                                bool counter_zeroed = false, RayShard shard = RayShard());
+                                bool counter_zeroed = false, RayShard shard = RayShard(), const uint32_t *pixel = nullptr,
+                                int64_t n_xf = 0, float *point = nullptr, double *point64 = nullptr);
+// dir4 == nullptr: the traversal generates the rays itself from pixel[] / xf[] and writes the hit points (point, point64)
 // per-vertex maxima from the per-face maxima (run when the accumulators are read, not per hit)
 cudaError_t launch_vertex_max(const uint32_t *fmax, const int32_t *F, int64_t nF, uint32_t *vmax, cudaStream_t s);
 cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n, const FrameXf &xf, double *rays3,

@@ -296,11 +296,8 @@ __device__ __forceinline__ bool node_step(RayState &r, const WideNode *__restric
     return true;
 }
 
-#ifndef DP_FAT_PREFETCH
-#define DP_FAT_PREFETCH 0
-#endif
 // Selection half for the uncompressed set: as node_select, without the prefetch (the set is L2-resident by construction).
-__device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2 *lstack, const uint4 *__restrict__ fat)
+__device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2 *lstack)
 {
     uint2 ng = r.ng;
     const unsigned hits = ng.y;
@@ -315,12 +312,6 @@ __device__ __forceinline__ void node_select_fat(RayState &r, uint2 *stack, uint2
         ++r.sp;
     }
     r.next = ng.x + __popc(hits & 0xffu & ((1u << slot) - 1u));
-#if DP_FAT_PREFETCH
-    // the node is fetched at the start of the next step, after this step's triangle work: pull its lines into L1 now
-    const char *np = reinterpret_cast<const char *>(fat + (size_t)r.next * FAT_QUADS);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 128));
-#endif
 }
 
 // Visit half for the uncompressed 208-byte node (dp_internal.cuh): thirteen 16-byte loads, per child six FMAs on the
@@ -373,7 +364,7 @@ __device__ __forceinline__ bool node_step_fat(RayState &r, const uint4 *__restri
         ng = (r.sp < STACK_SMEM) ? stack[r.sp * TR_THREADS] : lstack[r.sp - STACK_SMEM];
     }
     r.ng = ng;
-    node_select_fat(r, stack, lstack, fat);
+    node_select_fat(r, stack, lstack);
     return true;
 }
 
@@ -460,6 +451,56 @@ constexpr int NR_STACK = 64;                          // stack entries per ray (
                                                       // 16-23 % faster than packets at 35k-110k rays, 30-35 % at 9k-16k)
 #endif
 
+__device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
+                                              uint32_t &fr, double &dcx, double &dcy, double &dcz)
+{
+    const uint32_t hw = (uint32_t)H * (uint32_t)W;
+    fr = pix / hw;
+    const uint32_t rem = pix - fr * hw;
+    const uint32_t y = rem / (uint32_t)W;
+    const uint32_t x = rem - y * (uint32_t)W;
+    if ((long long)fr >= n_xf) fr = 0;
+    const double *c = xf[fr].v;
+    const double xn = __ddiv_rn(__dsub_rn((double)x, c[2]), c[0]);
+    const double yn = __ddiv_rn(__dsub_rn((double)y, c[3]), c[1]);
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xn, xn), __dmul_rn(yn, yn)), 1.0));
+    dcx = __ddiv_rn(xn, nrm);
+    dcy = __ddiv_rn(yn, nrm);
+    dcz = __ddiv_rn(1.0, nrm);
+}
+
+// The float32 object-frame ray of a compacted pixel (what k_raygen writes to dir4) and its float64 camera-frame unit
+// direction (what k_points multiplies by t), computed in place by the traversal when rays are generated in-kernel:
+// same operations in the same order, bit-identical results, no 32-byte ray record through HBM.
+__device__ __forceinline__ void pixel_ray_object(uint32_t pix, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
+                                                 float &ox, float &oy, float &oz, float &dx, float &dy, float &dz,
+                                                 double &dcx, double &dcy, double &dcz)
+{
+    uint32_t fr;
+    pixel_ray_f64(pix, H, W, xf, n_xf, fr, dcx, dcy, dcz);
+    const double *Ri = xf[fr].v + 4;
+    dx = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[0], dcx), __dmul_rn(Ri[1], dcy)), __dmul_rn(Ri[2], dcz));
+    dy = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[3], dcx), __dmul_rn(Ri[4], dcy)), __dmul_rn(Ri[5], dcz));
+    dz = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[6], dcx), __dmul_rn(Ri[7], dcy)), __dmul_rn(Ri[8], dcz));
+    const double *ti = xf[fr].v + 13;
+    ox = (float)ti[0]; oy = (float)ti[1]; oz = (float)ti[2];
+}
+
+// hit point p = d_cam (float64) * t (float32), NaN on a miss  (:261-263 with origin 0; as k_points)
+__device__ __forceinline__ void store_point(long long i, bool hit, float tf, double dcx, double dcy, double dcz,
+                                            float *__restrict__ point, double *__restrict__ point64)
+{
+    double px, py, pz;
+    if (hit) {
+        const double t = (double)tf;
+        px = __dmul_rn(dcx, t); py = __dmul_rn(dcy, t); pz = __dmul_rn(dcz, t);
+    } else {
+        px = py = pz = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    if (point64) { point64[3 * i] = px; point64[3 * i + 1] = py; point64[3 * i + 2] = pz; }
+    if (point) { point[3 * i] = (float)px; point[3 * i + 1] = (float)py; point[3 * i + 2] = (float)pz; }
+}
+
 // ------------------------------------------------------------------------------------------
 // Single-frame ray sharding: with `world` > 1 a launch traces only rank `rank`'s contiguous block of
 // the compacted ray list, in units of 32-ray packets -- whole tile rows (4 image rows) when the dense frame is walked in
@@ -500,7 +541,8 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
              const float4 *__restrict__ dir4, const float *__restrict__ intensity, long long n,
              float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
              unsigned long long *work_counter, long long *d_hits, TraceStats *stats, uint2 *s_stack, long long s_lo,
-             long long s_hi)
+             long long s_hi, const uint32_t *__restrict__ pixel, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
+             float *__restrict__ point, double *__restrict__ point64)
 {
     const int lane = threadIdx.x & 31, c = lane & 7, g = lane >> 3;
     const unsigned gmask = 0xffu << (8 * g);
@@ -519,11 +561,22 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
         const bool valid = i < n;
         bool alive = valid;
         RayState r;
+        double dcx = 0.0, dcy = 0.0, dcz = 0.0;                       // camera-frame direction (lane c == 0, in-kernel rays)
         {
             float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
             if (valid) {
-                const float4 o4 = __ldg(dir4 + 2 * i), d = __ldg(dir4 + 2 * i + 1);
-                ox = o4.x; oy = o4.y; oz = o4.z; dx = d.x; dy = d.y; dz = d.z;
+                if (dir4) {
+                    const float4 o4 = __ldg(dir4 + 2 * i), d = __ldg(dir4 + 2 * i + 1);
+                    ox = o4.x; oy = o4.y; oz = o4.z; dx = d.x; dy = d.y; dz = d.z;
+                } else {
+                    // in-kernel ray generation: lane 0 of the ray's eight computes, the others receive
+                    if (c == 0) pixel_ray_object(pixel[i], H, W, xf, n_xf, ox, oy, oz, dx, dy, dz, dcx, dcy, dcz);
+                }
+            }
+            if (!dir4) {
+                const int src = lane & 24;
+                ox = __shfl_sync(0xffffffffu, ox, src); oy = __shfl_sync(0xffffffffu, oy, src); oz = __shfl_sync(0xffffffffu, oz, src);
+                dx = __shfl_sync(0xffffffffu, dx, src); dy = __shfl_sync(0xffffffffu, dy, src); dz = __shfl_sync(0xffffffffu, dz, src);
             }
             ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
         }
@@ -616,6 +669,7 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
         if (valid && c == 0) {
             if (t_hit) t_hit[i] = tb;
             if (face) face[i] = bf;
+            if (!dir4 && (point || point64)) store_point(i, bf >= 0, tb, dcx, dcy, dcz, point, point64);
             if (STATS) { ++nray; nn += steps_nodes; if (stats->ray_nodes) stats->ray_nodes[i] = steps_nodes; }
             if (bf >= 0) {
                 ++nhit;
@@ -660,12 +714,7 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
 #ifndef DP_FAT_OCT
 #define DP_FAT_OCT 1
 #endif
-#ifndef DP_TQ_ATOMIC
-#define DP_TQ_ATOMIC 0
-#endif
-#ifndef DP_BEST_ASM
-#define DP_BEST_ASM 0
-#endif
+
 template <bool STATS, int SRC, int MINB, int FMT>
 __global__ void __launch_bounds__(TR_THREADS, MINB)
 k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const TriRec *__restrict__ tris, const float *__restrict__ d_scale,
@@ -674,24 +723,22 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         const FrameXf *__restrict__ xf, float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
         unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
         const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch, int narrow_enabled, int shard_rank,
-        int shard_world)
+        int shard_world, const uint32_t *__restrict__ pixel, long long n_xf, float *__restrict__ point,
+        double *__restrict__ point64)
 {
+    // dir4 == nullptr (SRC 0): rays are generated here from pixel[] and xf[], hit points written here (no k_raygen / k_points)
     // (the learnt packet lists hold packets of the previous launch over the same shard: dp_set_ray_shard drops them)
     const bool pf = prefetch != 0;
     __shared__ uint2 s_stack[STACK_SMEM * TR_THREADS];
     __shared__ unsigned s_queue[(TR_THREADS / 32) * TQ_CAP];
     __shared__ unsigned long long s_best[TR_THREADS];
-#if DP_TQ_ATOMIC
-    __shared__ unsigned s_qn[TR_THREADS / 32];
-#endif
+    __shared__ double s_dcam[SRC == 0 ? 3 * TR_THREADS : 1];     // camera-frame directions of the packet (in-kernel rays)
+    const bool want_pts = SRC == 0 && dir4 == nullptr && (point != nullptr || point64 != nullptr);
     uint2 lstack[STACK_LOCAL];
     uint2 *stack = s_stack + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *queue = s_queue + warp * TQ_CAP;
     unsigned long long *best = s_best + warp * 32;
-#if DP_BEST_ASM
-    const unsigned best_sa = (unsigned)__cvta_generic_to_shared(&s_best[threadIdx.x]);
-#endif
     const unsigned lt = (1u << lane) - 1u;
     long long n = d_n ? *d_n : n_max;
     if (n > n_max) n = n_max;
@@ -700,7 +747,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         // sparse frame: eight lanes per ray (work items come from the second counter)
         static_assert(STACK_SMEM * TR_THREADS >= (NR_THREADS / 8) * NR_STACK, "the narrow path borrows the packet stack");
         trace_narrow<STATS>(nodes, tris, d_scale, dir4, intensity, n, t_hit, face, acc, has_acc, work_counter + 1, d_hits, stats,
-                            s_stack, sh.s_lo, sh.s_hi);
+                            s_stack, sh.s_lo, sh.s_hi, pixel, H, W, xf, n_xf, point, point64);
         return;
     }
     const bool tiled = sh.tiled;
@@ -745,10 +792,16 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             if (valid) {
                 slot = work_to_slot(i, tiled, W);
                 if (SRC == 0) {
-                    // 32 bytes per ray written by k_raygen: origin (object frame) | direction
-                    const float4 o4 = __ldg(dir4 + 2 * slot), d = __ldg(dir4 + 2 * slot + 1);
-                    ox = o4.x; oy = o4.y; oz = o4.z;
-                    dx = d.x; dy = d.y; dz = d.z;
+                    if (dir4) {
+                        // 32 bytes per ray written by k_raygen: origin (object frame) | direction
+                        const float4 o4 = __ldg(dir4 + 2 * slot), d = __ldg(dir4 + 2 * slot + 1);
+                        ox = o4.x; oy = o4.y; oz = o4.z;
+                        dx = d.x; dy = d.y; dz = d.z;
+                    } else {
+                        double dcx, dcy, dcz;
+                        pixel_ray_object(pixel[slot], H, W, xf, n_xf, ox, oy, oz, dx, dy, dz, dcx, dcy, dcz);
+                        if (want_pts) { s_dcam[threadIdx.x] = dcx; s_dcam[TR_THREADS + threadIdx.x] = dcy; s_dcam[2 * TR_THREADS + threadIdx.x] = dcz; }
+                    }
                     if (has_acc && intensity) prefetch_l1(intensity + slot, true);   // read by the packet epilogue
                 } else {
                     const float *q = rays6 + 6 * slot;
@@ -759,7 +812,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             ray_setup(r, ox, oy, oz, dx, dy, dz, scale);
         }
         best[lane] = KEY_MISS;
-        if (alive) { if (FMT == 1) node_select_fat(r, stack, lstack, fat); else node_select(r, nodes, stack, lstack, pf); }
+        if (alive) { if (FMT == 1) node_select_fat(r, stack, lstack); else node_select(r, nodes, stack, lstack, pf); }
         __syncwarp();
         // the packet's octant, from the signs the slab test itself uses; -1 when its rays disagree
         int poct = -1;
@@ -776,13 +829,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         while (__any_sync(0xffffffffu, alive)) {
             unsigned tmask = 0, tbase = 0, tvalid = 0xffffffffu;
             if (alive) {
-#if DP_BEST_ASM
-                unsigned best_hi;
-                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(best_hi) : "r"(best_sa));
-                const float tlimit = __uint_as_float(best_hi) * T_SLACK;
-#else
                 const float tlimit = __uint_as_float((unsigned)(best[lane] >> 32)) * T_SLACK;
-#endif
                 if (FMT == 1) {
 #if DP_FAT_OCT
                     switch (poct) {
@@ -822,16 +869,6 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             // it then fills in a short private loop; the queue is tested 32 pairs at a time
             if (__any_sync(0xffffffffu, tmask != 0u)) {
                 const unsigned k = __popc(tmask);
-#if DP_TQ_ATOMIC
-                // queue slots from a per-warp shared counter (the order of the pairs in the queue is irrelevant: the
-                // results meet in an atomicMin) instead of a five-round warp prefix sum
-                if (lane == 0) s_qn[warp] = 0u;
-                __syncwarp();
-                unsigned inc = k;
-                if (k) inc += atomicAdd(&s_qn[warp], k);
-                __syncwarp();
-                const int total = (int)s_qn[warp];
-#else
                 unsigned inc = k;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -839,7 +876,6 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
                     if (lane >= d) inc += y;
                 }
                 const int total = (int)__shfl_sync(0xffffffffu, inc, 31);
-#endif
                 if (qcount + total > TQ_CAP) {
                     // does not fit behind what is pending (at most 31 pairs): test those first; a step never yields
                     // more than 32 x 24 pairs, and more than TQ_CAP only on pathological nodes -> chunked below
@@ -910,6 +946,9 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             if (t_hit) t_hit[slot] = tb;
             if (face) face[slot] = bf;
             if (STATS && stats->ray_nodes) stats->ray_nodes[slot] = nn - nn_start;
+            if (want_pts)
+                store_point(slot, bf >= 0, tb, s_dcam[threadIdx.x], s_dcam[TR_THREADS + threadIdx.x], s_dcam[2 * TR_THREADS + threadIdx.x],
+                            point, point64);
         }
         const bool hit = valid && bf >= 0;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
@@ -958,24 +997,6 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
 // rotation in float64 and the float32 cast of :251.  One thread per compacted pixel; dir4.w carries
 // the frame index.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
-                                              uint32_t &fr, double &dcx, double &dcy, double &dcz)
-{
-    const uint32_t hw = (uint32_t)H * (uint32_t)W;
-    fr = pix / hw;
-    const uint32_t rem = pix - fr * hw;
-    const uint32_t y = rem / (uint32_t)W;
-    const uint32_t x = rem - y * (uint32_t)W;
-    if ((long long)fr >= n_xf) fr = 0;
-    const double *c = xf[fr].v;
-    const double xn = __ddiv_rn(__dsub_rn((double)x, c[2]), c[0]);
-    const double yn = __ddiv_rn(__dsub_rn((double)y, c[3]), c[1]);
-    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xn, xn), __dmul_rn(yn, yn)), 1.0));
-    dcx = __ddiv_rn(xn, nrm);
-    dcy = __ddiv_rn(yn, nrm);
-    dcz = __ddiv_rn(1.0, nrm);
-}
-
 __global__ void __launch_bounds__(256)
 k_raygen(const uint32_t *__restrict__ pixel, const long long *__restrict__ d_n, long long n_max, int H, int W,
          const FrameXf *__restrict__ xf, long long n_xf, float4 *__restrict__ dir4, long long total_px, int allow_tiled,
@@ -1167,7 +1188,8 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 int64_t n_max, int64_t total_px, int H, int W, const FrameXf *xf, float *t_hit,
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
-                                bool counter_zeroed, RayShard shard)
+                                bool counter_zeroed, RayShard shard, const uint32_t *pixel, int64_t n_xf, float *point,
+                                double *point64)
 {
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
@@ -1185,7 +1207,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     k_trace<ST, 0, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, \
                                                         n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, \
                                                         d_hits, stats, knob_tiled(), ord_prev, ord_next, pf, narrow, shard.rank, \
-                                                        shard.world)
+                                                        shard.world, pixel, (long long)n_xf, point, point64)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG, 0);
@@ -1215,7 +1237,7 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
 #define DP_LAUNCH_TRACE1(ST, MB, FMT)                                                                                          \
     k_trace<ST, 1, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, \
                                                         n, 0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, \
-                                                        nullptr, nullptr, pf, 0, 0, 1)
+                                                        nullptr, nullptr, pf, 0, 0, 1, nullptr, 0, nullptr, nullptr)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG, 0);

@@ -697,8 +697,9 @@ def run_ours(args):
                                "counts; pixel u32 is the identity for a dense frame (synthesised on the host, not copied); "
                                "heatmap f32 in; pinned host memory",
                     "modes": {k: e2e_entry(k) for k in keys}},
-            "gpu_launches": 5 * args.steps + 3 * nb_batches,   # k_project_prologue, k_compact, k_raygen, k_trace, k_points per
-                                                               # frame; k_pack_records, k_vertex_max + the snapshot copy per batch
+            # k_project_prologue, k_compact, k_trace per frame (rays and hit points are generated inside k_trace; with
+            # DP_FUSE_RAYS=0 also k_raygen and k_points); k_pack_records, k_vertex_max + the snapshot copy per batch
+            "gpu_launches": (3 if os.environ.get("DP_FUSE_RAYS", "1") != "0" else 5) * args.steps + 3 * nb_batches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
                          "kernel": "k_trace<false,0,%d,%d>" % ((6, 1) if nb == B_NODE_FAT else (7, 0)), "kernel_ms": k_ms,

@@ -445,6 +445,49 @@ def test_project_batch_of_frames_single_launch(ctx, orc):
     assert np.array_equal(hist, h0) and np.array_equal(fmax, f0) and np.array_equal(vmax, v0)
 
 
+@pytest.mark.parametrize("kind", ["dense", "sparse", "batch", "camera"])
+def test_in_kernel_rays_and_points_equal_the_separate_kernels(ctx, kind, monkeypatch):
+    """dp_project generates the rays and writes the hit points inside the traversal kernel (default); DP_FUSE_RAYS=0 runs
+    the separate k_raygen / k_points kernels around it.  Same operations in the same order: every output bit-identical,
+    for the packet traversal (dense), the eight-lanes-per-ray traversal (sparse), a batch of frames and the camera frame;
+    both node sets."""
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0, scale=6.0)
+    pose = synth.fill_frame_pose()
+    ctx.set_mesh(V.astype(np.float64), F).build_bvh()
+    H, W = 384, 512
+    K = synth.K_matrix(126.0, 126.0, W / 2, H / 2)
+    if kind == "dense":
+        heat, poses, frame = np.ones((H, W), np.float32), pose[None], "object"
+    elif kind == "sparse":
+        heat, poses, frame = synth.blob_heatmap((H, W), seed=9), pose[None], "object"
+    elif kind == "batch":
+        heat = np.stack([synth.blob_heatmap((H, W), seed=20 + i, dtype=np.float64) for i in range(3)])
+        poses, frame = np.stack([pose, pose @ synth._pose(synth.rot_z(7.0), [3.0, 1.0, -2.0]), pose]), "object"
+    else:
+        heat, poses, frame = np.ones((H, W), np.float32), None, "camera"
+        ctx.pose_mesh(pose)
+    want = ("pixel", "intensity", "t_hit", "face", "point", "point64")
+    got = {}
+    for fat in ("1", "0"):
+        monkeypatch.setenv("DP_FAT", fat)
+        for fuse in ("1", "0"):
+            monkeypatch.setenv("DP_FUSE_RAYS", fuse)
+            ctx.accum_reset()
+            r = ctx.project(heat, K, poses, 0.5, frame, True, want=want)
+            r["acc"] = ctx.accum_get()
+            got[(fat, fuse)] = r
+    ref = got[("1", "0")]
+    assert ref["hits"] > 1000
+    for key, r in got.items():
+        assert r["n"] == ref["n"] and r["hits"] == ref["hits"], key
+        for k in want:
+            a, b = r[k], ref[k]
+            assert np.array_equal(a.view(np.uint32 if a.dtype.itemsize == 4 else np.uint64),
+                                  b.view(np.uint32 if b.dtype.itemsize == 4 else np.uint64)), (key, k)
+        for a, b in zip(r["acc"], ref["acc"]):
+            assert np.array_equal(a, b), key
+
+
 def test_project_empty_selection_and_miss_all(ctx):
     V, F = synth.param_mesh(*synth.MESH_CONFIGS["tiny"], seed=0)
     K, H, W = synth.camera_720p()

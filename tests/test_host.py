@@ -157,8 +157,10 @@ def test_normals_facade_rejects_what_it_does_not_implement_before_touching_the_g
 
 
 def test_scene_cache_decides_between_skip_refit_and_rebuild(monkeypatch):
-    """ray_tracing's scene cache: the same arrays -> nothing; the same faces at new vertex positions (what
-    run.py:109-110 hands over on every capture) -> dp_update_vertices; anything else -> set_mesh + build."""
+    """ray_tracing's scene cache: the previous call's arrays again (same buffers, sampled rows unchanged) -> nothing; the
+    same faces with a vertex array in another buffer (what run.py:109-110 hands over on every capture: a fresh copy of
+    the model at the current pose) -> dp_update_vertices without a host-side comparison of 12 MB; anything else ->
+    set_mesh + build."""
     from defectproj import defect_projection as dpj
 
     class Fake:
@@ -184,11 +186,15 @@ def test_scene_cache_decides_between_skip_refit_and_rebuild(monkeypatch):
     V = V.astype(np.float64)
     dpj._scene(V, F)
     assert fake.calls == ["set_mesh", "build"]
-    dpj._scene(V.copy(), F.copy())
-    assert fake.calls == ["set_mesh", "build"]                       # equal contents: nothing to do
+    dpj._scene(V, F)
+    assert fake.calls == ["set_mesh", "build"]                       # the same arrays: nothing to do
+    dpj._scene(V, F.copy())
+    assert fake.calls == ["set_mesh", "build"]                       # an equal index array in a new buffer is compared in full
     V2 = V + 1.0
     dpj._scene(V2, F)
-    assert fake.calls[-1] == "update" and len(fake.calls) == 3
+    assert fake.calls[-1] == "update" and len(fake.calls) == 3       # another vertex buffer: uploaded and refitted, unread
+    dpj._scene(V2, F)
+    assert len(fake.calls) == 3
     V2[0, 0] += 1.0                                                  # the caller's array mutated in place is seen
     dpj._scene(V2, F)
     assert fake.calls[-1] == "update" and len(fake.calls) == 4
