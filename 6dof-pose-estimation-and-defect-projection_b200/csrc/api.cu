@@ -621,8 +621,23 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     CK(launch_project_prologue(ctx->cscratch.as<unsigned long long>(), n_elems, d_counts, ord_next, ctx->xf.as<FrameXf>(),
                                hxf.data(), nframes, s),
        "dp_project: prologue");
+    // out->counts in pinned host memory: the ray count is stored there by the compaction itself (early), both counts at
+    // the end of the call
+    long long *early_n = nullptr;
+    if (out && out->counts) {
+        if (out->counts != ctx->counts_alias_src) {
+            cudaPointerAttributes at{};
+            ctx->counts_alias = nullptr;
+            if (cudaPointerGetAttributes(&at, out->counts) == cudaSuccess && at.devicePointer)
+                ctx->counts_alias = static_cast<long long *>(at.devicePointer);
+            else
+                cudaGetLastError();
+            ctx->counts_alias_src = out->counts;
+        }
+        early_n = ctx->counts_alias;
+    }
     CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
-                      ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s, true),
+                      ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s, true, early_n),
        "dp_project: compaction");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[1], s), "dp_project");
 
@@ -665,15 +680,6 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
            "dp_project: hit points");
     if (out && out->counts) {
         // device memory: plain store; pinned host memory: zero-copy store through its device alias
-        if (out->counts != ctx->counts_alias_src) {
-            cudaPointerAttributes at{};
-            ctx->counts_alias = nullptr;
-            if (cudaPointerGetAttributes(&at, out->counts) == cudaSuccess && at.devicePointer)
-                ctx->counts_alias = static_cast<long long *>(at.devicePointer);
-            else
-                cudaGetLastError();
-            ctx->counts_alias_src = out->counts;
-        }
         if (ctx->counts_alias) CK(launch_publish_counts(d_counts, ctx->counts_alias, s), "dp_project: counts");
         else CK(cudaMemcpyAsync(out->counts, d_counts, 16, cudaMemcpyDefault, s), "dp_project: counts");
     }

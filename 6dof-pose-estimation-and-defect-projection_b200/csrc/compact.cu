@@ -40,7 +40,7 @@ __device__ __forceinline__ void load4(const double *p, Vec4<double> &o)
 template <typename T>
 __global__ void __launch_bounds__(CT_THREADS)
 k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
-          float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *d_count,
+          float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *d_count, long long *early_n,
           int aligned)
 {
     __shared__ unsigned s_tile;
@@ -103,7 +103,12 @@ k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__
         const unsigned long long prefix = lookback_exclusive_prefix(state, tile, total, lane);
         if (lane == 0) {
             s_base = (long long)prefix;
-            if (tile_base + CT_TILE >= n) *d_count = (long long)(prefix + total);   // last tile
+            if (tile_base + CT_TILE >= n) {                                        // last tile
+                *d_count = (long long)(prefix + total);
+                // the ray count as soon as it exists (mapped pinned-host memory): a caller that shards the frame's rays over
+                // several GPUs sizes its gather while the traversal still runs
+                if (early_n) *reinterpret_cast<volatile long long *>(early_n) = (long long)(prefix + total);
+            }
         }
     }
     __syncthreads();
@@ -228,7 +233,8 @@ size_t compact_scratch_bytes(int64_t n_elems)
 
 cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t frame_elems, double thr,
                            uint32_t *pixel, float *intensity, int64_t cap, unsigned long long *scratch,
-                           long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s, bool scratch_zeroed)
+                           long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s, bool scratch_zeroed,
+                           long long *early_n)
 {
     cudaError_t e;
     if (n_elems <= 0) {
@@ -242,11 +248,11 @@ cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t
     const int aligned = ((uintptr_t)heat % 16) == 0;
     if (dtype == 1) {
         k_compact<double><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const double *>(heat), n_elems, thr,
-                                                                   pixel, intensity, cap, scratch, d_count, aligned);
+                                                                   pixel, intensity, cap, scratch, d_count, early_n, aligned);
     } else {
         k_compact<float><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const float *>(heat), n_elems,
                                                                   (float)thr, pixel, intensity, cap, scratch,
-                                                                  d_count, aligned);
+                                                                  d_count, early_n, aligned);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (d_frame_count && nframes > 0) {

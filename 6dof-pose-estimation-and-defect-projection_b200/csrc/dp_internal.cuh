@@ -135,7 +135,7 @@ size_t compact_scratch_bytes(int64_t n_elems);
 cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t frame_elems, double thr,
                            uint32_t *pixel, float *intensity, int64_t cap, unsigned long long *scratch,
                            long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s,
-                           bool scratch_zeroed = false);
+                           bool scratch_zeroed = false, long long *early_n = nullptr);
 // dp_project's resets and uploads as kernel launches (no copy-engine work in the kernel stream): zeroes the
 // compaction scratch, counts[0..2] (rays, hits, traversal work counter), resets `ord_next`, writes the per-frame
 // constants.  launch_publish_counts stores counts[0..1] to a device or mapped pinned-host address.

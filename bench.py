@@ -420,30 +420,47 @@ def strong_scaling(mesh, rank, world, local, steps, flush):
     out = dict(t_hit=torch.empty(n_pix, device=dev), face=torch.empty(n_pix, dtype=torch.int32, device=dev))
     poses = [frame_pose(i) for i in range(steps + 3)]            # the SAME frame on every rank
     for i in range(3):
-        proj.project_frame_sharded(heat, K, poses[i], THR, out=out)
-        proj.combined()
+        proj.project_frame_sharded(heat, K, poses[i], THR, out=out, reduce=False, reset=False)
+    proj.combiner.submit()
+    proj.combined()
+    proj.combiner.reset_totals()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = []
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hits_local = 0
     for i in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        n, h, rng = proj.project_frame_sharded(heat, K, poses[3 + i], THR, out=out)
-        hist = proj.combined()[0]
+        n, h, rng = proj.project_frame_sharded(heat, K, poses[3 + i], THR, out=out, reduce=False, reset=False)
         e1.record(stream)
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
-    t = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device=dev)
+        hits_local += int(h)
+    # the accumulators are combined ONCE for the batch of frames (not per frame)
+    e_all0.record(stream)
+    proj.combiner.submit()
+    hist = proj.combined()[0]
+    e_all1.record(stream)
+    torch.cuda.synchronize()
+    combine_ms = e_all0.elapsed_time(e_all1)
+    t = torch.tensor([float(np.mean(ms)) + combine_ms / steps, combine_ms], dtype=torch.float64, device=dev)
+    hl = torch.tensor([hits_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ok = int(hist.sum().item()) == h == int((out["face"][:n] >= 0).sum().item())
+        dist.all_reduce(hl)
+    h = int(hl[0]) // steps
+    ok = int(hist.sum().item()) == int(hl[0]) and h == int((out["face"][:n] >= 0).sum().item())
     proj.ctx.close()
     return {"triangles": len(F), "rays_per_frame": n, "hits": h, "ms_per_frame": float(t[0]), "mrays_s": n / float(t[0]) / 1e3,
+            "combine_ms_per_batch": float(t[1]), "frames": steps,
             "slots_of_rank0": list(rng) if rank == 0 else None, "hist_total_equals_hits_equals_gathered_faces": bool(ok),
-            "timed": "blocking call per frame (counts read back), incl. the gather of every rank's t_hit/face slices to all "
-                     "ranks and the accumulator combine; L2 flushed before each frame outside the events; max over ranks"}
+            "timed": "blocking call per frame (the ray count is read back), incl. ONE all-gather per result array (t_hit, "
+                     "face) that leaves every rank with the whole frame; the accumulator block is combined once for the "
+                     "batch of frames (its time / frames is added); L2 flushed before each frame outside the events; max "
+                     "over ranks"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -543,6 +560,8 @@ def run_ours(args):
     trace_ms = []
     for b in range(nb_batches):
         for i in range(bounds[b], bounds[b + 1]):
+            if b > 0 and i == min(bounds[b] + 3, bounds[b + 1] - 1):
+                batch_gather(b - 1)          # queued behind batch b-1's reductions on the side stream: overlaps this batch
             flush.zero_()
             sampled = i % 16 == 15 or i == args.steps - 1
             if sampled:
@@ -557,8 +576,6 @@ def run_ours(args):
                 # kernel-only duration of the traversal launch of this step
                 trace_ms.append(ctx.last_timings()["trace_ms"])
                 ctx.set_timing(False)
-        if b > 0:
-            batch_gather(b - 1)              # overlaps with this batch's frames
     batch_gather(nb_batches - 1)
     stream.wait_stream(comb.side)            # the last batch's reductions and gather are exposed
     ev_tail.record(stream)

@@ -69,13 +69,17 @@ typedef struct dp_rays_out {
     double *point64;   /* [cap*3] the same in float64: d (float64) * t (float32), as :261-263 */
     int64_t cap;       /* capacity in rays of every non-NULL array above                     */
     int64_t *counts;   /* optional [2], device or PINNED host memory: receives (n_rays, n_hits) by
-                          an asynchronous copy on the call's stream (for pipelined callers)       */
+                          an asynchronous store on the call's stream (for pipelined callers).  In
+                          pinned host memory counts[0] is ALSO stored by the compaction kernel as
+                          soon as the ray count exists, long before the traversal ends: a caller
+                          that set counts[0] = -1 can poll it and size follow-up work (the slice
+                          gather of a ray-sharded frame) while the traversal still runs           */
 } dp_rays_out;
 
 typedef struct dp_stats {
     int64_t rays;           /* rays traced by the last counted launch                        */
     int64_t hits;
-    int64_t nodes_fetched;  /* 80-byte wide nodes fetched (sum over rays)                    */
+    int64_t nodes_fetched;  /* wide nodes fetched, 80 or 208 bytes each (sum over rays)      */
     int64_t tris_tested;    /* 48-byte triangle records fetched (sum over rays)              */
     int64_t n_wide_nodes;   /* BVH size                                                      */
     int64_t n_tris;

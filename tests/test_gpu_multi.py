@@ -150,3 +150,29 @@ def test_batch_combiner_counts_every_hit_once(ctx):
     assert ctx.accum_get()[0].sum() == 0
     comb.reset_totals()
     assert int(comb.result()[0].sum()) == 0
+
+
+def test_sharded_frame_api_on_one_rank_and_the_early_ray_count(built_lib):
+    """Projector.project_frame_sharded without a process group (world 1): the ray count is read from pinned memory as soon
+    as the compaction kernel has stored it, nothing waits for the traversal, results equal the plain projection."""
+    import torch
+    from defectproj import Projector
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0, scale=6.0)
+    pose = synth.fill_frame_pose()
+    H, W = 384, 512
+    K = synth.K_matrix(126.0, 126.0, W / 2, H / 2)
+    proj = Projector(V, F, device=0)
+    try:
+        for heat in (torch.ones((H, W), device="cuda"), torch.from_numpy(synth.blob_heatmap((H, W), seed=3)).cuda(),
+                     torch.zeros((H, W), device="cuda")):
+            out = _outs(H * W)
+            n, h, (lo, hi) = proj.project_frame_sharded(heat, K, pose, 0.5, out={"t_hit": out["t_hit"], "face": out["face"]})
+            ref = _outs(H * W)
+            proj.ctx.accum_reset()
+            n0, h0 = proj.ctx.project_device(heat[None], K, pose[None], 0.5, "object", True, out=ref, sync=True)
+            assert (n, int(h), lo, hi) == (n0, h0, 0, n0)
+            assert torch.equal(out["face"][:n], ref["face"][:n])
+            assert torch.equal(out["t_hit"][:n].view(torch.int32), ref["t_hit"][:n].view(torch.int32))
+            assert int(proj.combined()[0].sum()) == h0
+    finally:
+        proj.ctx.close()
