@@ -294,7 +294,8 @@ class Projector:
             self.combiner.submit(reset=True)
         return n, h
 
-    def project_frame_sharded(self, heat, K, pose, thr=0.5, out=None, gather="all", reduce=True, reset=True):
+    def project_frame_sharded(self, heat, K, pose, thr=0.5, out=None, gather="all", reduce=True, reset=True,
+                              gather_stream=None):
         """ONE frame, its compacted ray list split over the ranks (the reference casts the frame's rays in
         one call, /root/reference/src/defect_projection.py:247-256).  Every rank holds the same `heat` [H,W] (CUDA) and
         pose, compacts the whole frame and traces block `rank` of `world`.  `out`: full-length per-ray CUDA tensors
@@ -304,7 +305,8 @@ class Projector:
         combined into the running totals (asynchronously; callers that project many frames pass reduce=False and call
         `combiner.submit()` once per batch).  Returns (n_rays of the frame, the hit count of THIS rank's shard -- an object
         whose int() waits for the frame --, (lo, hi) of this rank); the frame's hit total is the combined histogram's sum.
-        Nothing here waits for the traversal: the call returns with the gathers queued behind it."""
+        Nothing here waits for the traversal: the call returns with the gathers queued behind it -- on `gather_stream`
+        when given, so that a sequence of frames overlaps frame i's gathers with frame i+1's kernels."""
         import torch
         ctx = self.ctx
         if reset:
@@ -330,9 +332,16 @@ class Projector:
         n = int(cview[0])
         ranges = [Context.shard_slots(r, self.world, n, H, W) for r in range(self.world)]
         if gather and out and _dist(self.group) is not None:
-            for k, t in out.items():
-                if k not in ("counts", "pixel", "intensity"):      # the selection is replicated: only results travel
-                    gather_slices(t, ranges, group=self.group, dst=0 if gather == "root" else None)
+            cur = torch.cuda.current_stream()
+            gs = gather_stream if gather_stream is not None else cur
+            if gs is not cur:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                gs.wait_event(ev)                                   # the gathers follow this frame's kernels ...
+            with torch.cuda.stream(gs):                             # ... on a stream of their own when asked: the next
+                for k, t in out.items():                            # frame's kernels overlap them (caller double-buffers `out`)
+                    if k not in ("counts", "pixel", "intensity"):   # the selection is replicated: only results travel
+                        gather_slices(t, ranges, group=self.group, dst=0 if gather == "root" else None)
         if reduce:
             self.combiner.submit(reset=True)
         return n, _LazyHits(cnt), ranges[self.rank]
