@@ -346,6 +346,42 @@ __device__ __forceinline__ void node_table(const float cl[7], const float cr[7],
     for (int i = 2; i <= 7; ++i) C[i - 1] = fminf(distribute_cost(cl, cr, i, nullptr), C[i - 2]);
 }
 
+// What the collapse's selection walk needs of a binary node, in ONE 32-byte record (one sector) written by k_binfit:
+// the walk used to gather it from seven arrays (left, right, first, last, blo, bhi, ctab), seven cache lines per node.
+struct __align__(32) BinRec {
+    int32_t left, right, count;
+    float area;                    // dx*dy + dy*dz + dz*dx of the node's box
+    unsigned long long dec;        // node_decisions() (0 without cost tables)
+    unsigned long long pad_;
+};
+static_assert(sizeof(BinRec) == 32, "binary node record must be 32 bytes");
+
+// The cut decisions of a node, precomputed where its tables are in registers, so that the collapse's selection walk is
+// one 8-byte load per visited binary node instead of a re-evaluation of the tables of both children (fourteen floats
+// from two more cache lines, min-plus loops over local-memory arrays: 60-90 us per LEVEL of the collapse).
+//   bits 7(b-2) .. 7(b-2)+6, b = 2..8:  eff(b) in 4 bits = the largest b' <= b with C_distribute(n, b') < C(n, b'-1),
+//                                       else 1 ("this node is one child");  split(b) in 3 bits = the k of C_distribute(n, b)
+//   bit 63: as ONE child the node is an inner child (its own wide node), not a leaf slot
+// Exactly the comparisons the walk used to make, on the same floats: the wide tree is unchanged.
+__device__ __forceinline__ unsigned long long node_decisions(const float cl[7], const float cr[7], const float C[7], float A,
+                                                             int P, float c_prim)
+{
+    unsigned long long d = 0;
+    int eff = 1;
+#pragma unroll
+    for (int b = 2; b <= 8; ++b) {
+        int k;
+        const float dc = distribute_cost(cl, cr, b, &k);
+        if (dc < C[b - 2]) eff = b;
+        d |= (unsigned long long)(unsigned)(eff | (k << 4)) << (7 * (b - 2));
+    }
+    const bool inner = P > LEAF_MAX || !(A * (float)P * c_prim == C[0]);
+    if (inner) d |= 1ull << 63;
+    return d;
+}
+__device__ __forceinline__ int dec_eff(unsigned long long d, int b) { return b < 2 ? 1 : (int)((d >> (7 * (b - 2))) & 15u); }
+__device__ __forceinline__ int dec_split(unsigned long long d, int b) { return (int)((d >> (7 * (b - 2) + 4)) & 7u); }
+
 // Tree rotations at `cur` (Kensler 2008), applied by the thread that completes the node on the way up.  With
 // children L = (l0, l1) and R = (r0, r1) the candidates are
 //   child <-> grandchild:       L changes places with r_j (R keeps the other one), or R with l_i;
@@ -366,7 +402,7 @@ __device__ __forceinline__ RotBox rot_union(const RotBox &a, const RotBox &b)
 
 __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *left, int32_t *right, int32_t *parent,
                                            const int32_t *first, int32_t *last, float *blo, float *bhi, float *ctab,
-                                           float c_prim, int gg)
+                                           float c_prim, int gg, BinRec *rec)
 {
     auto count = [&](long long id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
     auto box = [&](long long id) -> RotBox {
@@ -382,6 +418,7 @@ __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *
 #pragma unroll
         for (int k = 0; k < 3; ++k) { blo[3 * id + k] = bx.lo[k]; bhi[3 * id + k] = bx.hi[k]; }
         last[id] = first[id] + cnt - 1;
+        unsigned long long d = 0;
         if (ctab) {
             float cl[7], cr[7], C[7];
             load_table(c0, n, ctab, blo, bhi, c_prim, cl);
@@ -389,7 +426,11 @@ __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *
             node_table(cl, cr, half_area(bx.lo, bx.hi), cnt, c_prim, C);
 #pragma unroll
             for (int i = 0; i < 7; ++i) ctab[8 * id + i] = C[i];
+            d = node_decisions(cl, cr, C, half_area(bx.lo, bx.hi), cnt, c_prim);
         }
+        BinRec q;
+        q.left = (int32_t)c0; q.right = (int32_t)c1; q.count = cnt; q.area = half_area(bx.lo, bx.hi); q.dec = d; q.pad_ = 0;
+        rec[id] = q;
     };
     const long long ch[2] = {left[cur], right[cur]};
     const bool inner[2] = {ch[0] < n - 1, ch[1] < n - 1};
@@ -451,7 +492,8 @@ __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *
 // at a node completes it: box, optional rotation (nodes of at most rot_max triangles), cost table of the collapse.
 __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict__ F, const uint32_t *__restrict__ sorted_tri,
                          long long n, int32_t *parent, int32_t *left, int32_t *right, const int32_t *first, int32_t *last,
-                         float *blo, float *bhi, int *flags, float *ctab, float c_prim, int rot_min, int rot_max, int rot_gg)
+                         float *blo, float *bhi, int *flags, float *ctab, float c_prim, int rot_min, int rot_max, int rot_gg,
+                         BinRec *rec)
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -466,7 +508,7 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
         __threadfence();
         if (atomicAdd(&flags[cur], 1) == 0) return;       // the sibling subtree is not done yet
         const int P = last[cur] - first[cur] + 1;
-        if (rot_max > 0 && P <= rot_max && P >= rot_min && P > 2 * LEAF_MAX) try_rotate(cur, n, left, right, parent, first, last, blo, bhi, ctab, c_prim, rot_gg);
+        if (rot_max > 0 && P <= rot_max && P >= rot_min && P > 2 * LEAF_MAX) try_rotate(cur, n, left, right, parent, first, last, blo, bhi, ctab, c_prim, rot_gg, rec);
         const long long L = left[cur], R = right[cur];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -475,6 +517,7 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
             blo[3 * cur + k] = lo[k];
             bhi[3 * cur + k] = hi[k];
         }
+        unsigned long long d = 0;
         if (ctab) {
             float cl[7], cr[7], C[7];
             load_table(L, n, ctab, blo, bhi, c_prim, cl);
@@ -482,6 +525,12 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
             node_table(cl, cr, half_area(lo, hi), P, c_prim, C);
 #pragma unroll
             for (int i = 0; i < 7; ++i) ctab[8 * cur + i] = C[i];
+            d = node_decisions(cl, cr, C, half_area(lo, hi), P, c_prim);
+        }
+        {
+            BinRec q;
+            q.left = (int32_t)L; q.right = (int32_t)R; q.count = P; q.area = half_area(lo, hi); q.dec = d; q.pad_ = 0;
+            rec[cur] = q;
         }
         if (cur == 0) return;
         cur = parent[cur];
@@ -513,6 +562,7 @@ struct CollapseArgs {
     int dp_max_count;
     int32_t *sel;
     long long cap_nodes;
+    const BinRec *rec;                 // per internal binary node: children, count, area, cut decisions
 };
 
 // one wide node `w` of the level that starts at `begin`; MODE 1: called by ONE thread (gl = 0), else by the eight lanes
@@ -554,27 +604,16 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
     int nc = 0;
     // cost tables decide the cut of subtrees of up to dp_max_count triangles (0 = all); above that the greedy
     // largest-area expansion keeps the upper levels balanced
+    const BinRec *__restrict__ rec = A.rec;
     const bool use_dp = ctab != nullptr && (dp_max_count <= 0 || count(r) <= dp_max_count);
     if (gl != 0 || MODE == 2) {
         // lanes 1..7 wait for lane 0's choice; MODE 2 reads it below
     } else if (use_dp) {
-        // cost-optimal cut of the binary subtree (tables from k_binfit); `inner` marks the children that become
-        // wide nodes themselves
-        auto cost = [&](int32_t id, int i) -> float {
-            return id < n - 1 ? ctab[8ll * id + (i - 1)] : area(id) * c_prim;
-        };
-        auto load7 = [&](int32_t id, float *c) {
-            for (int i = 1; i <= 7; ++i) c[i - 1] = cost(id, i);
-        };
-        auto is_inner = [&](int32_t id) -> bool {
-            if (id >= n - 1) return false;
-            const int P = last[id] - first[id] + 1;
-            if (P > LEAF_MAX) return true;
-            return !(area(id) * (float)P * c_prim == ctab[8ll * id]);      // C(id,1) came from the internal option
-        };
+        // cost-optimal cut of the binary subtree, from the decisions k_binfit stored with the tables: a visited node is
+        // one 8-byte load (plus its two child ids); `inner` marks the children that become wide nodes themselves
         nc = 0;
         inner_mask = 0;
-        if (r >= n - 1 || (w == 0 && !is_inner(r))) {
+        if (r >= n - 1 || (w == 0 && !(rec[r].dec >> 63))) {
             cand[0] = r; nc = 1;                                            // a whole mesh of <= LEAF_MAX triangles
         } else {
             int32_t st_id[16];
@@ -586,47 +625,61 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
                 const int32_t id = st_id[sp];
                 int b = st_b[sp];
                 if (id >= n - 1) { cand[nc++] = id; continue; }
-                float cl[7], cr[7];
-                load7(left[id], cl);
-                load7(right[id], cr);
+                const BinRec q = rec[id];
                 if (!force) {
-                    while (b > 1 && !(distribute_cost(cl, cr, b, nullptr) < cost(id, b - 1))) --b;
+                    b = dec_eff(q.dec, b);
                     if (b == 1) {
-                        if (is_inner(id)) inner_mask |= 1u << nc;
+                        if (q.dec >> 63) inner_mask |= 1u << nc;
                         cand[nc++] = id;
                         continue;
                     }
                 }
                 force = false;
-                int k;
-                distribute_cost(cl, cr, b, &k);
-                st_id[sp] = right[id]; st_b[sp] = b - k; ++sp;
-                st_id[sp] = left[id]; st_b[sp] = k; ++sp;
+                const int k = dec_split(q.dec, b);
+                st_id[sp] = q.right; st_b[sp] = b - k; ++sp;
+                st_id[sp] = q.left; st_b[sp] = k; ++sp;
             }
         }
-    } else if (!expandable(r)) {
-        cand[0] = r; carea[0] = -1.0f; nc = 1;
     } else {
-        cand[0] = left[r]; cand[1] = right[r];
-        carea[0] = expandable(cand[0]) ? prio(cand[0]) : -1.0f;
-        carea[1] = expandable(cand[1]) ? prio(cand[1]) : -1.0f;
-        nc = 2;
-        while (nc < 8) {
-            int b = -1;
-            float ba = -1.0f;
-            for (int j = 0; j < nc; ++j)
-                if (carea[j] > ba) { ba = carea[j]; b = j; }
-            if (b < 0) break;
-            const int32_t id = cand[b];
-            const int32_t l = left[id], rr = right[id];
-            cand[b] = l; carea[b] = expandable(l) ? prio(l) : -1.0f;
-            cand[nc] = rr; carea[nc] = expandable(rr) ? prio(rr) : -1.0f;
-            ++nc;
+        // greedy largest-priority expansion, one record load per new candidate (both children of an expansion in parallel)
+        auto prio_of = [&](const BinRec &q) -> float {
+            if (greedy_mode == 2) return (float)q.count;
+            if (greedy_mode == 3) return q.area * (float)q.count;
+            if (greedy_mode == 4) return q.area * sqrtf((float)q.count);
+            return q.area;
+        };
+        int32_t cleft[8], cright[8];
+        auto fetch = [&](int32_t id, int slot) {
+            cand[slot] = id; carea[slot] = -1.0f; cleft[slot] = cright[slot] = -1;
+            if (id < n - 1) {
+                const BinRec q = rec[id];
+                if (q.count > LEAF_MAX) { carea[slot] = prio_of(q); cleft[slot] = q.left; cright[slot] = q.right; inner_mask |= 1u << slot; }
+            }
+        };
+        inner_mask = 0;
+        fetch(r, 0);
+        nc = 1;
+        if (inner_mask) {
+            // the root always expands; then the candidate with the largest priority, until eight
+            inner_mask = 0;
+            const int32_t l0 = cleft[0], r0 = cright[0];
+            fetch(l0, 0);
+            fetch(r0, 1);
+            nc = 2;
+            while (nc < 8) {
+                int b = -1;
+                float ba = -1.0f;
+                for (int j = 0; j < nc; ++j)
+                    if (carea[j] > ba) { ba = carea[j]; b = j; }
+                if (b < 0) break;
+                const int32_t l = cleft[b], rr = cright[b];
+                inner_mask &= ~(1u << b);
+                fetch(l, b);
+                fetch(rr, nc);
+                ++nc;
+            }
         }
     }
-    if (MODE != 2 && gl == 0 && !use_dp)
-        for (int c = 0; c < nc; ++c)
-            if (expandable(cand[c])) inner_mask |= 1u << c;
     if (MODE == 1) {
         int32_t *o = sel + 9 * (w - begin);
         for (int c = 0; c < 8; ++c) o[c] = c < nc ? cand[c] : -1;
@@ -1145,7 +1198,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     const long long n = nF;
     const size_t N = (size_t)(n > 0 ? n : 1);
     size_t need = 4096 + sizeof(CollapseResult) + 256 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
-                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + (9 * (N / 2 + 64) * 4 + 256) + 1024;
+                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + (N * 32 + 256) + (9 * (N / 2 + 64) * 4 + 256) + 1024;
     if ((e = ensure_scratch(scratch, scratch_bytes, need)) != cudaSuccess) return e;
     Bump b{static_cast<char *>(*scratch)};
     unsigned *bounds_u = b.take<unsigned>(8);
@@ -1163,6 +1216,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     int32_t *wroot = b.take<int32_t>(N);
     int32_t *selbuf = b.take<int32_t>(9 * (N / 2 + 64));       // selection of one level (two-phase collapse)
     float *ctab = knob_sah_collapse() == 1 ? b.take<float>(8 * N) : nullptr;
+    BinRec *rec = b.take<BinRec>(N);
     const float c_prim = knob_c_prim();
 
     out.n_tris = n;
@@ -1204,12 +1258,12 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
     if (n > 1) k_karras<<<blocks_for(n - 1, 256), 256, 0, s>>>(keys, n, left, right, parent, first, last);
     k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab, c_prim,
-                                                knob_rotate_min(), knob_rotate_max(), knob_rotate_gg());
+                                                knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec);
     // further rotation passes over the rotated tree (each node looks at its new grandchildren once more)
     for (int pass = 1; pass < knob_rotate_passes() && knob_rotate_max() > 0; ++pass) {
         if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
         k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab,
-                                                    c_prim, knob_rotate_min(), knob_rotate_max(), knob_rotate_gg());
+                                                    c_prim, knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec);
     }
 
     // top-down collapse, one launch per level of the wide tree
@@ -1220,7 +1274,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         if ((e = cudaMemcpyAsync(wroot, &root_id, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     }
     CollapseArgs ca{n, left, right, first, last, blo, bhi, vals, wroot, out.nodes, topo.tri_face, counters, ctab, c_prim,
-                    knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes};
+                    knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes, rec};
     long long begin = 0, end = 1;
     int L = 0;
     if (knob_collapse_launches() == 0) {
