@@ -320,21 +320,37 @@ __device__ __forceinline__ float distribute_cost(const float cl[7], const float 
     return best;
 }
 
+// Boxes of the binary nodes (internal 0..n-2, leaves n-1..2n-2): 32 bytes per node = lo.xyz, -, hi.xyz, -, read and
+// written as two 16-byte words (one sector per node; the separate 12-byte-stride lo / hi arrays cost six scalar loads
+// from two sectors per box, and k_binfit -- the largest kernel of a build -- is made of such loads).
+__device__ __forceinline__ void box_load(const float *bbox, long long id, float lo[3], float hi[3])
+{
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(bbox + 8 * id));
+    const float4 b = __ldcg(reinterpret_cast<const float4 *>(bbox + 8 * id + 4));
+    lo[0] = a.x; lo[1] = a.y; lo[2] = a.z;
+    hi[0] = b.x; hi[1] = b.y; hi[2] = b.z;
+}
+__device__ __forceinline__ void box_store(float *bbox, long long id, const float lo[3], const float hi[3])
+{
+    *reinterpret_cast<float4 *>(bbox + 8 * id) = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    *reinterpret_cast<float4 *>(bbox + 8 * id + 4) = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
 // C(id, 1..7) of a node from its children (tables of internal children from ctab, read past L1: another thread may
 // have written them; a single triangle costs A * c_prim for every i)
-__device__ __forceinline__ void load_table(long long id, long long n, const float *ctab, const float *blo, const float *bhi,
-                                           float c_prim, float out[7])
+__device__ __forceinline__ void load_table(long long id, long long n, const float *ctab, const float *bbox, float c_prim,
+                                           float out[7])
 {
     if (id >= n - 1) {
         float lo[3], hi[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { lo[k] = __ldcg(&blo[3 * id + k]); hi[k] = __ldcg(&bhi[3 * id + k]); }
+        box_load(bbox, id, lo, hi);
         const float c = half_area(lo, hi) * c_prim;
 #pragma unroll
         for (int i = 0; i < 7; ++i) out[i] = c;
     } else {
-#pragma unroll
-        for (int i = 0; i < 7; ++i) out[i] = __ldcg(&ctab[8 * id + i]);
+        const float4 a = __ldcg(reinterpret_cast<const float4 *>(ctab + 8 * id));
+        const float4 b = __ldcg(reinterpret_cast<const float4 *>(ctab + 8 * id + 4));
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z;
     }
 }
 
@@ -401,31 +417,29 @@ __device__ __forceinline__ RotBox rot_union(const RotBox &a, const RotBox &b)
 }
 
 __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *left, int32_t *right, int32_t *parent,
-                                           const int32_t *first, int32_t *last, float *blo, float *bhi, float *ctab,
+                                           const int32_t *first, int32_t *last, float *bbox, float *ctab,
                                            float c_prim, int gg, BinRec *rec)
 {
     auto count = [&](long long id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
     auto box = [&](long long id) -> RotBox {
         RotBox r;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { r.lo[k] = __ldcg(&blo[3 * id + k]); r.hi[k] = __ldcg(&bhi[3 * id + k]); }
+        box_load(bbox, id, r.lo, r.hi);
         return r;
     };
     // make node `id` the parent of (c0, c1) with the given box and count, and refresh its cost table
     auto rebuild = [&](long long id, long long c0, long long c1, const RotBox &bx, int cnt) {
         left[id] = (int32_t)c0; right[id] = (int32_t)c1;
         parent[c0] = (int32_t)id; parent[c1] = (int32_t)id;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { blo[3 * id + k] = bx.lo[k]; bhi[3 * id + k] = bx.hi[k]; }
+        box_store(bbox, id, bx.lo, bx.hi);
         last[id] = first[id] + cnt - 1;
         unsigned long long d = 0;
         if (ctab) {
             float cl[7], cr[7], C[7];
-            load_table(c0, n, ctab, blo, bhi, c_prim, cl);
-            load_table(c1, n, ctab, blo, bhi, c_prim, cr);
+            load_table(c0, n, ctab, bbox, c_prim, cl);
+            load_table(c1, n, ctab, bbox, c_prim, cr);
             node_table(cl, cr, half_area(bx.lo, bx.hi), cnt, c_prim, C);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) ctab[8 * id + i] = C[i];
+            *reinterpret_cast<float4 *>(ctab + 8 * id) = make_float4(C[0], C[1], C[2], C[3]);
+            *reinterpret_cast<float4 *>(ctab + 8 * id + 4) = make_float4(C[4], C[5], C[6], 0.0f);
             d = node_decisions(cl, cr, C, half_area(bx.lo, bx.hi), cnt, c_prim);
         }
         BinRec q;
@@ -492,7 +506,7 @@ __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *
 // at a node completes it: box, optional rotation (nodes of at most rot_max triangles), cost table of the collapse.
 __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict__ F, const uint32_t *__restrict__ sorted_tri,
                          long long n, int32_t *parent, int32_t *left, int32_t *right, const int32_t *first, int32_t *last,
-                         float *blo, float *bhi, int *flags, float *ctab, float c_prim, int rot_min, int rot_max, int rot_gg,
+                         float *bbox, int *flags, float *ctab, float c_prim, int rot_min, int rot_max, int rot_gg,
                          BinRec *rec)
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -500,31 +514,31 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
     float lo[3], hi[3];
     tri_box(V, F, sorted_tri[j], lo, hi);
     long long id = (n - 1) + j;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { blo[3 * id + k] = lo[k]; bhi[3 * id + k] = hi[k]; }
+    box_store(bbox, id, lo, hi);
     if (n == 1) return;
     long long cur = parent[id];
     for (;;) {
         __threadfence();
         if (atomicAdd(&flags[cur], 1) == 0) return;       // the sibling subtree is not done yet
         const int P = last[cur] - first[cur] + 1;
-        if (rot_max > 0 && P <= rot_max && P >= rot_min && P > 2 * LEAF_MAX) try_rotate(cur, n, left, right, parent, first, last, blo, bhi, ctab, c_prim, rot_gg, rec);
+        if (rot_max > 0 && P <= rot_max && P >= rot_min && P > 2 * LEAF_MAX) try_rotate(cur, n, left, right, parent, first, last, bbox, ctab, c_prim, rot_gg, rec);
         const long long L = left[cur], R = right[cur];
+        {
+            float llo[3], lhi[3], rlo[3], rhi[3];
+            box_load(bbox, L, llo, lhi);
+            box_load(bbox, R, rlo, rhi);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            lo[k] = fminf(__ldcg(&blo[3 * L + k]), __ldcg(&blo[3 * R + k]));
-            hi[k] = fmaxf(__ldcg(&bhi[3 * L + k]), __ldcg(&bhi[3 * R + k]));
-            blo[3 * cur + k] = lo[k];
-            bhi[3 * cur + k] = hi[k];
+            for (int k = 0; k < 3; ++k) { lo[k] = fminf(llo[k], rlo[k]); hi[k] = fmaxf(lhi[k], rhi[k]); }
+            box_store(bbox, cur, lo, hi);
         }
         unsigned long long d = 0;
         if (ctab) {
             float cl[7], cr[7], C[7];
-            load_table(L, n, ctab, blo, bhi, c_prim, cl);
-            load_table(R, n, ctab, blo, bhi, c_prim, cr);
+            load_table(L, n, ctab, bbox, c_prim, cl);
+            load_table(R, n, ctab, bbox, c_prim, cr);
             node_table(cl, cr, half_area(lo, hi), P, c_prim, C);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) ctab[8 * cur + i] = C[i];
+            *reinterpret_cast<float4 *>(ctab + 8 * cur) = make_float4(C[0], C[1], C[2], C[3]);
+            *reinterpret_cast<float4 *>(ctab + 8 * cur + 4) = make_float4(C[4], C[5], C[6], 0.0f);
             d = node_decisions(cl, cr, C, half_area(lo, hi), P, c_prim);
         }
         {
@@ -549,7 +563,7 @@ __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict_
 struct CollapseArgs {
     long long n;
     const int32_t *left, *right, *first, *last;
-    const float *blo, *bhi;
+    const float *bbox;
     const uint32_t *sorted_tri;
     int32_t *wroot;
     WideNode *nodes;
@@ -567,13 +581,16 @@ struct CollapseArgs {
 
 // one wide node `w` of the level that starts at `begin`; MODE 1: called by ONE thread (gl = 0), else by the eight lanes
 // gl = 0..7 of an aligned group
+// MODE 0 and 2 must be called by ALL threads of a 256-thread block (`active` = this group has a node): the children
+// and records of the block's 32 nodes are allocated with ONE pair of global atomics per block (shared-memory
+// aggregation; one pair per node made the two counters the bottleneck of the large levels: 0.65 ms at 5M triangles).
 template <int MODE>
-__device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w, long long begin, int gl)
+__device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w, long long begin, int gl, bool active = true)
 {
     const long long n = A.n;
     const int32_t *__restrict__ left = A.left, *__restrict__ right = A.right, *__restrict__ first = A.first,
                   *__restrict__ last = A.last;
-    const float *__restrict__ blo = A.blo, *__restrict__ bhi = A.bhi, *__restrict__ ctab = A.ctab;
+    const float *__restrict__ bbox = A.bbox, *__restrict__ ctab = A.ctab;
     const uint32_t *__restrict__ sorted_tri = A.sorted_tri;
     int32_t *wroot = A.wroot, *tri_face = A.tri_face, *wparent = A.wparent, *sel = A.sel;
     WideNode *nodes = A.nodes;
@@ -584,13 +601,13 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
     const int lane32 = threadIdx.x & 31;
     const unsigned gmask = 0xffu << (lane32 & 24);
     const int gbase = lane32 & 24;
-    const int32_t r = wroot[w];
+    const int32_t r = active ? wroot[w] : 0;
     unsigned inner_mask = 0;
     auto count = [&](int32_t id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
     auto expandable = [&](int32_t id) -> bool { return id < n - 1 && (last[id] - first[id] + 1) > LEAF_MAX; };
     auto area = [&](int32_t id) -> float {
-        const float dx = bhi[3ll * id] - blo[3ll * id], dy = bhi[3ll * id + 1] - blo[3ll * id + 1],
-                    dz = bhi[3ll * id + 2] - blo[3ll * id + 2];
+        const float dx = bbox[8ll * id + 4] - bbox[8ll * id], dy = bbox[8ll * id + 5] - bbox[8ll * id + 1],
+                    dz = bbox[8ll * id + 6] - bbox[8ll * id + 2];
         return dx * dy + dy * dz + dz * dx;
     };
     auto prio = [&](int32_t id) -> float {
@@ -606,7 +623,9 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
     // largest-area expansion keeps the upper levels balanced
     const BinRec *__restrict__ rec = A.rec;
     const bool use_dp = ctab != nullptr && (dp_max_count <= 0 || count(r) <= dp_max_count);
-    if (gl != 0 || MODE == 2) {
+    if (!active) {
+        nc = 0;                                             // takes part in the block's allocation with nothing to allocate
+    } else if (gl != 0 || MODE == 2) {
         // lanes 1..7 wait for lane 0's choice; MODE 2 reads it below
     } else if (use_dp) {
         // cost-optimal cut of the binary subtree, from the decisions k_binfit stored with the tables: a visited node is
@@ -686,7 +705,7 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
         o[8] = nc | (int)(inner_mask << 8);
         return;
     }
-    if (MODE == 2 && gl == 0) {
+    if (MODE == 2 && gl == 0 && active) {
         const int32_t *o = sel + 9 * (w - begin);
         for (int c = 0; c < 8; ++c) cand[c] = o[c];
         nc = o[8] & 0xff;
@@ -707,7 +726,7 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
     if (have) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            lo[k] = blo[3ll * my + k]; hi[k] = bhi[3ll * my + k];
+            lo[k] = bbox[8ll * my + k]; hi[k] = bbox[8ll * my + 4 + k];
             cen[k] = 0.5f * (lo[k] + hi[k]);
         }
     }
@@ -766,9 +785,23 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
         if (sj < my_slot) { k_inner += ij; toff += cj; }
     }
     unsigned cbase = 0, tbase = 0;
-    if (gl == 0) {
-        cbase = n_inner ? atomicAdd(&counters[0], (unsigned)n_inner) : 0u;
-        tbase = n_leaf_tris ? atomicAdd(&counters[1], (unsigned)n_leaf_tris) : 0u;
+    {
+        __shared__ unsigned s_alloc[4];                     // demand of the block (inner, records), then its two bases
+        if (threadIdx.x == 0) { s_alloc[0] = 0u; s_alloc[1] = 0u; }
+        __syncthreads();
+        if (gl == 0) {
+            if (n_inner) cbase = atomicAdd(&s_alloc[0], (unsigned)n_inner);
+            if (n_leaf_tris) tbase = atomicAdd(&s_alloc[1], (unsigned)n_leaf_tris);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_alloc[2] = s_alloc[0] ? atomicAdd(&counters[0], s_alloc[0]) : 0u;
+            s_alloc[3] = s_alloc[1] ? atomicAdd(&counters[1], s_alloc[1]) : 0u;
+        }
+        __syncthreads();
+        cbase += s_alloc[2];
+        tbase += s_alloc[3];
+        __syncthreads();                                    // the next call of this block may zero the counters again
     }
     cbase = __shfl_sync(gmask, cbase, gbase);
     tbase = __shfl_sync(gmask, tbase, gbase);
@@ -797,7 +830,7 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
         meta_hi |= __shfl_xor_sync(gmask, meta_hi, d);
         ibit |= __shfl_xor_sync(gmask, ibit, d);
     }
-    if (gl == 0) {
+    if (gl == 0 && active) {
         nodes[w].w[0] = make_uint4(0u, 0u, 0u, ibit << 24);
         nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
     }
@@ -809,8 +842,11 @@ __global__ void __launch_bounds__(256) k_collapse(CollapseArgs A, long long begi
 {
     const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long w = begin + (MODE == 1 ? gt : (gt >> 3));
-    if (w >= end) return;                                   // whole groups leave together
-    collapse_node<MODE>(A, w, begin, MODE == 1 ? 0 : (int)(gt & 7));
+    if (MODE == 1) {
+        if (w < end) collapse_node<1>(A, w, begin, 0);
+    } else {
+        collapse_node<MODE>(A, w, begin, (int)(gt & 7), w < end);      // every thread of the block (block allocation)
+    }
 }
 
 // The whole top-down collapse in ONE cooperative launch: the grid walks the levels itself, a grid-wide barrier where the
@@ -863,12 +899,16 @@ __global__ void __launch_bounds__(256) k_collapse_all(CollapseArgs A, CollapseRe
     while (begin < end) {
         if (L + 1 >= 127) { if (gt == 0) { res->n_levels = -1; res->n_nodes = end; } return; }
         const long long lvl = end - begin;
+        // MODE 0 / 2: whole blocks walk tiles of 32 nodes (the same trip count for every thread of a block)
+        const int gib = threadIdx.x >> 3, gl = threadIdx.x & 7;
         if (lvl < 2048) {
-            for (long long g = gt >> 3; g < lvl; g += nthreads >> 3) collapse_node<0>(A, begin + g, begin, (int)(gt & 7));
+            for (long long base = blockIdx.x * 32ll; base < lvl; base += gridDim.x * 32ll)
+                collapse_node<0>(A, begin + base + gib, begin, gl, base + gib < lvl);
         } else {
             for (long long t = gt; t < lvl; t += nthreads) collapse_node<1>(A, begin + t, begin, 0);
             grid_barrier_publish(res, A.counters, phase);
-            for (long long g = gt >> 3; g < lvl; g += nthreads >> 3) collapse_node<2>(A, begin + g, begin, (int)(gt & 7));
+            for (long long base = blockIdx.x * 32ll; base < lvl; base += gridDim.x * 32ll)
+                collapse_node<2>(A, begin + base + gib, begin, gl, base + gib < lvl);
         }
         const long long next_end = grid_barrier_publish(res, A.counters, phase);
         ++L;
@@ -1198,7 +1238,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     const long long n = nF;
     const size_t N = (size_t)(n > 0 ? n : 1);
     size_t need = 4096 + sizeof(CollapseResult) + 256 + 4 * (N * 4 + 256) + (radix_table_entries(n) * 4 + 256) + 4 * (N * 4 + 256) +
-                  (2 * N * 4 + 256) + 2 * (2 * N * 3 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + (N * 32 + 256) + (9 * (N / 2 + 64) * 4 + 256) + 1024;
+                  (2 * N * 4 + 256) + (2 * N * 8 * 4 + 256) + (N * 4 + 256) + (N * 4 + 256) + (8 * N * 4 + 256) + (N * 32 + 256) + (9 * (N / 2 + 64) * 4 + 256) + 1024;
     if ((e = ensure_scratch(scratch, scratch_bytes, need)) != cudaSuccess) return e;
     Bump b{static_cast<char *>(*scratch)};
     unsigned *bounds_u = b.take<unsigned>(8);
@@ -1211,7 +1251,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     int32_t *left = b.take<int32_t>(N), *right = b.take<int32_t>(N);
     int32_t *first = b.take<int32_t>(N), *last = b.take<int32_t>(N);
     int32_t *parent = b.take<int32_t>(2 * N);
-    float *blo = b.take<float>(2 * N * 3), *bhi = b.take<float>(2 * N * 3);
+    float *bbox = b.take<float>(2 * N * 8);
     int *flags = b.take<int>(N);
     int32_t *wroot = b.take<int32_t>(N);
     int32_t *selbuf = b.take<int32_t>(9 * (N / 2 + 64));       // selection of one level (two-phase collapse)
@@ -1257,12 +1297,12 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     if ((e = cudaMemsetAsync(parent, 0xff, 2 * N * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
     if (n > 1) k_karras<<<blocks_for(n - 1, 256), 256, 0, s>>>(keys, n, left, right, parent, first, last);
-    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab, c_prim,
+    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, bbox, flags, ctab, c_prim,
                                                 knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec);
     // further rotation passes over the rotated tree (each node looks at its new grandchildren once more)
     for (int pass = 1; pass < knob_rotate_passes() && knob_rotate_max() > 0; ++pass) {
         if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
-        k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, blo, bhi, flags, ctab,
+        k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, bbox, flags, ctab,
                                                     c_prim, knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec);
     }
 
@@ -1273,7 +1313,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         if ((e = cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(wroot, &root_id, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     }
-    CollapseArgs ca{n, left, right, first, last, blo, bhi, vals, wroot, out.nodes, topo.tri_face, counters, ctab, c_prim,
+    CollapseArgs ca{n, left, right, first, last, bbox, vals, wroot, out.nodes, topo.tri_face, counters, ctab, c_prim,
                     knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes, rec};
     long long begin = 0, end = 1;
     int L = 0;
