@@ -11,10 +11,11 @@ threshold+compaction -> pixel rays (object frame) -> 8-wide BVH traversal -> his
 * value      device-resident: heatmap already in HBM, outputs stay in HBM; per-step CUDA events on the
              launching stream, L2 flushed between steps (256 MiB memset, outside the events).
 * e2e        the same frames through the host-buffer API (FrameStream over dp_project): pinned host heatmap in, the
-             drop-in's payload out -- t_hit, face id and the float32 hit point of every ray (20 B/ray; the pixel list of
-             a dense frame is the identity and is not shipped) + counts; copies inside the timed region.  Two more modes
-             are reported beside it: `lean` (t_hit + face, 8 B/ray) and `accumulate_only` (no per-ray read-back: the
-             per-face histogram / maxima ARE the product for go.Mesh3d, /root/reference/src/web_vis.py:203-217).
+             drop-in's payload out -- the float32 hit point and the face id of every ray (16 B/ray; the pixel list of
+             a dense frame is the identity and is not shipped) + counts; copies inside the timed region.  Three more modes
+             are reported beside it: `full` (+ t_hit, 20 B/ray), `lean` (t_hit + face, 8 B/ray) and `accumulate_only` (no
+             per-ray read-back: the per-face histogram / maxima ARE the product for go.Mesh3d,
+             /root/reference/src/web_vis.py:203-217).
 * roofline   traversal kernel (k_trace): algorithmic bytes/ray (node bytes x nodes fetched + 48 B x triangles tested +
              32 B of ray I/O + 32 B of accumulator RMW per hit; counts measured live by the counting kernel variant;
              node bytes = 208 for the uncompressed node set traced while the hierarchy fits L2, 80 for the compressed
@@ -662,7 +663,10 @@ def run_ours(args):
         wall = time.perf_counter() - t0
         return dict(rays=rays, ms=float(fs.last_elapsed_ms), wall=wall, d2h=fs.last_d2h_bytes)
 
-    modes = {"payload": ("pixel", "t_hit", "face", "point"), "lean": ("pixel", "t_hit", "face"), "accumulate_only": ()}
+    # payload: what north_star names as the per-ray outputs -- hit point and face id (t_hit is |point|, not shipped);
+    # full: t_hit as well (20 B/ray); lean: t_hit + face only; accumulate_only: nothing per ray
+    modes = {"payload": ("pixel", "face", "point"), "full": ("pixel", "t_hit", "face", "point"),
+             "lean": ("pixel", "t_hit", "face"), "accumulate_only": ()}
     e2e = {k: run_mode(w) for k, w in modes.items()}
     h2d = n_pix * 4 + 128                       # heatmap + per-frame constants
     # the same frame as one blocking call (no overlap), for reference
@@ -738,9 +742,10 @@ def run_ours(args):
                     "blocking_call_ms_per_frame": blocking_ms,
                     "api": "defectproj.FrameStream.run (3-stream pipeline over dp_project); blocking_call = Context.project",
                     "l2": "132 MiB (> 126 MB L2) memset on the kernel stream before every frame, inside the timed region",
-                    "outputs": "the drop-in's payload: t_hit f32, face i32 and the float32 hit point of every ray (20 B/ray; the "
-                               "reference returns the hit points, /root/reference/src/defect_projection.py:261-264) + ray/hit "
-                               "counts; pixel u32 is the identity for a dense frame (synthesised on the host, not copied); "
+                    "outputs": "the drop-in's payload: the float32 hit point and the face id of every ray (16 B/ray; the reference "
+                               "returns the hit points, /root/reference/src/defect_projection.py:261-264, the face ids are the "
+                               "extension north_star names) + ray/hit counts; t_hit (= |point|) travels in mode 'full' "
+                               "(20 B/ray); pixel u32 is the identity for a dense frame (synthesised on the host, not copied); "
                                "heatmap f32 in; pinned host memory",
                     "modes": {k: e2e_entry(k) for k in keys}},
             # k_project_prologue, k_compact, k_trace per frame (rays and hit points are generated inside k_trace; with
