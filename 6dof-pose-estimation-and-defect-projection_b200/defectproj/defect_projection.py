@@ -390,7 +390,7 @@ def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_thresh
     stage = _PINNED.get((heat.shape, heat.dtype.str))
     if stage is None:
         stage = _PINNED[(heat.shape, heat.dtype.str)] = ctx.pinned_array(heat.shape, heat.dtype)
-    np.copyto(stage, heat)
+    np.copyto(stage, heat)       # (splitting this copy over threads measured slower: dispatch costs more than it saves)
     res = ctx.project(stage, K, None, heatmap_threshold, frame="camera", accumulate=True,
                       want=("pixel", "t_hit", "face", "point64"))
     pix = res["pixel"].astype(np.int64)

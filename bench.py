@@ -546,12 +546,22 @@ def run_ours(args):
     ev_pack = [torch.cuda.Event() for _ in range(2)]
     gathered = [0]
 
-    def batch_end(b):
+    skew_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    skew_t = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def batch_end(b, probe_skew=False):
         """compute stream: hit records of the batch's last frame + accumulator snapshot; the reductions go to the side stream"""
         k = b & 1
         ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec_buf[k], count_async=rec_cnt[k],
                                 sync=False, stream=stream)
         ev_pack[k].record(stream)
+        if probe_skew and world > 1:
+            # how long this rank waits for the slowest one: a 4-byte all-reduce right behind this rank's last kernel
+            with torch.cuda.stream(comb.side):
+                comb.side.wait_event(ev_pack[k])
+                skew_ev[0].record(comb.side)
+                dist.all_reduce(skew_t)
+                skew_ev[1].record(comb.side)
         comb.submit(stream)
 
     def batch_gather(b):
@@ -597,7 +607,7 @@ def run_ours(args):
             step_device(args.warmup + i)
             last_of_batch = i == bounds[b + 1] - 1
             if last_of_batch:
-                batch_end(b)                 # inside the step's event pair: pack + vertex maxima + snapshot
+                batch_end(b, probe_skew=(b == nb_batches - 1))   # inside the step's event pair: pack + vertex maxima + snapshot
             ev[i][1].record(stream)
             if sampled:
                 # kernel-only duration of the traversal launch of this step
@@ -613,6 +623,7 @@ def run_ours(args):
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     tail_ms = ev[-1][1].elapsed_time(ev_tail)
+    skew_ms = skew_ev[0].elapsed_time(skew_ev[1]) if world > 1 else 0.0
     total_ms = float(sum(step_ms)) + tail_ms
     hist_t, fmax_t, vmax_t = comb.result()
     hist_total = int(hist_t.sum().item())                         # all ranks, all batches
@@ -685,12 +696,12 @@ def run_ours(args):
     # -- max over ranks
     keys = list(modes)
     if world > 1:
-        t = torch.tensor([total_ms, tail_ms, serial_reduce_ms, serial_gather_ms] + [e2e[k]["ms"] for k in keys],
+        t = torch.tensor([total_ms, tail_ms, serial_reduce_ms, serial_gather_ms, skew_ms] + [e2e[k]["ms"] for k in keys],
                          dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, tail_ms, serial_reduce_ms, serial_gather_ms = (float(x) for x in t[:4])
+        total_ms, tail_ms, serial_reduce_ms, serial_gather_ms, skew_ms = (float(x) for x in t[:5])
         for j, k in enumerate(keys):
-            e2e[k]["ms"] = float(t[4 + j])
+            e2e[k]["ms"] = float(t[5 + j])
         c = torch.tensor([n_rays * args.steps, n_hits * 0] + [e2e[k]["rays"] for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         rays_total = float(c[0])
@@ -765,13 +776,15 @@ def run_ours(args):
             "ms_per_frame": total_ms / args.steps,
             "bvh": {"build_ms": st2["last_build_ms"], "wide_nodes": st2["n_wide_nodes"], "depth": st2["wide_depth"],
                     "bytes": st2["n_wide_nodes"] * nb + st2["n_tris"] * B_TRI},
-            "combine": {"batches": nb_batches, "exposed_tail_ms": tail_ms,
+            "combine": {"batches": nb_batches, "exposed_tail_ms": tail_ms, "wait_slowest_rank_ms": skew_ms,
                         "serial_reduce_ms": serial_reduce_ms, "serial_gather_ms": serial_gather_ms,
                         "what": "per batch: k_pack_records (hit records of the batch's last frame) + k_vertex_max + ONE "
                                 "snapshot copy of the accumulator block inside the last step's event pair; on a side stream: "
                                 "all_reduce SUM (hist) + ONE all_reduce MAX (fmax|vmax) of the snapshot, count exchange, "
                                 "unpadded gather of the records to rank 0.  Batch b's side-stream work overlaps batch b+1's "
-                                "frames; the last batch's is the exposed tail (inside the timed total).  serial_*: the same "
+                                "frames; the last batch's is the exposed tail (inside the timed total).  wait_slowest_rank_ms: a "
+                                "4-byte all-reduce right behind the last kernel of the run, as seen by the rank that waits longest "
+                                "(part of the tail).  serial_*: the same "
                                 "reduce / pack+gather run serially after the timed region (includes waiting for the slowest rank)",
                         "hit_records_gathered": gathered[0]},
             "checks": {"rays_per_frame": n_rays, "hits_per_frame": n_hits, "hist_total_all_ranks": hist_total,
