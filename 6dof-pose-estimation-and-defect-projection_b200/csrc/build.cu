@@ -604,18 +604,6 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
     const int32_t r = active ? wroot[w] : 0;
     unsigned inner_mask = 0;
     auto count = [&](int32_t id) -> int { return id < n - 1 ? last[id] - first[id] + 1 : 1; };
-    auto expandable = [&](int32_t id) -> bool { return id < n - 1 && (last[id] - first[id] + 1) > LEAF_MAX; };
-    auto area = [&](int32_t id) -> float {
-        const float dx = bbox[8ll * id + 4] - bbox[8ll * id], dy = bbox[8ll * id + 5] - bbox[8ll * id + 1],
-                    dz = bbox[8ll * id + 6] - bbox[8ll * id + 2];
-        return dx * dy + dy * dz + dz * dx;
-    };
-    auto prio = [&](int32_t id) -> float {
-        if (greedy_mode == 2) return (float)count(id);
-        if (greedy_mode == 3) return area(id) * (float)count(id);
-        if (greedy_mode == 4) return area(id) * sqrtf((float)count(id));
-        return area(id);
-    };
     int32_t cand[8];
     float carea[8];
     int nc = 0;

@@ -758,6 +758,36 @@ def test_frame_stream_equals_blocking_calls(ctx, orc):
     assert np.array_equal(hist_stream, ctx.accum_get()[0]) and hist_stream.sum() == sum(g["hits"] for g in got.values())
 
 
+def test_frame_stream_modes_ship_only_what_was_asked(ctx):
+    """FrameStream(want=...): 'payload' (face + point, no t_hit), accumulate-only (nothing per ray: counts and the device
+    accumulators are the product).  Same hits, same histogram; only the bytes that cross PCIe differ."""
+    import torch
+    from defectproj import FrameStream
+    V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
+    K, H, W = synth.K_matrix(305.0, 305.0, 320.0, 180.0), 360, 640
+    B = 4
+    poses = synth.helix_poses(B, turns=1)
+    heats = [torch.from_numpy(synth.blob_heatmap((H, W), seed=60 + i)).pin_memory() for i in range(B)]
+    ctx.set_mesh(V, F).build_bvh()
+    ref, hist = {}, {}
+    for name, want in (("full", ("pixel", "t_hit", "face", "point")), ("payload", ("pixel", "face", "point")), ("acc", ())):
+        ctx.accum_reset()
+        fs = FrameStream(ctx, H, W, want=want)
+        got = {i: {k: (v.copy() if hasattr(v, "copy") else v) for k, v in res.items()}
+               for i, res in fs.run(heats, K, poses, 0.5, "object", True)}
+        hist[name] = ctx.accum_get()[0]
+        ref[name] = got
+        assert fs.last_d2h_bytes == 16 + sum({"pixel": 4, "t_hit": 4, "face": 4, "point": 12}[k] for k in want) * got[B - 1]["n"]
+    for i in range(B):
+        assert ref["payload"][i]["n"] == ref["full"][i]["n"] == ref["acc"][i]["n"] > 0
+        assert ref["payload"][i]["hits"] == ref["full"][i]["hits"] == ref["acc"][i]["hits"]
+        assert np.array_equal(ref["payload"][i]["face"], ref["full"][i]["face"])
+        assert np.array_equal(ref["payload"][i]["point"], ref["full"][i]["point"], equal_nan=True)
+        assert "t_hit" not in ref["payload"][i] and set(ref["acc"][i]) == {"n", "hits"}
+    assert np.array_equal(hist["payload"], hist["full"]) and np.array_equal(hist["acc"], hist["full"])
+    assert hist["full"].sum() == sum(ref["full"][i]["hits"] for i in range(B)) > 0
+
+
 # ------------------------------------------------------------------------------------------ depth path (8f #1)
 def test_depth_projection_path_matches_reference(built_lib, orc):
     """heatmap_to_point3d / calc_coordinates / align_to_surface / depth_projection_heatmap through the drop-in
