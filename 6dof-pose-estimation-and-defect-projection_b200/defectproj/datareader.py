@@ -37,10 +37,25 @@ class HeatmapReader:
     def __init__(self, base_dir, color_H, color_W, downscale=1):
         self.base_dir, self.color_H, self.color_W, self.downscale = base_dir, int(color_H), int(color_W), downscale
 
-    def get_heatmap(self, color_image=None):
-        """(heatmap_full, color_original, heatmap_vis, color_original) like datareader.py:675."""
+    def get_heatmap(self, color_image=None, device=False):
+        """(heatmap_full, color_original, heatmap_vis, color_original) like datareader.py:675.  device=True: the raw map
+        (224x224: 400 KB) is uploaded and heatmap_full / heatmap_vis are CUDA tensors -- ray_tracing() takes heatmap_full as
+        it is, so the padded 720p map (7.4 MB as float64) never crosses PCIe."""
         heatmap_data = np.load(f"{self.base_dir}/heatmap/0002.npy")
-        full, vis = prepare_heatmap(heatmap_data, self.color_H, self.color_W, self.downscale, with_vis=True)
+        if device:
+            import torch
+            ctx = get_context()
+            data = heatmap_data if heatmap_data.dtype in (np.float32, np.float64) else heatmap_data.astype(np.float64)
+            data_t = torch.from_numpy(np.ascontiguousarray(data)).to(f"cuda:{ctx.device}")
+            H, W = int(self.color_H / self.downscale), int(self.color_W / self.downscale)
+            full = ctx.prepare_heatmap(data_t, H, W, np.float64)
+            o = min(H, W)
+            y0, x0 = (H - o) // 2, (W - o) // 2
+            vis = full[y0:y0 + o, x0:x0 + o]
+            if data.dtype == np.float32:
+                vis = vis.float()
+        else:
+            full, vis = prepare_heatmap(heatmap_data, self.color_H, self.color_W, self.downscale, with_vis=True)
         color_original = None
         if color_image is not None:
             try:

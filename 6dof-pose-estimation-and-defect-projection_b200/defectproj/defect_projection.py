@@ -375,6 +375,8 @@ def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_thresh
     T = np.linalg.inv(color_to_depth)
     V, F = _mesh_arrays(target_mesh)
     K = _K(color_intrinsics)
+    if _is_cuda_tensor(heatmap):
+        return _ray_tracing_device(T, V, F, K, heatmap, heatmap_threshold)
     heat = np.asarray(heatmap)
     if heat.ndim != 2:
         raise ValueError("heatmap must be 2-D")
@@ -409,6 +411,61 @@ def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_thresh
         return pcd, mesh_copy
     # miss-all: the reference draws the rays (:561-563)
     W = heat.shape[1]
+    ys, xs = np.divmod(pix, W)
+    rays = ctx.compute_rays(xs, ys, K) if len(pix) else np.zeros((0, 3))
+    return project_debug_rays(rays, np.array([0, 0, 0])), mesh_copy
+
+
+def _is_cuda_tensor(x):
+    return type(x).__module__.startswith("torch") and bool(getattr(x, "is_cuda", False))
+
+
+_DEVOUT = {}
+
+
+def _ray_tracing_device(T, V, F, K, heat_t, heatmap_threshold):
+    """ray_tracing() for a heatmap that already lives on the GPU (a CUDA tensor, e.g. from
+    ``HeatmapReader.get_heatmap(..., device=True)``: the raw 224x224 map is 400 KB, the padded 720p float64 map the
+    reference hands over is 7.4 MB -- copying that into pinned memory and across PCIe is half of the host-array call).
+    Nothing per-pixel crosses PCIe: the per-ray results stay on the device, the hits are selected and coloured there, and
+    only the hit cloud (and the per-ray arrays of last_result()) come back.  Bit-identical to the host-array path."""
+    global _LAST
+    import torch
+    if heat_t.dim() != 2:
+        raise ValueError("heatmap must be 2-D")
+    if heat_t.dtype not in (torch.float32, torch.float64):
+        heat_t = heat_t.double()
+    heat_t = heat_t.contiguous()
+    H, W = heat_t.shape
+    ctx = _scene(V, F)
+    if heat_t.device.index != ctx.device:
+        raise ValueError("the heatmap lives on another device than the projection context")
+    ctx.pose_mesh(T)
+    mesh_copy = PosedMesh(ctx.posed_vertices_device(np.float64 if V.dtype == np.float64 else np.float32), F)
+    ctx.accum_reset()
+    cap = H * W
+    o = _DEVOUT.get((cap, ctx.device))
+    if o is None:
+        dev = heat_t.device
+        o = _DEVOUT[(cap, ctx.device)] = dict(pixel=torch.empty(cap, dtype=torch.int32, device=dev),
+                                              t_hit=torch.empty(cap, dtype=torch.float32, device=dev),
+                                              face=torch.empty(cap, dtype=torch.int32, device=dev),
+                                              point64=torch.empty((cap, 3), dtype=torch.float64, device=dev))
+    n, h = ctx.project_device(heat_t[None], K, None, heatmap_threshold, "camera", True, out=o, sync=True)
+    pix_d, face_d, t_d = o["pixel"][:n], o["face"][:n], o["t_hit"][:n]
+    inten_d = heat_t.reshape(-1)[pix_d.long()]                          # exact values, in the heatmap's own dtype
+    pix = pix_d.cpu().numpy().view(np.uint32).astype(np.int64)
+    face = face_d.cpu().numpy()
+    t_hit = t_d.cpu().numpy()
+    _GEN[0] += 1
+    _LAST = _LazyResult(ctx, _GEN[0], pixel=pix, intensity=inten_d.cpu().numpy(), t_hit=t_hit, face=face, n_rays=n, n_hits=h)
+    if h > 0:
+        pk = ctx.pack_hits_device(inten_d, face_d, pix_d, o["point64"][:n], want=("points", "colors", "face", "pixel"))
+        pcd = PointCloud(pk["points"].cpu().numpy(), pk["colors"].cpu().numpy())
+        pcd.face_ids = pk["face"].cpu().numpy()
+        pcd.t_hit = t_hit[face >= 0]
+        pcd.pixels = pk["pixel"].cpu().numpy().view(np.uint32).astype(np.int64)
+        return pcd, mesh_copy
     ys, xs = np.divmod(pix, W)
     rays = ctx.compute_rays(xs, ys, K) if len(pix) else np.zeros((0, 3))
     return project_debug_rays(rays, np.array([0, 0, 0])), mesh_copy

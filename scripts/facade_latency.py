@@ -48,6 +48,20 @@ with tempfile.TemporaryDirectory() as d:
                    "cpu_port_ms": cpu_ms, "cpu_cores": orc.num_threads()}
             out.append(row)
             print(json.dumps(row), flush=True)
+        # the heatmap already on the GPU (HeatmapReader.get_heatmap(device=True) prepares it there from the 224x224 raw map)
+        import torch
+        heat_d = torch.from_numpy(heat).cuda()
+        for thr in (0.75, 0.5):
+            pcd, _ = dpj.ray_tracing(d, tm, heat_d, K, thr)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                pcd, _ = dpj.ray_tracing(d, tm, heat_d, K, thr)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            row = {"mesh": mesh, "threshold": thr, "heatmap": "device-resident", "rays": int(dpj.last_result()["n_rays"]),
+                   "hits": len(pcd.points), "ray_tracing_ms_median": float(np.median(ts)), "ray_tracing_ms_min": float(min(ts))}
+            out.append(row)
+            print(json.dumps(row), flush=True)
         # the production pattern: the same model at a new pose on every call (run.py:109-110) -> refit, not rebuild
         moved = []
         for k in range(12):

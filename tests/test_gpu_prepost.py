@@ -101,6 +101,51 @@ def test_heatmap_reader_mirrors_get_heatmap(tmp_path, depth_golden):
     assert again is color_original
 
 
+def test_device_resident_heatmap_gives_the_host_array_result(tmp_path, depth_golden, golden):
+    """HeatmapReader.get_heatmap(device=True) keeps heatmap_full on the GPU (bit-identical to the host version, which is
+    the reference's own cv2 output); ray_tracing() takes that CUDA tensor and returns exactly what it returns for the
+    host array: hit cloud, colours, face ids, pixels, t_hit, posed mesh, accumulators, miss-all LineSet."""
+    import torch
+    from defectproj import defect_projection as dpj
+    from defectproj.datareader import HeatmapReader
+    g = depth_golden
+    os.makedirs(tmp_path / "heatmap")
+    for tag in ("c", "d"):                                          # float64 and float32 raw maps
+        np.save(tmp_path / "heatmap" / "0002.npy", g[f"h_data_{tag}"])
+        cH, cW, ds = (int(v) for v in g[f"h_cfg_{tag}"])
+        rd = HeatmapReader(str(tmp_path), cH, cW, ds)
+        full_h, _, vis_h, _ = rd.get_heatmap()
+        full_d, _, vis_d, _ = rd.get_heatmap(device=True)
+        assert full_d.is_cuda and np.array_equal(full_d.cpu().numpy(), full_h) and np.array_equal(full_h, g[f"h_full_{tag}"])
+        assert np.array_equal(vis_d.cpu().numpy(), vis_h) and vis_d.cpu().numpy().dtype == vis_h.dtype
+    K = golden["g5_K"]
+    synth.write_scene_dir(str(tmp_path), K, (96, 128), color_to_depth=golden["g5_color_to_depth"])
+    mesh = dpj.TriangleMesh(golden["g5_V_depthcam"], golden["g5_F"])
+    for heat in (golden["g2_heat"], golden["g2_heat"].astype(np.float32)):
+        for thr in (0.5, 0.75):
+            a, ma = dpj.ray_tracing(str(tmp_path), mesh, heat, K, heatmap_threshold=thr)
+            la = dict(dpj.last_result())
+            fa = dpj.face_intensities()
+            b, mb = dpj.ray_tracing(str(tmp_path), mesh, torch.from_numpy(heat).cuda(), K, heatmap_threshold=thr)
+            lb = dict(dpj.last_result())
+            fb = dpj.face_intensities()
+            assert len(a.points) == len(b.points) > 0
+            for k in ("points", "colors", "face_ids", "pixels", "t_hit"):
+                assert np.array_equal(getattr(a, k), getattr(b, k)), k
+            assert np.array_equal(ma.vertices, mb.vertices)
+            for k in ("pixel", "intensity", "t_hit", "face", "n_rays", "n_hits"):
+                assert np.array_equal(la[k], lb[k]), k
+            assert la["intensity"].dtype == lb["intensity"].dtype
+            for x, y in zip(fa, fb):
+                assert np.array_equal(x, y)
+    far = dpj.TriangleMesh(golden["g5_V_model"].astype(np.float64) + np.array([5000.0, 0, 0]), golden["g5_F"])
+    ls_h, _ = dpj.ray_tracing(str(tmp_path), far, golden["g2_heat"], K, heatmap_threshold=0.9)
+    ls_d, _ = dpj.ray_tracing(str(tmp_path), far, torch.from_numpy(golden["g2_heat"]).cuda(), K, heatmap_threshold=0.9)
+    assert isinstance(ls_d, dpj.LineSet) and np.array_equal(ls_d.points, ls_h.points) and np.array_equal(ls_d.lines, ls_h.lines)
+    ls_e, _ = dpj.ray_tracing(str(tmp_path), mesh, torch.zeros((96, 128), device="cuda"), K)
+    assert len(ls_e.lines) == 0
+
+
 # ------------------------------------------------------------------------------------------ 8f #2
 def test_colours_equal_reference_create_intersection_pcd(ctx, golden):
     from defectproj import defect_projection as dpj
