@@ -73,6 +73,16 @@ struct dp_ctx {
     size_t accum_bytes = 0;
     RayShard shard;                  // dp_set_ray_shard
 
+    // exchange over peer-mapped memory (peer.cu): the own window, the mapped windows of all ranks, call epochs
+    DevBuf peer_win, peer_out;
+    PeerView peer{};
+    bool peer_exported = false, peer_opened = false;
+    bool peer_ipc[PEER_MAX] = {};
+    size_t peer_stage_bytes = 0, peer_rec_bytes = 0, peer_win_bytes = 0;
+    unsigned long long peer_epoch[2] = {0, 0};
+    int peer_res_slot = -1;          // dp_peer_results: result slot the next ray-sharded dp_project stores into (-1: off)
+    bool peer_res_points = false;
+
     // per-call scratch
     DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, counts, fcounts, xf, stats, jet;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
@@ -195,6 +205,9 @@ void dp_destroy(dp_ctx *ctx)
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
+    dp_peer_close(ctx);
+    ctx->peer_win.release();
+    ctx->peer_out.release();
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->obj_fat, &ctx->cam_fat, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
                       &ctx->accum, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
@@ -246,6 +259,8 @@ int dp_set_mesh(dp_ctx *ctx, const void *V, int vdtype, int64_t nV, const int32_
         ctx->hist.p = ctx->accum.p;
         ctx->fmax.p = ctx->accum.as<char>() + af;
         ctx->vmax.p = ctx->accum.as<char>() + 2 * af;
+        if (ctx->peer_exported && ctx->peer_stage_bytes != 2 * af + av)
+            return fail(ctx, DP_E_STATE, "dp_set_mesh: the exchange window was sized for another mesh (dp_peer_close, then export again)");
         ctx->accum_bytes = 2 * af + av;
     }
     const cudaMemcpyKind kind = mem == DP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -555,6 +570,15 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
         if (out->cap < 0) return fail(ctx, DP_E_ARG, "dp_project: negative capacity");
         if (out->cap < cap) cap = out->cap;
     }
+    const bool peer_mode = ctx->peer_res_slot >= 0 && ctx->peer_opened && ctx->shard.world > 1;
+    if (peer_mode) {
+        if (mem != DP_DEVICE || want_t || want_face || want_pt || want_p64)
+            return fail(ctx, DP_E_ARG, "dp_project: with dp_peer_results the per-ray results live in the exchange window "
+                                       "(device call, no t_hit / face / point / point64 in dp_rays_out)");
+        if (ctx->shard.world != ctx->peer.world || ctx->shard.rank != ctx->peer.rank)
+            return fail(ctx, DP_E_STATE, "dp_project: dp_set_ray_shard and dp_peer_open disagree on (rank, world)");
+        if ((int64_t)ctx->peer.res_cap < cap) cap = (int64_t)ctx->peer.res_cap;
+    }
 
     // per-frame constants (uploaded by the prologue kernel below)
     std::vector<FrameXf> hxf((size_t)(nframes > 0 ? nframes : 1));
@@ -584,6 +608,16 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     if (want_face) { if (own) { CK(ctx->face.ensure((size_t)cap * 4 + 16), "dp_project: face"); d_face = ctx->face.as<int32_t>(); } else d_face = out->face; }
     if (want_p64) { if (own) { CK(ctx->point64.ensure((size_t)cap * 24 + 16), "dp_project: point64"); d_p64 = ctx->point64.as<double>(); } else d_p64 = out->point64; }
     if (want_pt) { if (own) { CK(ctx->point.ensure((size_t)cap * 12 + 16), "dp_project: point"); d_pt = ctx->point.as<float>(); } else d_pt = out->point; }
+    // ray-sharded frame over peer memory: t_hit / face / point live in the exchange windows; this rank's traversal stores
+    // its slice into every rank's arrays (its own window is the local destination) and the call ends with the frame barrier
+    const PeerOut *peer_out = nullptr;
+    if (peer_mode) {
+        char *r = ctx->peer_win.as<char>() + ctx->peer.res_off[ctx->peer_res_slot];
+        d_t = reinterpret_cast<float *>(r);
+        d_face = reinterpret_cast<int32_t *>(r + ctx->peer.res_cap * 4);
+        d_pt = ctx->peer_res_points ? reinterpret_cast<float *>(r + ctx->peer.res_cap * 8) : nullptr;
+        peer_out = ctx->peer_out.as<PeerOut>() + ctx->peer_res_slot;
+    }
 
     CK(ctx->cscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_project: scratch");
     long long *d_counts = ctx->counts.as<long long>();
@@ -654,7 +688,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     Accum acc{ctx->hist.as<int32_t>(), ctx->fmax.as<uint32_t>(), ctx->vmax.as<uint32_t>(), ctx->F.as<int32_t>()};
     const BvhStorage &b = frame == DP_FRAME_OBJECT ? ctx->obj : ctx->cam;
     // t_hit is needed by the hit-point kernel even when the caller does not want it
-    if ((want_pt || want_p64) && !d_t) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
+    if ((want_pt || want_p64) && !d_t && !peer_mode) { CK(ctx->t_hit.ensure((size_t)cap * 4 + 16), "dp_project: t"); d_t = ctx->t_hit.as<float>(); }
     // DP_FUSE_RAYS=0: separate ray-generation and hit-point kernels around the traversal (the round-1 sequence, kept for
     // A/B); default: the traversal generates its rays from the compacted pixels and writes the hit points itself --
     // two launches and the 32-byte ray records (write + read) less per frame
@@ -662,6 +696,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     const char *fuse_env = getenv("DP_FUSE_RAYS");
     const bool fuse = fuse_env ? atoi(fuse_env) != 0 : fuse_default != 0;
     float4 *d_dir4 = nullptr;
+    if (peer_mode && !fuse) return fail(ctx, DP_E_STATE, "dp_project: dp_peer_results needs the fused traversal (DP_FUSE_RAYS=1)");
     if (!fuse) {
         CK(ctx->dir4.ensure((size_t)cap * 32 + 32), "dp_project: rays");
         d_dir4 = ctx->dir4.as<float4>();
@@ -672,8 +707,9 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     CK(launch_trace_pixels(view_of(b), d_dir4, d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
                            d_counts + 1, st, ord_prev, ord_next, s, true, ctx->shard, d_pixel, nframes, fuse ? d_pt : nullptr,
-                           fuse ? d_p64 : nullptr),
+                           fuse ? d_p64 : nullptr, peer_out),
        "dp_project: traversal");
+    if (peer_mode) CK(launch_peer_frame_done(ctx->peer, ++ctx->peer_epoch[1], s), "dp_project: frame barrier");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[3], s), "dp_project");
     if (!fuse)
         CK(launch_points(d_pixel, d_t, d_counts, cap, H, W, ctx->xf.as<FrameXf>(), nframes, d_pt, d_p64, s, n_elems, ctx->shard),
@@ -1056,6 +1092,220 @@ int dp_pack_records(dp_ctx *ctx, const uint32_t *pixel, const float *t_hit, cons
         *m = ctx->h_counts[4];
         if (*m > cap) return fail(ctx, DP_E_NOMEM, "dp_pack_records: capacity too small for the hits");
     }
+    return DP_OK;
+}
+
+// ---- exchange over peer-mapped memory -------------------------------------------------------------------------
+int dp_peer_export(dp_ctx *ctx, int64_t record_bytes, int64_t result_rays, void *handle, int64_t *window_bytes)
+{
+    if (!ctx) return DP_E_ARG;
+    if (record_bytes < 0 || result_rays < 0) return fail(ctx, DP_E_ARG, "dp_peer_export: negative size");
+    if (!ctx->has_mesh) return fail(ctx, DP_E_STATE, "dp_peer_export: no mesh (the window holds accumulator snapshots)");
+    if (ctx->peer_opened) return fail(ctx, DP_E_STATE, "dp_peer_export: windows are open (dp_peer_close first)");
+    DeviceGuard g(ctx->device);
+    const size_t a256 = 255;
+    const size_t stage = (ctx->accum_bytes + a256) & ~a256, rec = ((size_t)record_bytes + a256) & ~a256,
+                 res = ((size_t)result_rays * 20 + a256) & ~a256;
+    size_t off = sizeof(PeerCtl);
+    PeerView &pv = ctx->peer;
+    memset(&pv, 0, sizeof(pv));
+    for (int k = 0; k < 2; ++k) { pv.stage_off[k] = off; off += stage; }
+    for (int k = 0; k < 2; ++k) { pv.rec_off[k] = off; off += rec; }
+    for (int k = 0; k < 2; ++k) { pv.res_off[k] = off; off += res; }
+    pv.res_cap = (unsigned long long)result_rays;
+    // a fresh allocation of its own (cudaMalloc, never sub-allocated): that is what an IPC handle names
+    ctx->peer_win.release();
+    CK(ctx->peer_win.ensure(off), "dp_peer_export: window");
+    CK(cudaMemset(ctx->peer_win.p, 0, off), "dp_peer_export: zero");
+    ctx->peer_stage_bytes = ctx->accum_bytes;
+    ctx->peer_rec_bytes = (size_t)record_bytes;
+    ctx->peer_win_bytes = off;
+    ctx->peer_epoch[0] = ctx->peer_epoch[1] = 0;
+    ctx->peer_exported = true;
+    ctx->peer_res_slot = -1;
+    if (handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == DP_PEER_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->peer_win.p), "dp_peer_export: cudaIpcGetMemHandle");
+        memcpy(handle, &h, sizeof(h));
+    }
+    if (window_bytes) *window_bytes = (int64_t)off;
+    return DP_OK;
+}
+
+static int peer_finish_open(dp_ctx *ctx, int rank, int world)
+{
+    ctx->peer.rank = rank;
+    ctx->peer.world = world;
+    ctx->peer.win[rank] = ctx->peer_win.as<char>();
+    // result arrays of the other ranks, per result slot, for the traversal's epilogue (device table)
+    PeerOut po[2];
+    memset(po, 0, sizeof(po));
+    for (int k = 0; k < 2; ++k) {
+        int n = 0;
+        for (int p = 0; p < world; ++p) {
+            if (p == rank) continue;
+            char *r = ctx->peer.win[p] + ctx->peer.res_off[k];
+            po[k].t_hit[n] = reinterpret_cast<float *>(r);
+            po[k].face[n] = reinterpret_cast<int32_t *>(r + ctx->peer.res_cap * 4);
+            po[k].point[n] = reinterpret_cast<float *>(r + ctx->peer.res_cap * 8);
+            ++n;
+        }
+        po[k].n = n;
+    }
+    CK(ctx->peer_out.ensure(sizeof(po)), "dp_peer_open: table");
+    CK(cudaMemcpy(ctx->peer_out.p, po, sizeof(po), cudaMemcpyHostToDevice), "dp_peer_open: table");
+    ctx->peer_opened = true;
+    return DP_OK;
+}
+
+int dp_peer_open(dp_ctx *ctx, int rank, int world, const void *handles)
+{
+    if (!ctx) return DP_E_ARG;
+    if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world || !handles)
+        return fail(ctx, DP_E_ARG, "dp_peer_open: need 0 <= rank < world <= 16 and the handles of all ranks");
+    if (!ctx->peer_exported) return fail(ctx, DP_E_STATE, "dp_peer_open: dp_peer_export first");
+    if (ctx->peer_opened) return fail(ctx, DP_E_STATE, "dp_peer_open: already open");
+    DeviceGuard g(ctx->device);
+    for (int p = 0; p < world; ++p) {
+        ctx->peer_ipc[p] = false;
+        if (p == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + (size_t)p * DP_PEER_HANDLE_BYTES, sizeof(h));
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < p; ++q)
+                if (ctx->peer_ipc[q]) { cudaIpcCloseMemHandle(ctx->peer.win[q]); ctx->peer_ipc[q] = false; }
+            return fail(ctx, DP_E_CUDA, "dp_peer_open: cudaIpcOpenMemHandle (peer access between the devices of one node is needed)", e);
+        }
+        ctx->peer.win[p] = static_cast<char *>(ptr);
+        ctx->peer_ipc[p] = true;
+    }
+    return peer_finish_open(ctx, rank, world);
+}
+
+int dp_peer_open_local(dp_ctx *ctx, int rank, int world, dp_ctx *const *peers)
+{
+    if (!ctx) return DP_E_ARG;
+    if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world || !peers)
+        return fail(ctx, DP_E_ARG, "dp_peer_open_local: need 0 <= rank < world <= 16 and the contexts of all ranks");
+    if (!ctx->peer_exported) return fail(ctx, DP_E_STATE, "dp_peer_open_local: dp_peer_export first");
+    if (ctx->peer_opened) return fail(ctx, DP_E_STATE, "dp_peer_open_local: already open");
+    DeviceGuard g(ctx->device);
+    for (int p = 0; p < world; ++p) {
+        ctx->peer_ipc[p] = false;
+        if (p == rank) continue;
+        const dp_ctx *o = peers[p];
+        if (!o || !o->peer_exported || o->peer_win_bytes != ctx->peer_win_bytes)
+            return fail(ctx, DP_E_STATE, "dp_peer_open_local: every context needs an exported window of the same layout");
+        if (o->device != ctx->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, o->device), "dp_peer_open_local");
+            if (!can) return fail(ctx, DP_E_CUDA, "dp_peer_open_local: no peer access between the devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "dp_peer_open_local: cudaDeviceEnablePeerAccess", e);
+        }
+        ctx->peer.win[p] = o->peer_win.as<char>();
+    }
+    return peer_finish_open(ctx, rank, world);
+}
+
+int dp_peer_close(dp_ctx *ctx)
+{
+    if (!ctx) return DP_E_ARG;
+    DeviceGuard g(ctx->device);
+    if (ctx->peer_opened) cudaDeviceSynchronize();
+    for (int p = 0; p < PEER_MAX; ++p) {
+        if (ctx->peer_ipc[p]) cudaIpcCloseMemHandle(ctx->peer.win[p]);
+        ctx->peer_ipc[p] = false;
+        ctx->peer.win[p] = nullptr;
+    }
+    ctx->peer_opened = false;
+    ctx->peer_exported = false;     // the window stays allocated until the next export / dp_destroy (peers may still map it)
+    ctx->peer_res_slot = -1;
+    return DP_OK;
+}
+
+int dp_peer_window(dp_ctx *ctx, int what, int slot, void **ptr, int64_t *bytes)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->peer_exported) return fail(ctx, DP_E_STATE, "dp_peer_window: no exchange window");
+    if (slot < 0 || slot > 1) return fail(ctx, DP_E_ARG, "dp_peer_window: slot is 0 or 1");
+    char *w = ctx->peer_win.as<char>();
+    const PeerView &pv = ctx->peer;
+    void *p = nullptr;
+    int64_t b = 0;
+    switch (what) {
+    case DP_PEER_STAGE: p = w + pv.stage_off[slot]; b = (int64_t)ctx->peer_stage_bytes; break;
+    case DP_PEER_RECORDS: p = w + pv.rec_off[slot]; b = (int64_t)ctx->peer_rec_bytes; break;
+    case DP_PEER_REC_COUNT: p = &reinterpret_cast<PeerCtl *>(w)->rec_count[slot]; b = 8; break;
+    case DP_PEER_T_HIT: p = w + pv.res_off[slot]; b = (int64_t)pv.res_cap * 4; break;
+    case DP_PEER_FACE: p = w + pv.res_off[slot] + pv.res_cap * 4; b = (int64_t)pv.res_cap * 4; break;
+    case DP_PEER_POINT: p = w + pv.res_off[slot] + pv.res_cap * 8; b = (int64_t)pv.res_cap * 12; break;
+    default: return fail(ctx, DP_E_ARG, "dp_peer_window: unknown region");
+    }
+    if (ptr) *ptr = p;
+    if (bytes) *bytes = b;
+    return DP_OK;
+}
+
+int dp_peer_snapshot(dp_ctx *ctx, int slot, int reset, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->peer_exported) return fail(ctx, DP_E_STATE, "dp_peer_snapshot: no exchange window");
+    if (slot < 0 || slot > 1) return fail(ctx, DP_E_ARG, "dp_peer_snapshot: slot is 0 or 1");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(launch_vertex_max(ctx->fmax.as<uint32_t>(), ctx->F.as<int32_t>(), ctx->nF, ctx->vmax.as<uint32_t>(), s), "dp_peer_snapshot: vertex maxima");
+    CK(launch_peer_snapshot(ctx->accum.p, ctx->peer_win.as<char>() + ctx->peer.stage_off[slot], ctx->accum_bytes, reset != 0, s),
+       "dp_peer_snapshot: launch");
+    return DP_OK;
+}
+
+int dp_peer_combine(dp_ctx *ctx, int slot, void *total, int gather_root, uint32_t *gathered, int64_t cap_rows, int row_words,
+                    int64_t *m_async, void *stream)
+{
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->peer_opened) return fail(ctx, DP_E_STATE, "dp_peer_combine: windows are not open (dp_peer_open)");
+    if (slot < 0 || slot > 1 || cap_rows < 0 || (gathered && row_words < 1) || gather_root >= ctx->peer.world)
+        return fail(ctx, DP_E_ARG, "dp_peer_combine: bad arguments");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    long long *d_async = nullptr;
+    if (m_async) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, m_async) == cudaSuccess && at.devicePointer) d_async = static_cast<long long *>(at.devicePointer);
+        else { cudaGetLastError(); return fail(ctx, DP_E_ARG, "dp_peer_combine: m_async must be device or pinned host memory"); }
+    }
+    const unsigned long long epoch = ++ctx->peer_epoch[0];
+    CK(launch_peer_combine(ctx->peer, slot, epoch, total, ctx->accum_bytes, (size_t)(ctx->fmax.as<char>() - ctx->accum.as<char>()),
+                           total != nullptr, gather_root, gathered, cap_rows, row_words, nullptr, d_async, s),
+       "dp_peer_combine: launch");
+    return DP_OK;
+}
+
+int dp_peer_results(dp_ctx *ctx, int slot, int with_points)
+{
+    if (!ctx) return DP_E_ARG;
+    if (slot < -1 || slot > 1) return fail(ctx, DP_E_ARG, "dp_peer_results: slot is 0, 1 or -1 (off)");
+    if (slot >= 0 && !ctx->peer_opened) return fail(ctx, DP_E_STATE, "dp_peer_results: windows are not open (dp_peer_open)");
+    if (slot >= 0 && ctx->peer.res_cap == 0) return fail(ctx, DP_E_STATE, "dp_peer_results: the window was exported without result arrays");
+    ctx->peer_res_slot = slot;
+    ctx->peer_res_points = with_points != 0;
+    return DP_OK;
+}
+
+int dp_peer_status(dp_ctx *ctx, int *error)
+{
+    if (!ctx || !error) return DP_E_ARG;
+    *error = 0;
+    if (!ctx->peer_exported) return DP_OK;
+    DeviceGuard g(ctx->device);
+    unsigned e = 0;
+    CK(cudaMemcpy(&e, &ctx->peer_win.as<PeerCtl>()->error, 4, cudaMemcpyDeviceToHost), "dp_peer_status");
+    *error = (int)e;
     return DP_OK;
 }
 

@@ -162,7 +162,8 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
                                 bool counter_zeroed = false, RayShard shard = RayShard(), const uint32_t *pixel = nullptr,
-                                int64_t n_xf = 0, float *point = nullptr, double *point64 = nullptr);
+                                int64_t n_xf = 0, float *point = nullptr, double *point64 = nullptr,
+                                const struct PeerOut *peer_out = nullptr);
 // dir4 == nullptr: the traversal generates the rays itself from pixel[] / xf[] and writes the hit points (point, point64)
 // per-vertex maxima from the per-face maxima (run when the accumulators are read, not per hit)
 cudaError_t launch_vertex_max(const uint32_t *fmax, const int32_t *F, int64_t nF, uint32_t *vmax, cudaStream_t s);
@@ -170,6 +171,40 @@ cudaError_t launch_compute_rays(const int32_t *xs, const int32_t *ys, int64_t n,
                                 cudaStream_t s);
 cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n, float *t_hit, int32_t *face,
                                unsigned long long *work_counter, TraceStats *stats, cudaStream_t s);
+
+// ---- peer.cu: result combination over peer-mapped memory (NVLink / NVSwitch) ---------------------------------
+constexpr int PEER_MAX = 16;           // ranks of one exchange (one node)
+// Head of every rank's exchange window.  flag[c][r]: the last epoch rank r signalled on channel c (0 = batch combine,
+// 1 = ray-sharded frame), written by rank r over NVLink; rec_count[k]: rows in record slot k (written by the owner's
+// k_pack_records); error: set by a wait of this rank that timed out.
+struct PeerCtl {
+    unsigned long long flag[2][PEER_MAX];
+    long long rec_count[2];
+    unsigned error;
+    unsigned pad_[59];
+};
+static_assert(sizeof(PeerCtl) == 512, "control block is 512 bytes");
+// The windows of all ranks as mapped in THIS process (win[rank] = the own one) and the common layout:
+// [PeerCtl | snapshot 0 | snapshot 1 | records 0 | records 1 | results 0 | results 1], results k = t_hit f32 [res_cap] |
+// face i32 [res_cap] | point f32 [res_cap*3].
+struct PeerView {
+    char *win[PEER_MAX];
+    int rank, world;
+    unsigned long long stage_off[2], rec_off[2], res_off[2];
+    unsigned long long res_cap;
+};
+// per-ray result arrays of the OTHER ranks (n entries) for a traversal that stores its slice everywhere
+struct PeerOut {
+    float *t_hit[PEER_MAX];
+    int32_t *face[PEER_MAX];
+    float *point[PEER_MAX];
+    int n;
+};
+cudaError_t launch_peer_snapshot(void *live, void *stage, size_t bytes, bool reset, cudaStream_t s);
+cudaError_t launch_peer_combine(const PeerView &pv, int slot, unsigned long long epoch, void *total, size_t bytes, size_t max_from,
+                                bool fold, int gather_root, uint32_t *gathered, int64_t cap_rows, int row_words, long long *m_out,
+                                long long *m_async, cudaStream_t s);
+cudaError_t launch_peer_frame_done(const PeerView &pv, unsigned long long epoch, cudaStream_t s);
 
 // ---- depth.cu ------------------------------------------------------------------------------
 size_t depth_select_scratch_bytes(int64_t n_elems);

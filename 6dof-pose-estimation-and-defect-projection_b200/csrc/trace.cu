@@ -487,18 +487,39 @@ __device__ __forceinline__ void pixel_ray_object(uint32_t pix, int H, int W, con
 }
 
 // hit point p = d_cam (float64) * t (float32), NaN on a miss  (:261-263 with origin 0; as k_points)
-__device__ __forceinline__ void store_point(long long i, bool hit, float tf, double dcx, double dcy, double dcz,
-                                            float *__restrict__ point, double *__restrict__ point64)
+__device__ __forceinline__ void hit_point(bool hit, float tf, double dcx, double dcy, double dcz, double &px, double &py, double &pz)
 {
-    double px, py, pz;
     if (hit) {
         const double t = (double)tf;
         px = __dmul_rn(dcx, t); py = __dmul_rn(dcy, t); pz = __dmul_rn(dcz, t);
     } else {
         px = py = pz = __longlong_as_double(0x7ff8000000000000ll);
     }
+}
+__device__ __forceinline__ void store_point(long long i, bool hit, float tf, double dcx, double dcy, double dcz,
+                                            float *__restrict__ point, double *__restrict__ point64)
+{
+    double px, py, pz;
+    hit_point(hit, tf, dcx, dcy, dcz, px, py, pz);
     if (point64) { point64[3 * i] = px; point64[3 * i + 1] = py; point64[3 * i + 2] = pz; }
     if (point) { point[3 * i] = (float)px; point[3 * i + 1] = (float)py; point[3 * i + 2] = (float)pz; }
+}
+
+// Ray-sharded frame over peer memory (peer.cu): the ray's results also go into the result arrays of every OTHER rank,
+// mapped into this process (NVLink stores), as the traversal produces them -- the all-gather of the slices is the
+// traversal's own epilogue.  Out of line: a launch without peers never executes it and keeps its registers.
+__device__ __noinline__ void peer_store(const PeerOut *__restrict__ po, long long i, float tb, int bf, bool with_point, double dcx,
+                                        double dcy, double dcz)
+{
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (with_point) hit_point(bf >= 0, tb, dcx, dcy, dcz, px, py, pz);
+    const int n = po->n;
+    for (int p = 0; p < n; ++p) {
+        if (po->t_hit[p]) po->t_hit[p][i] = tb;
+        if (po->face[p]) po->face[p][i] = bf;
+        float *q = po->point[p];
+        if (with_point && q) { q[3 * i] = (float)px; q[3 * i + 1] = (float)py; q[3 * i + 2] = (float)pz; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -542,7 +563,7 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
              float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
              unsigned long long *work_counter, long long *d_hits, TraceStats *stats, uint2 *s_stack, long long s_lo,
              long long s_hi, const uint32_t *__restrict__ pixel, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
-             float *__restrict__ point, double *__restrict__ point64)
+             float *__restrict__ point, double *__restrict__ point64, const PeerOut *__restrict__ peer_out)
 {
     const int lane = threadIdx.x & 31, c = lane & 7, g = lane >> 3;
     const unsigned gmask = 0xffu << (8 * g);
@@ -670,6 +691,7 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
             if (t_hit) t_hit[i] = tb;
             if (face) face[i] = bf;
             if (!dir4 && (point || point64)) store_point(i, bf >= 0, tb, dcx, dcy, dcz, point, point64);
+            if (peer_out) peer_store(peer_out, i, tb, bf, !dir4 && point != nullptr, dcx, dcy, dcz);
             if (STATS) { ++nray; nn += steps_nodes; if (stats->ray_nodes) stats->ray_nodes[i] = steps_nodes; }
             if (bf >= 0) {
                 ++nhit;
@@ -724,7 +746,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
         const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch, int narrow_enabled, int shard_rank,
         int shard_world, const uint32_t *__restrict__ pixel, long long n_xf, float *__restrict__ point,
-        double *__restrict__ point64)
+        double *__restrict__ point64, const PeerOut *__restrict__ peer_out)
 {
     // dir4 == nullptr (SRC 0): rays are generated here from pixel[] and xf[], hit points written here (no k_raygen / k_points)
     // (the learnt packet lists hold packets of the previous launch over the same shard: dp_set_ray_shard drops them)
@@ -747,7 +769,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         // sparse frame: eight lanes per ray (work items come from the second counter)
         static_assert(STACK_SMEM * TR_THREADS >= (NR_THREADS / 8) * NR_STACK, "the narrow path borrows the packet stack");
         trace_narrow<STATS>(nodes, tris, d_scale, dir4, intensity, n, t_hit, face, acc, has_acc, work_counter + 1, d_hits, stats,
-                            s_stack, sh.s_lo, sh.s_hi, pixel, H, W, xf, n_xf, point, point64);
+                            s_stack, sh.s_lo, sh.s_hi, pixel, H, W, xf, n_xf, point, point64, peer_out);
         return;
     }
     const bool tiled = sh.tiled;
@@ -949,6 +971,9 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
             if (want_pts)
                 store_point(slot, bf >= 0, tb, s_dcam[threadIdx.x], s_dcam[TR_THREADS + threadIdx.x], s_dcam[2 * TR_THREADS + threadIdx.x],
                             point, point64);
+            if (SRC == 0 && peer_out != nullptr)
+                peer_store(peer_out, slot, tb, bf, want_pts && point != nullptr, s_dcam[threadIdx.x], s_dcam[TR_THREADS + threadIdx.x],
+                           s_dcam[2 * TR_THREADS + threadIdx.x]);
         }
         const bool hit = valid && bf >= 0;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
@@ -1189,7 +1214,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
                                 bool counter_zeroed, RayShard shard, const uint32_t *pixel, int64_t n_xf, float *point,
-                                double *point64)
+                                double *point64, const PeerOut *peer_out)
 {
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
@@ -1207,7 +1232,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     k_trace<ST, 0, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, \
                                                         n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, \
                                                         d_hits, stats, knob_tiled(), ord_prev, ord_next, pf, narrow, shard.rank, \
-                                                        shard.world, pixel, (long long)n_xf, point, point64)
+                                                        shard.world, pixel, (long long)n_xf, point, point64, peer_out)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG, 0);
@@ -1237,7 +1262,7 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
 #define DP_LAUNCH_TRACE1(ST, MB, FMT)                                                                                          \
     k_trace<ST, 1, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, \
                                                         n, 0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, \
-                                                        nullptr, nullptr, pf, 0, 0, 1, nullptr, 0, nullptr, nullptr)
+                                                        nullptr, nullptr, pf, 0, 0, 1, nullptr, 0, nullptr, nullptr, nullptr)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG, 0);

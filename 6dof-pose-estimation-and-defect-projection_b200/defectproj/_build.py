@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 SO_PATH = os.path.join(_HERE, "libdefectproj.so")
-SOURCES = ["api.cu", "compact.cu", "build.cu", "trace.cu", "depth.cu", "prep.cu", "icp.cu", "normals.cu"]
+SOURCES = ["api.cu", "compact.cu", "build.cu", "trace.cu", "depth.cu", "prep.cu", "icp.cu", "normals.cu", "peer.cu"]
 HEADERS = ["dp_internal.cuh", os.path.join("..", "..", "include", "defectproj.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false"]

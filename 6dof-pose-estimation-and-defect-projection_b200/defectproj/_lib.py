@@ -15,6 +15,8 @@ DP_OK, DP_E_ARG, DP_E_CUDA, DP_E_NOMEM, DP_E_STATE = 0, -1, -2, -3, -4
 DP_HOST, DP_DEVICE = 0, 1
 DP_F32, DP_F64 = 0, 1
 DP_FRAME_OBJECT, DP_FRAME_CAMERA = 0, 1
+DP_PEER_HANDLE_BYTES = 64
+DP_PEER_STAGE, DP_PEER_RECORDS, DP_PEER_REC_COUNT, DP_PEER_T_HIT, DP_PEER_FACE, DP_PEER_POINT = range(6)
 ABI_VERSION = 1
 
 i64, i32, f64, vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
@@ -60,6 +62,15 @@ SYMBOLS = {
     "dp_set_ray_shard": (i32, [vp, i32, i32]),
     "dp_shard_slots": (i32, [i32, i32, i64, i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
     "dp_pack_records": (i32, [vp, vp, vp, vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp, i32, vp]),
+    "dp_peer_export": (i32, [vp, i64, i64, vp, C.POINTER(i64)]),
+    "dp_peer_open": (i32, [vp, i32, i32, vp]),
+    "dp_peer_open_local": (i32, [vp, i32, i32, C.POINTER(vp)]),
+    "dp_peer_close": (i32, [vp]),
+    "dp_peer_window": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]),
+    "dp_peer_snapshot": (i32, [vp, i32, i32, vp]),
+    "dp_peer_combine": (i32, [vp, i32, vp, i32, vp, i64, i32, vp, vp]),
+    "dp_peer_results": (i32, [vp, i32, i32]),
+    "dp_peer_status": (i32, [vp, C.POINTER(i32)]),
     "dp_accum_layout": (i32, [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "dp_icp_point_to_plane": (i32, [vp, vp, i64, vp, vp, i64, f64, vp, i32, f64, f64, vp, C.POINTER(f64), C.POINTER(f64),
                                     C.POINTER(i32), vp, i32, vp]),

@@ -45,6 +45,14 @@ def _frame(frame):
     raise ValueError(f"frame must be 'object' or 'camera', got {frame!r}")
 
 
+class DevView:
+    """__cuda_array_interface__ view of library-owned device memory (no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
 class Context:
     """One dp_ctx: a mesh, its BVH(s), accumulators and scratch on one B200.  Not thread-safe."""
 
@@ -609,6 +617,78 @@ class Context:
                                             _ptr(count_async) if count_async is not None else None, DP_DEVICE,
                                             self._stream(stream)))
         return out[:m.value] if sync else out
+
+    # ------------------------------------------------------------------ exchange over peer-mapped memory (csrc/peer.cu)
+    def peer_export(self, record_bytes: int = 0, result_rays: int = 0):
+        """Allocate this context's exchange window; returns its 64-byte CUDA IPC handle (bytes)."""
+        buf = (C.c_ubyte * _lib.DP_PEER_HANDLE_BYTES)()
+        n = C.c_int64(0)
+        self._check(self._L.dp_peer_export(self._h, int(record_bytes), int(result_rays), buf, C.byref(n)))
+        self.peer_window_bytes = n.value
+        return bytes(buf)
+
+    def peer_open(self, rank: int, world: int, handles):
+        """handles: the handles of all ranks in rank order (bytes of world * 64, or a list of bytes)."""
+        blob = b"".join(handles) if isinstance(handles, (list, tuple)) else bytes(handles)
+        if len(blob) != world * _lib.DP_PEER_HANDLE_BYTES:
+            raise ValueError("peer_open needs one 64-byte handle per rank")
+        self._check(self._L.dp_peer_open(self._h, int(rank), int(world), C.c_char_p(blob)))
+        self.peer_rank, self.peer_world = int(rank), int(world)
+        return self
+
+    def peer_open_local(self, rank: int, contexts):
+        """The same for contexts of this process (a list in rank order; contexts[rank] is self)."""
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        self._check(self._L.dp_peer_open_local(self._h, int(rank), len(contexts), arr))
+        self.peer_rank, self.peer_world = int(rank), len(contexts)
+        return self
+
+    def peer_close(self):
+        self._check(self._L.dp_peer_close(self._h))
+
+    def peer_region(self, what: int, slot: int):
+        """(device address, bytes) of a region of the own window (DP_PEER_* of include/defectproj.h)."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        self._check(self._L.dp_peer_window(self._h, int(what), int(slot), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def peer_tensor(self, what: int, slot: int, row_words: int = 3):
+        """Torch view (no copy) of a region of the own window: snapshot int32 [words]; records int32 [rows, row_words];
+        record count int64 [1]; t_hit float32 [cap]; face int32 [cap]; point float32 [cap, 3]."""
+        import torch
+        ptr, n = self.peer_region(what, slot)
+        dev = f"cuda:{self.device}"
+        if n == 0:
+            return None
+        if what == _lib.DP_PEER_REC_COUNT:
+            return torch.as_tensor(DevView(ptr, 1, "<i8"), device=dev)
+        if what in (_lib.DP_PEER_T_HIT, _lib.DP_PEER_POINT):
+            t = torch.as_tensor(DevView(ptr, n // 4, "<f4"), device=dev)
+            return t.view(-1, 3) if what == _lib.DP_PEER_POINT else t
+        t = torch.as_tensor(DevView(ptr, n // 4, "<i4"), device=dev)
+        if what == _lib.DP_PEER_RECORDS:
+            rows = (n // 4) // row_words
+            return t[:rows * row_words].view(rows, row_words)
+        return t
+
+    def peer_snapshot(self, slot: int, reset: bool = True, stream=None):
+        self._check(self._L.dp_peer_snapshot(self._h, int(slot), int(bool(reset)), self._stream(stream)))
+
+    def peer_combine(self, slot: int, total=None, gather_root: int = -1, gathered=None, count_async=None, stream=None):
+        """ONE launch: barrier over the ranks, totals (+)= / max= every rank's snapshot `slot`, and on rank `gather_root`
+        the record slots of all ranks land in `gathered` (int32 CUDA tensor [cap_rows, row_words]) in rank order;
+        `count_async` (pinned or CUDA int64 [1]) receives the total row count."""
+        rows, words = (gathered.shape[0], gathered.shape[1]) if gathered is not None else (0, 3)
+        self._check(self._L.dp_peer_combine(self._h, int(slot), _ptr(total), int(gather_root), _ptr(gathered), int(rows), int(words),
+                                            _ptr(count_async) if count_async is not None else None, self._stream(stream)))
+
+    def peer_results(self, slot: int = -1, with_points: bool = False):
+        self._check(self._L.dp_peer_results(self._h, int(slot), int(bool(with_points))))
+
+    def peer_status(self):
+        e = C.c_int(0)
+        self._check(self._L.dp_peer_status(self._h, C.byref(e)))
+        return e.value
 
     # ------------------------------------------------------------------ instrumentation
     def set_stats(self, on: bool):

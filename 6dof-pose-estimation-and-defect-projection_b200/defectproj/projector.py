@@ -13,9 +13,9 @@ from __future__ import annotations
 
 import numpy as np
 
-from .core import Context
+from .core import Context, DevView
 
-__all__ = ["Projector", "FrameStream", "BatchCombiner", "shard_range", "combine_accumulators", "combine_block", "fold_block",
+__all__ = ["Projector", "FrameStream", "BatchCombiner", "PeerCombiner", "shard_range", "combine_accumulators", "combine_block", "fold_block",
            "gather_hits", "gather_slices"]
 
 
@@ -146,12 +146,7 @@ def gather_slices(full, ranges, group=None, mine=None, dst=None):
     return full
 
 
-class _DevView:
-    """__cuda_array_interface__ view of library-owned device memory (no copy)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
+_DevView = DevView
 
 
 class BatchCombiner:
@@ -218,6 +213,106 @@ class BatchCombiner:
         return (t[:nF], t[self.f_off:self.f_off + nF].view(torch.float32), t[self.v_off:self.v_off + nV].view(torch.float32))
 
 
+class PeerCombiner:
+    """BatchCombiner over peer-mapped memory (csrc/peer.cu): per batch ONE kernel of the library -- a flag barrier over
+    NVLink, then every rank folds the accumulator snapshots of all ranks into its totals straight out of the peers'
+    memory, and the gathering rank pulls every rank's hit records into one array -- instead of two all-reduces, a count
+    exchange with a host read-back and a padded all-gather.  Same interface and same (bit-identical) totals as
+    BatchCombiner; the process group is only used once, to exchange the 64-byte window handles.
+
+    Slots alternate per batch.  A slot (snapshot + records) may be rewritten once this rank's most recent combine has
+    completed: it passed the barrier every peer enters only after finishing the combine before -- `acquire()` makes the
+    compute stream wait for exactly that (it is long done when batches are longer than a combine)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, group=None, record_rows: int = 0, row_words: int = 3,
+                 result_rays: int = 0, local_contexts=None, handles=None):
+        import torch
+        self.ctx, self.group, self.rank, self.world = ctx, group, int(rank), int(world)
+        self.dev = torch.device(f"cuda:{ctx.device}")
+        self.row_words = int(row_words)
+        base, h_off, f_off, v_off, nbytes = ctx.accum_layout()
+        self.words, self.max_from = nbytes // 4, f_off // 4
+        self.f_off, self.v_off = f_off // 4, v_off // 4
+        self.handle = ctx.peer_export(int(record_rows) * self.row_words * 4, int(result_rays))
+        if local_contexts is None and handles is None:
+            import torch.distributed as dist
+            mine = torch.frombuffer(bytearray(self.handle), dtype=torch.uint8).to(self.dev)
+            allh = torch.empty(world * len(self.handle), dtype=torch.uint8, device=self.dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            handles = bytes(allh.cpu().numpy())
+        self._local = local_contexts
+        if handles is not None:
+            ctx.peer_open(self.rank, self.world, handles)
+        self.total = torch.zeros(self.words, dtype=torch.int32, device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.ev_snap = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.last_done = None
+        self.k = 0
+        self._acquired = None
+        self._rec = [None, None]
+
+    def open_local(self):
+        """second phase for contexts of one process: call after EVERY context has been constructed (exported)"""
+        self.ctx.peer_open_local(self.rank, self._local)
+        return self
+
+    def reset_totals(self, stream=None):
+        import torch
+        stream = stream or torch.cuda.current_stream(self.dev)
+        stream.wait_stream(self.side)
+        with torch.cuda.stream(stream):
+            self.total.zero_()
+
+    def acquire(self, stream=None):
+        """The slot of the batch that is ending; `stream` may write its records and snapshot from here on."""
+        import torch
+        if self._acquired is None:
+            stream = stream or torch.cuda.current_stream(self.dev)
+            if self.last_done is not None:
+                stream.wait_event(self.last_done)
+            self._acquired = self.k
+            self.k ^= 1
+        return self._acquired
+
+    def records(self, slot):
+        """(int32 [rows, row_words] record slot, int64 [1] row count) of the own window: pass them to
+        Context.pack_records_device(out=..., count_async=...) so the batch's hit records are packed in place."""
+        from . import _lib
+        if self._rec[slot] is None:
+            self._rec[slot] = (self.ctx.peer_tensor(_lib.DP_PEER_RECORDS, slot, self.row_words),
+                               self.ctx.peer_tensor(_lib.DP_PEER_REC_COUNT, slot))
+        return self._rec[slot]
+
+    def submit(self, stream=None, reset=True, gather_root=-1, gathered=None, count_async=None):
+        import torch
+        stream = stream or torch.cuda.current_stream(self.dev)
+        k = self.acquire(stream)
+        self._acquired = None
+        self.ctx.peer_snapshot(k, reset, stream)               # vertex maxima + snapshot (+ zero) of the live block
+        self.ev_snap[k].record(stream)
+        self.side.wait_event(self.ev_snap[k])
+        self.ctx.peer_combine(k, self.total, gather_root, gathered if self.rank == gather_root else None, count_async,
+                              stream=self.side)
+        self.ev_done[k].record(self.side)
+        self.last_done = self.ev_done[k]
+        return self
+
+    def result(self, stream=None):
+        import torch
+        stream = stream or torch.cuda.current_stream(self.dev)
+        stream.wait_stream(self.side)
+        nF, nV = self.ctx.nF, self.ctx.nV
+        t = self.total
+        return (t[:nF], t[self.f_off:self.f_off + nF].view(torch.float32), t[self.v_off:self.v_off + nV].view(torch.float32))
+
+    def check(self):
+        """raises if a wait of this rank timed out (a peer never arrived); synchronises"""
+        e = self.ctx.peer_status()
+        if e:
+            raise RuntimeError(f"peer exchange: a wait on channel {e - 1} timed out (a rank did not reach the same call)")
+
+
 class _LazyHits:
     """The shard's hit count of a ray-sharded frame: in pinned memory once the frame's kernels have run (int() waits)."""
 
@@ -228,6 +323,20 @@ class _LazyHits:
         import torch
         torch.cuda.current_stream().synchronize()
         return int(self._cnt[1])
+
+    __index__ = __int__
+
+
+class _LazyCount(_LazyHits):
+    """counts[i] of a frame queued without waiting: int() synchronises the current stream"""
+
+    def __init__(self, cnt, i):
+        self._cnt, self._i = cnt, i
+
+    def __int__(self):
+        import torch
+        torch.cuda.current_stream().synchronize()
+        return int(self._cnt[self._i])
 
     __index__ = __int__
 
@@ -250,7 +359,54 @@ class Projector:
         self.ctx.build_bvh()          # deterministic: every rank builds the identical BVH
         self.nV, self.nF = self.ctx.nV, self.ctx.nF
         self.combiner = BatchCombiner(self.ctx, group)
+        self.peer = None
         self._cnt = None
+        self._res_slot = 0
+        import os
+        if self.world > 1 and os.environ.get("DP_PEER", "1") != "0" and dist.get_backend(group) == "nccl":
+            self.enable_peer()
+
+    def enable_peer(self, record_rows: int = 0, row_words: int = 3, result_rays: int = 0):
+        """(Re)create the exchange windows over peer-mapped memory (collective: every rank calls it with the same sizes).
+        record_rows: capacity of a batch's hit records per rank; result_rays: rays of a ray-sharded frame.  When any rank
+        cannot map its peers (no NVLink / PCIe peer access, ranks on several nodes) every rank keeps the NCCL combiner.
+        Returns True when the peer path is in use."""
+        import torch
+        import torch.distributed as dist
+        if self.world < 2:
+            return False
+        if self.peer is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)                   # nobody still reads a window that is about to go
+            self.peer.ctx.peer_close()
+            dist.barrier(group=self.group)                   # ... and nobody maps a window that is about to be freed
+            self.peer = None
+            self.combiner = BatchCombiner(self.ctx, self.group)
+        ok, comb = 1, None
+        try:
+            comb = PeerCombiner(self.ctx, self.rank, self.world, self.group, record_rows, row_words, result_rays)
+        except Exception as e:                               # DP_E_CUDA: no peer access / IPC unavailable
+            ok, self.peer_error = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{self.device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag[0]) == 1:
+            self.peer = self.combiner = comb
+            return True
+        if comb is not None:
+            comb.ctx.peer_close()
+        return False
+
+    def close(self):
+        """Collective when the peer path is in use: every rank unmaps its peers' windows before any window is freed."""
+        import torch
+        if self.peer is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self.ctx.peer_close()
+            dist.barrier(group=self.group)
+            self.peer = None
+        self.ctx.close()
 
     def accumulators(self):
         """Torch views (no copy) of THIS rank's live hist int32 [nF], fmax float32 [nF], vmax float32 [nV]."""
@@ -317,6 +473,30 @@ class Projector:
         H, W = heat.shape[-2:]
         # the shard stays set between frames (changing it drops the learnt packet schedule); project_batch restores (0, 1)
         ctx.set_ray_shard(self.rank, self.world)
+        if gather == "peer":
+            # the traversal itself stores this rank's slice into the result arrays of EVERY rank (NVLink stores from the
+            # kernel's epilogue) and the call ends with a flag barrier: no collective, no host wait for the ray count.
+            # `out` (a dict) receives views of this rank's result slot: whole-frame t_hit / face (/ point) once the
+            # stream has passed the call.  Slots alternate per frame (a frame's arrays live until the frame after next).
+            from . import _lib
+            if self.peer is None or self.world < 2:
+                raise RuntimeError("gather='peer' needs enable_peer(result_rays=...) on every rank")
+            slot = self._res_slot
+            self._res_slot ^= 1
+            with_points = out is not None and "point" in out
+            ctx.peer_results(slot, with_points)
+            if self._cnt is None:
+                self._cnt = torch.zeros(2, dtype=torch.int64).pin_memory()
+            ctx.project_device(heat, K, np.asarray(pose, np.float64).reshape(1, 4, 4), thr, "object", True,
+                               out={"counts": self._cnt}, sync=False)
+            if out is not None:
+                out["t_hit"] = ctx.peer_tensor(_lib.DP_PEER_T_HIT, slot)
+                out["face"] = ctx.peer_tensor(_lib.DP_PEER_FACE, slot)
+                if with_points:
+                    out["point"] = ctx.peer_tensor(_lib.DP_PEER_POINT, slot)
+            if reduce:
+                self.combiner.submit(reset=True)
+            return _LazyCount(self._cnt, 0), _LazyCount(self._cnt, 1), None
         # the ray count arrives in pinned memory straight from the compaction kernel: the host sizes and queues the slice
         # gathers while the traversal still runs, and never waits for the frame
         if self._cnt is None:

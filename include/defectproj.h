@@ -259,6 +259,54 @@ DP_API int dp_pack_records(dp_ctx *ctx, const uint32_t *pixel, const float *t_hi
                            int64_t n, int64_t first, uint32_t *records, int64_t cap, int64_t *m, int64_t *m_async, int mem,
                            void *stream);
 
+/* ---- multi-GPU: result exchange over peer-mapped memory (NVLink / NVSwitch) ---------------------
+ * One process per GPU on one node.  The data path has no exchange step; what travels are RESULTS: per batch the
+ * accumulator block (hist SUM, fmax | vmax MAX) and the compacted hit records, per ray-sharded frame the slices of the
+ * per-ray arrays.  Instead of collectives (two all-reduces, a count exchange with a host read-back and a padded
+ * all-gather per batch; one all-gather per array and frame) every rank maps every other rank's EXCHANGE WINDOW
+ *     [control | accumulator snapshot x2 | hit records x2 | per-ray results x2 (t_hit f32, face i32, point f32 x3)]
+ * and the library's own kernels read / write the peers' memory directly:
+ *   dp_peer_combine   ONE launch per batch: flag barrier, then every rank folds the snapshots of all ranks into its
+ *                     running totals straight out of the peers' memory, and rank `gather_root` pulls all ranks' hit
+ *                     records into one array in rank order (the counts are read on the device, never on the host);
+ *   dp_project        after dp_peer_results(slot): the traversal stores its slice of t_hit / face / point into the result
+ *                     arrays of EVERY rank as it produces them (the gather is the kernel's epilogue), then one tiny
+ *                     barrier launch; when it has run, this rank's result slot holds the whole frame.
+ * Integer sums and float maxima do not depend on the order: N GPUs give the 1-GPU result bit for bit.
+ * All ranks must issue the same sequence of dp_peer_combine calls, and of ray-sharded dp_project calls (collective
+ * semantics); slots alternate 0, 1, 0, ... per channel, which is what makes reuse safe without a second barrier.  A wait
+ * that sees no progress for 4 s gives up and sets the error word (dp_peer_status) instead of hanging the GPU. */
+#define DP_PEER_HANDLE_BYTES 64
+enum { DP_PEER_STAGE = 0, DP_PEER_RECORDS = 1, DP_PEER_REC_COUNT = 2, DP_PEER_T_HIT = 3, DP_PEER_FACE = 4, DP_PEER_POINT = 5 };
+/* Allocate this context's window (snapshots sized by the current mesh, `record_bytes` per record slot, `result_rays`
+ * rays per result slot; either may be 0) and write its CUDA IPC handle (DP_PEER_HANDLE_BYTES) to `handle` (HOST; may be
+ * NULL for dp_peer_open_local).  The caller exchanges the handles (e.g. one 64-byte all-gather at start-up). */
+DP_API int dp_peer_export(dp_ctx *ctx, int64_t record_bytes, int64_t result_rays, void *handle, int64_t *window_bytes);
+/* Map the windows of all ranks: handles [world * DP_PEER_HANDLE_BYTES] in rank order (the own entry is ignored).
+ * Every rank must have exported with the same sizes.  Fails with DP_E_CUDA when the devices have no peer access. */
+DP_API int dp_peer_open(dp_ctx *ctx, int rank, int world, const void *handles);
+/* The same for contexts of ONE process (one thread driving several GPUs, or several contexts on one GPU in the tests):
+ * peers [world] contexts in rank order. */
+DP_API int dp_peer_open_local(dp_ctx *ctx, int rank, int world, dp_ctx *const *peers);
+DP_API int dp_peer_close(dp_ctx *ctx);
+/* device address / size of a region of the OWN window: DP_PEER_STAGE (snapshot `slot`), DP_PEER_RECORDS (record slot; pass
+ * it as `records` to dp_pack_records), DP_PEER_REC_COUNT (int64 row count of the slot; pass it as `m_async`),
+ * DP_PEER_T_HIT / FACE / POINT (result slot: the whole frame after a ray-sharded dp_project) */
+DP_API int dp_peer_window(dp_ctx *ctx, int what, int slot, void **ptr, int64_t *bytes);
+/* the accumulator block (per-vertex maxima brought up to date first) -> snapshot `slot`; reset != 0 zeroes the live block */
+DP_API int dp_peer_snapshot(dp_ctx *ctx, int slot, int reset, void *stream);
+/* total: device int32 [accumulator block words] running totals of this rank (+= / max= the snapshots `slot` of all ranks;
+ * NULL skips the fold).  gathered (device, on rank gather_root only; gather_root < 0: nobody gathers): [cap_rows *
+ * row_words] uint32 rows, the record slots `slot` of all ranks in rank order; m_async (device or pinned host): the total
+ * row count (rows beyond cap_rows are dropped).  Asynchronous on `stream`. */
+DP_API int dp_peer_combine(dp_ctx *ctx, int slot, void *total, int gather_root, uint32_t *gathered, int64_t cap_rows,
+                           int row_words, int64_t *m_async, void *stream);
+/* slot 0 / 1: the following ray-sharded dp_project calls (dp_set_ray_shard with world > 1, DP_DEVICE, no t_hit / face /
+ * point in dp_rays_out) keep their per-ray results in result slot `slot` of the windows of ALL ranks; -1: off. */
+DP_API int dp_peer_results(dp_ctx *ctx, int slot, int with_points);
+/* *error: 0, or 1 + channel of a wait of this rank that timed out (synchronises with the device) */
+DP_API int dp_peer_status(dp_ctx *ctx, int *error);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* enable != 0: the next traversal launches use the counting variant of the kernel */
 DP_API int dp_set_stats(dp_ctx *ctx, int enable);
