@@ -497,6 +497,8 @@ class Projector:
             if reduce:
                 self.combiner.submit(reset=True)
             return _LazyCount(self._cnt, 0), _LazyCount(self._cnt, 1), None
+        if self.peer is not None:
+            ctx.peer_results(-1)                 # the caller's `out` tensors receive the results (collective gathers below)
         # the ray count arrives in pinned memory straight from the compaction kernel: the host sizes and queues the slice
         # gathers while the traversal still runs, and never waits for the frame
         if self._cnt is None:

@@ -420,6 +420,47 @@ def strong_scaling(mesh, rank, world, local, steps, flush):
     heat = torch.ones((H, W), dtype=torch.float32, device=dev)
     out = dict(t_hit=torch.empty(n_pix, device=dev), face=torch.empty(n_pix, dtype=torch.int32, device=dev))
     poses = [frame_pose(i) for i in range(steps + 3)]            # the SAME frame on every rank
+    # peer-mapped result windows: the traversal stores its slice into every rank's arrays, no collective per frame
+    peer = world > 1 and proj.peer is not None and proj.enable_peer(result_rays=n_pix)
+    peer_res = None
+    if peer:
+        pout = {}
+        for i in range(3):
+            proj.project_frame_sharded(heat, K, poses[i], THR, out=pout, gather="peer", reduce=False, reset=False)
+        torch.cuda.synchronize()
+        dist.barrier()
+        pms = []
+        for i in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            pn, ph, _ = proj.project_frame_sharded(heat, K, poses[3 + i], THR, out=pout, gather="peer", reduce=False, reset=False)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            pms.append(e0.elapsed_time(e1))
+        # the same frames as a sequence: nothing waits between frames (slots alternate), one event pair around all of them
+        dist.barrier()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for i in range(steps):
+            proj.project_frame_sharded(heat, K, poses[3 + i], THR, out=pout, gather="peer", reduce=False, reset=False)
+        p1.record(stream)
+        torch.cuda.synchronize()
+        seq_ms = p0.elapsed_time(p1) / steps
+        ref_face = torch.empty(n_pix, dtype=torch.int32, device=dev)       # the last frame, unsharded, on this rank
+        proj.ctx.set_ray_shard(0, 1)
+        proj.ctx.project_device(heat[None], K, poses[3 + steps - 1][None], THR, "object", False, out=dict(face=ref_face), sync=True)
+        same = bool(torch.equal(ref_face, pout["face"][:n_pix])) and proj.ctx.peer_status() == 0
+        tt = torch.tensor([float(np.mean(pms)), seq_ms, 0.0 if same else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        peer_res = {"ms_per_frame": float(tt[0]), "mrays_s": n_pix / float(tt[0]) / 1e3, "sequence_ms_per_frame": float(tt[1]),
+                    "sequence_mrays_s": n_pix / float(tt[1]) / 1e3, "whole_frame_on_every_rank_equals_unsharded": float(tt[2]) == 0.0,
+                    "how": "csrc/peer.cu: k_trace stores its slice of t_hit / face into the result window of EVERY rank (NVLink "
+                           "stores from the traversal's epilogue), then a one-warp flag barrier; no collective, no host wait"}
+        proj.ctx.accum_reset(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
     for i in range(3):
         proj.project_frame_sharded(heat, K, poses[i], THR, out=out, reduce=False, reset=False)
     proj.combiner.submit()
@@ -478,8 +519,9 @@ def strong_scaling(mesh, rank, world, local, steps, flush):
     pm = float(t[2]) if pipelined_ms else None
     h = int(hl[0]) // steps
     ok = int(hist.sum().item()) == int(hl[0]) and h == int((out["face"][:n] >= 0).sum().item())
-    proj.ctx.close()
+    proj.close()
     return {"triangles": len(F), "rays_per_frame": n, "hits": h, "ms_per_frame": float(t[0]), "mrays_s": n / float(t[0]) / 1e3,
+            "peer": peer_res,
             "combine_ms_per_batch": float(t[1]), "frames": steps,
             "pipelined_ms_per_frame": pm, "pipelined_mrays_s": (n / pm / 1e3) if pm else None,
             "slots_of_rank0": list(rng) if rank == 0 else None, "hist_total_equals_hits_equals_gathered_faces": bool(ok),
@@ -545,27 +587,31 @@ def run_ours(args):
     rec_cnt = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
     ev_pack = [torch.cuda.Event() for _ in range(2)]
     gathered = [0]
+    # peer-mapped exchange windows (csrc/peer.cu): the per-batch combine is ONE kernel of the library per rank
+    peer = world > 1 and proj.peer is not None and proj.enable_peer(record_rows=n_pix)
+    comb = proj.combiner
+    peer_gathered = torch.empty((world * n_pix, 3), dtype=torch.int32, device=dev) if peer and rank == 0 else None
+    peer_rows = torch.zeros(1, dtype=torch.int64).pin_memory()
 
-    skew_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-    skew_t = torch.zeros(1, dtype=torch.int32, device=dev)
-
-    def batch_end(b, probe_skew=False):
+    def batch_end(b):
         """compute stream: hit records of the batch's last frame + accumulator snapshot; the reductions go to the side stream"""
+        if peer:
+            k = comb.acquire(stream)
+            rec, cnt = comb.records(k)
+            ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec, count_async=cnt,
+                                    sync=False, stream=stream)
+            comb.submit(stream, gather_root=0, gathered=peer_gathered, count_async=peer_rows)
+            return
         k = b & 1
         ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec_buf[k], count_async=rec_cnt[k],
                                 sync=False, stream=stream)
         ev_pack[k].record(stream)
-        if probe_skew and world > 1:
-            # how long this rank waits for the slowest one: a 4-byte all-reduce right behind this rank's last kernel
-            with torch.cuda.stream(comb.side):
-                comb.side.wait_event(ev_pack[k])
-                skew_ev[0].record(comb.side)
-                dist.all_reduce(skew_t)
-                skew_ev[1].record(comb.side)
         comb.submit(stream)
 
     def batch_gather(b):
         """side stream: the batch's hit records to rank 0, unpadded (the host reads the record count first)"""
+        if peer:
+            return                           # the records were pulled by rank 0's combine kernel
         k = b & 1
         ev_pack[k].synchronize()
         m = int(rec_cnt[k][0])
@@ -607,7 +653,7 @@ def run_ours(args):
             step_device(args.warmup + i)
             last_of_batch = i == bounds[b + 1] - 1
             if last_of_batch:
-                batch_end(b, probe_skew=(b == nb_batches - 1))   # inside the step's event pair: pack + vertex maxima + snapshot
+                batch_end(b)                 # inside the step's event pair: pack + vertex maxima + snapshot
             ev[i][1].record(stream)
             if sampled:
                 # kernel-only duration of the traversal launch of this step
@@ -623,8 +669,11 @@ def run_ours(args):
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     tail_ms = ev[-1][1].elapsed_time(ev_tail)
-    skew_ms = skew_ev[0].elapsed_time(skew_ev[1]) if world > 1 else 0.0
     total_ms = float(sum(step_ms)) + tail_ms
+    frames_ms = float(sum(step_ms))              # this rank's own frames; the spread over the ranks is what the tail waits for
+    if peer:
+        comb.check()
+        gathered[0] = int(peer_rows[0])
     hist_t, fmax_t, vmax_t = comb.result()
     hist_total = int(hist_t.sum().item())                         # all ranks, all batches
     hits_sum = torch.tensor([0], dtype=torch.int64, device=dev)
@@ -637,14 +686,38 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         e0.record(stream)
-        comb.submit(stream, reset=False)
-        stream.wait_stream(comb.side)
-        e1.record(stream)
-        rec = ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec_buf[0], stream=stream)
-        gather_hits(rec, dst=0)
+        if peer:
+            k = comb.acquire(stream)
+            rec, cnt = comb.records(k)
+            ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec, count_async=cnt, sync=False, stream=stream)
+            comb.submit(stream, reset=False, gather_root=0, gathered=peer_gathered, count_async=peer_rows)
+            stream.wait_stream(comb.side)
+            e1.record(stream)
+        else:
+            comb.submit(stream, reset=False)
+            stream.wait_stream(comb.side)
+            e1.record(stream)
+            rec = ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec_buf[0], stream=stream)
+            gather_hits(rec, dst=0)
         e2.record(stream)
         torch.cuda.synchronize()
         serial_reduce_ms, serial_gather_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    nccl_reduce_ms = nccl_gather_ms = None
+    if peer:
+        # the same combine through NCCL (two all-reduces; count exchange + all-gather of the records), for comparison
+        from defectproj.projector import BatchCombiner
+        nccl = BatchCombiner(ctx, None)
+        for rep in range(3):
+            dist.barrier()
+            e0.record(stream)
+            nccl.submit(stream, reset=False)
+            stream.wait_stream(nccl.side)
+            e1.record(stream)
+            rec = ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n_rays, out=rec_buf[0], stream=stream)
+            gather_hits(rec, dst=0)
+            e2.record(stream)
+            torch.cuda.synchronize()
+            nccl_reduce_ms, nccl_gather_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
 
     # -- end to end through the host-buffer API (defectproj.FrameStream -> dp_project): every frame's heatmap comes from
     #    pinned host memory and its per-ray results + counts go back to pinned host memory; H2D(i+1) | kernels(i) |
@@ -696,12 +769,15 @@ def run_ours(args):
     # -- max over ranks
     keys = list(modes)
     if world > 1:
-        t = torch.tensor([total_ms, tail_ms, serial_reduce_ms, serial_gather_ms, skew_ms] + [e2e[k]["ms"] for k in keys],
-                         dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, tail_ms, serial_reduce_ms, serial_gather_ms, frames_ms, -frames_ms, nccl_reduce_ms or 0.0,
+                          nccl_gather_ms or 0.0] + [e2e[k]["ms"] for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, tail_ms, serial_reduce_ms, serial_gather_ms, skew_ms = (float(x) for x in t[:5])
+        total_ms, tail_ms, serial_reduce_ms, serial_gather_ms = (float(x) for x in t[:4])
+        skew_ms = float(t[4]) + float(t[5])          # slowest rank's frames - fastest rank's frames
+        if peer:
+            nccl_reduce_ms, nccl_gather_ms = float(t[6]), float(t[7])
         for j, k in enumerate(keys):
-            e2e[k]["ms"] = float(t[5 + j])
+            e2e[k]["ms"] = float(t[8 + j])
         c = torch.tensor([n_rays * args.steps, n_hits * 0] + [e2e[k]["rays"] for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         rays_total = float(c[0])
@@ -710,6 +786,7 @@ def run_ours(args):
         # hits of every frame of every rank (the dense fill-frame: one count per step, read from the library)
         hits_sum[0] = int(hist_total)
     else:
+        skew_ms = 0.0
         rays_total = float(n_rays * args.steps)
         for k in keys:
             e2e[k]["rays_total"] = float(e2e[k]["rays"])
@@ -760,8 +837,9 @@ def run_ours(args):
                                "heatmap f32 in; pinned host memory",
                     "modes": {k: e2e_entry(k) for k in keys}},
             # k_project_prologue, k_compact, k_trace per frame (rays and hit points are generated inside k_trace; with
-            # DP_FUSE_RAYS=0 also k_raygen and k_points); k_pack_records, k_vertex_max + the snapshot copy per batch
-            "gpu_launches": (3 if os.environ.get("DP_FUSE_RAYS", "1") != "0" else 5) * args.steps + 3 * nb_batches,
+            # DP_FUSE_RAYS=0 also k_raygen and k_points); per batch k_pack_records, k_vertex_max, and k_peer_snapshot +
+            # k_peer_combine (peer path) or a snapshot copy followed by NCCL's kernels
+            "gpu_launches": (3 if os.environ.get("DP_FUSE_RAYS", "1") != "0" else 5) * args.steps + (4 if peer else 3) * nb_batches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
                          "kernel": "k_trace<false,0,%d,%d>" % ((6, 1) if nb == B_NODE_FAT else (7, 0)), "kernel_ms": k_ms,
@@ -776,16 +854,22 @@ def run_ours(args):
             "ms_per_frame": total_ms / args.steps,
             "bvh": {"build_ms": st2["last_build_ms"], "wide_nodes": st2["n_wide_nodes"], "depth": st2["wide_depth"],
                     "bytes": st2["n_wide_nodes"] * nb + st2["n_tris"] * B_TRI},
-            "combine": {"batches": nb_batches, "exposed_tail_ms": tail_ms, "wait_slowest_rank_ms": skew_ms,
+            "combine": {"batches": nb_batches, "path": "peer memory (csrc/peer.cu)" if peer else ("nccl" if world > 1 else "local"),
+                        "exposed_tail_ms": tail_ms, "rank_spread_of_frames_ms": skew_ms,
                         "serial_reduce_ms": serial_reduce_ms, "serial_gather_ms": serial_gather_ms,
-                        "what": "per batch: k_pack_records (hit records of the batch's last frame) + k_vertex_max + ONE "
-                                "snapshot copy of the accumulator block inside the last step's event pair; on a side stream: "
-                                "all_reduce SUM (hist) + ONE all_reduce MAX (fmax|vmax) of the snapshot, count exchange, "
-                                "unpadded gather of the records to rank 0.  Batch b's side-stream work overlaps batch b+1's "
-                                "frames; the last batch's is the exposed tail (inside the timed total).  wait_slowest_rank_ms: a "
-                                "4-byte all-reduce right behind the last kernel of the run, as seen by the rank that waits longest "
-                                "(part of the tail).  serial_*: the same "
-                                "reduce / pack+gather run serially after the timed region (includes waiting for the slowest rank)",
+                        "nccl_serial_reduce_ms": nccl_reduce_ms, "nccl_serial_gather_ms": nccl_gather_ms,
+                        "what": "per batch, inside the last step's event pair: k_pack_records (hit records of the batch's last "
+                                "frame) + k_vertex_max + ONE snapshot of the accumulator block.  Then, on a side stream, path "
+                                "'peer memory': ONE kernel per rank (k_peer_combine: flag barrier over NVLink, every rank folds "
+                                "the snapshots of all ranks into its totals straight out of the peers' memory -- SUM over the "
+                                "histogram words, MAX over the float bits of fmax | vmax --, rank 0 pulls every rank's records in "
+                                "rank order; the counts are read on the device); path 'nccl': all_reduce SUM + ONE all_reduce MAX "
+                                "of the snapshot, count exchange with a host read, all-gather of the records.  Batch b's "
+                                "side-stream work overlaps batch b+1's frames; the last batch's is the exposed tail (inside the "
+                                "timed total).  rank_spread_of_frames_ms: slowest minus fastest rank's own frames (the tail "
+                                "includes waiting for the slowest rank).  serial_*: pack + snapshot + combine (e0..e1) and what "
+                                "follows (e1..e2) run serially after the timed region; nccl_serial_*: the same work through the "
+                                "NCCL path on the same ranks, for comparison",
                         "hit_records_gathered": gathered[0]},
             "checks": {"rays_per_frame": n_rays, "hits_per_frame": n_hits, "hist_total_all_ranks": hist_total,
                        "hits_reported_all_ranks": int(hits_reported[0]),
@@ -812,6 +896,7 @@ def run_ours(args):
                           f"vertex posing + BVH build (per call, as the reference) + rays + closest hit + accumulation; "
                           f"cast-only {cb['rays'] / cb['cast_seconds'] / 1e6:.2f} Mrays/s; ms/frame {1e3 * cb['seconds'] / cb['frames']:.1f}"}
         print(json.dumps(line), flush=True)
+    proj.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
