@@ -84,7 +84,7 @@ struct dp_ctx {
     bool peer_res_points = false;
 
     // per-call scratch
-    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, counts, fcounts, xf, stats, jet;
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, pscratch, counts, fcounts, xf, stats, jet;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
     const void *counts_alias_src = nullptr;   // last dp_rays_out.counts address and its device alias
     long long *counts_alias = nullptr;
@@ -211,7 +211,7 @@ void dp_destroy(dp_ctx *ctx)
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->obj_fat, &ctx->cam_fat, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
                       &ctx->accum, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
-                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
+                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->pscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats, &ctx->jet};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : ctx->tmp) b.release();
@@ -619,7 +619,20 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
         peer_out = ctx->peer_out.as<PeerOut>() + ctx->peer_res_slot;
     }
 
-    CK(ctx->cscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_project: scratch");
+    // <= 8 frames: the compaction launch does the call's resets and uploads itself and leaves its scratch clean (a buffer
+    // of its own, zeroed when it is allocated); larger batches go through the prologue launch
+    static const bool fused_knob = [] { const char *e = getenv("DP_FUSED_PROLOGUE"); return e ? atoi(e) != 0 : true; }();
+    const bool fused_prologue = fused_knob && n_elems > 0 && nframes <= 8;
+    if (fused_prologue) {
+        const size_t before = ctx->pscratch.cap;            // (a re-allocation may return the same address)
+        CK(ctx->pscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_project: scratch");
+        if (ctx->pscratch.cap != before) {
+            CK(cudaMemsetAsync(ctx->pscratch.p, 0, ctx->pscratch.cap, s), "dp_project: scratch");
+            CK(cudaMemsetAsync(ctx->counts.p, 0, 32, s), "dp_project: counts");
+        }
+    } else {
+        CK(ctx->cscratch.ensure(compact_scratch_bytes(n_elems) + 64), "dp_project: scratch");
+    }
     long long *d_counts = ctx->counts.as<long long>();
     // packet schedule: read the state the previous call wrote, write the other one (double buffer)
     const OrderState *ord_prev = nullptr;
@@ -652,9 +665,10 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     }
     // one launch resets the counts, the traversal work counter, the compaction scratch and the schedule state this
     // call will write, and uploads the per-frame constants: no copy-engine work in the kernel stream
-    CK(launch_project_prologue(ctx->cscratch.as<unsigned long long>(), n_elems, d_counts, ord_next, ctx->xf.as<FrameXf>(),
-                               hxf.data(), nframes, s),
-       "dp_project: prologue");
+    if (!fused_prologue)
+        CK(launch_project_prologue(ctx->cscratch.as<unsigned long long>(), n_elems, d_counts, ord_next, ctx->xf.as<FrameXf>(),
+                                   hxf.data(), nframes, s),
+           "dp_project: prologue");
     // out->counts in pinned host memory: the ray count is stored there by the compaction itself (early), both counts at
     // the end of the call
     long long *early_n = nullptr;
@@ -670,9 +684,14 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
         }
         early_n = ctx->counts_alias;
     }
-    CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
-                      ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s, true, early_n),
-       "dp_project: compaction");
+    if (fused_prologue)
+        CK(launch_compact_fused(d_heat, dtype, n_elems, thr, d_pixel, d_int, cap, ctx->pscratch.as<unsigned long long>(), d_counts,
+                                ord_next, ctx->xf.as<FrameXf>(), hxf.data(), (int)nframes, early_n, s),
+           "dp_project: compaction");
+    else
+        CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
+                          ctx->cscratch.as<unsigned long long>(), d_counts, nullptr, nframes, s, true, early_n),
+           "dp_project: compaction");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[1], s), "dp_project");
 
     TraceStats *st = nullptr;

@@ -11,12 +11,17 @@
 // waiting tile only ever waits for a tile that is already running).
 #include "dp_internal.cuh"
 
+#include <string.h>
+
 namespace dp {
 
 namespace {
 
 constexpr int CT_THREADS = 256;
-constexpr int CT_CHUNKS = 4;                       // 16-byte (f32) / 32-byte (f64) loads per thread
+#ifndef DP_CT_CHUNKS
+#define DP_CT_CHUNKS 4
+#endif
+constexpr int CT_CHUNKS = DP_CT_CHUNKS;            // 16-byte (f32) / 32-byte (f64) loads per thread
 constexpr int CT_TILE = CT_THREADS * CT_CHUNKS * 4;  // 4096 pixels per tile
 
 
@@ -38,10 +43,10 @@ __device__ __forceinline__ void load4(const double *p, Vec4<double> &o)
 }
 
 template <typename T>
-__global__ void __launch_bounds__(CT_THREADS)
-k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
-          float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *d_count, long long *early_n,
-          int aligned)
+__device__ __forceinline__ void
+compact_tile(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
+             float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *d_count, long long *early_n,
+             int aligned)
 {
     __shared__ unsigned s_tile;
     __shared__ unsigned s_warp_tot[CT_CHUNKS * (CT_THREADS / 32)];
@@ -86,16 +91,23 @@ k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__
     }
     __syncthreads();
     if (warp == 0) {
-        // 32 partial counts in pixel order (chunk-major, then warp): exclusive scan by shuffles
-        const unsigned x = s_warp_tot[lane];
-        unsigned inc = x;
+        // the partial counts in pixel order (chunk-major, then warp), 32 at a time: exclusive scan by shuffles
+        constexpr int NPART = CT_CHUNKS * (CT_THREADS / 32);
+        static_assert(NPART % 32 == 0, "partial counts come in groups of 32");
+        unsigned carry = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += y;
+        for (int g = 0; g < NPART; g += 32) {
+            const unsigned x = s_warp_tot[g + lane];
+            unsigned inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            s_warp_off[g + lane] = carry + inc - x;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        s_warp_off[lane] = inc - x;
-        if (lane == 31) s_block_total = inc;
+        if (lane == 31) s_block_total = carry;
     }
     __syncthreads();
     if (warp == 0) {
@@ -131,6 +143,45 @@ k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+k_compact(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
+          float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *d_count, long long *early_n,
+          int aligned)
+{
+    compact_tile<T>(heat, n, thr, pixel, intensity, cap, scratch, d_count, early_n, aligned);
+}
+
+struct XfPack {
+    FrameXf f[8];
+};
+
+// The compaction of dp_project: the same tiles, plus the call's resets and uploads (see launch_compact_fused).
+// scratch: [0] tile ticket, [1 .. ntiles] look-back states, [ntiles + 1] finished tiles.
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+k_compact_project(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
+                  float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *counts,
+                  long long *early_n, int aligned, OrderState *ord_next, FrameXf *xf, int n_xf, const __grid_constant__ XfPack pack)
+{
+    __shared__ int s_last;
+    if (blockIdx.x == 0 && (int)threadIdx.x < 16 * n_xf) xf[threadIdx.x >> 4].v[threadIdx.x & 15] = pack.f[threadIdx.x >> 4].v[threadIdx.x & 15];
+    compact_tile<T>(heat, n, thr, pixel, intensity, cap, scratch, counts, early_n, aligned);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned *>(scratch + gridDim.x + 1), 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // every tile has published, read and scattered: the scratch and the traversal's counters start the next phase at zero
+    for (unsigned i = threadIdx.x; i < gridDim.x + 2; i += blockDim.x) scratch[i] = 0ull;
+    if (threadIdx.x < 3) counts[1 + threadIdx.x] = 0;
+    if (threadIdx.x == 3 && ord_next) {
+        ord_next->n_valid = -1; ord_next->cost_sum = 0; ord_next->cnt[0] = 0; ord_next->cnt[1] = 0; ord_next->cnt[2] = 0;
+    }
+}
+
 // per-frame counts from the sorted pixel list: count[f] = lb((f+1)*HW) - lb(f*HW)
 __global__ void k_frame_counts(const uint32_t *__restrict__ pixel, const long long *d_count, long long cap,
                                long long frame_elems, long long nframes, long long *frame_count)
@@ -158,10 +209,6 @@ __global__ void k_frame_counts(const uint32_t *__restrict__ pixel, const long lo
 // a cudaMemsetAsync / small cudaMemcpyAsync in the kernel stream queues behind the bulk H2D / D2H transfers of a
 // pipelined caller (measured on B200: compaction 0.02 -> 0.1-0.3 ms, ray generation 0.02 -> 0.09-0.25 ms with a
 // 12.6 MB copy in flight on another stream).
-struct XfPack {
-    FrameXf f[8];
-};
-
 __global__ void __launch_bounds__(256)
 k_project_prologue(unsigned long long *scratch, long long scratch_words, long long *counts, OrderState *ord_next,
                    FrameXf *xf, int n_xf, XfPack pack)
@@ -217,6 +264,26 @@ cudaError_t launch_project_prologue(unsigned long long *scratch, int64_t n_elems
         }
     }
     return e;
+}
+
+cudaError_t launch_compact_fused(const void *heat, int dtype, int64_t n_elems, double thr, uint32_t *pixel, float *intensity,
+                                 int64_t cap, unsigned long long *scratch, long long *counts, OrderState *ord_next,
+                                 FrameXf *d_xf, const FrameXf *h_xf, int n_xf, long long *early_n, cudaStream_t s)
+{
+    XfPack pack;
+    memset(&pack, 0, sizeof(pack));
+    for (int i = 0; i < n_xf && i < 8; ++i) pack.f[i] = h_xf[i];
+    const int64_t ntiles = (n_elems + CT_TILE - 1) / CT_TILE;
+    const int aligned = ((uintptr_t)heat % 16) == 0;
+    if (dtype == 1)
+        k_compact_project<double><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const double *>(heat), n_elems, thr, pixel,
+                                                                           intensity, cap, scratch, counts, early_n, aligned,
+                                                                           ord_next, d_xf, n_xf, pack);
+    else
+        k_compact_project<float><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const float *>(heat), n_elems, (float)thr,
+                                                                          pixel, intensity, cap, scratch, counts, early_n,
+                                                                          aligned, ord_next, d_xf, n_xf, pack);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_publish_counts(const long long *counts, long long *dst, cudaStream_t s)

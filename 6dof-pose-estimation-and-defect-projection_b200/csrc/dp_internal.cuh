@@ -99,29 +99,49 @@ constexpr unsigned long long LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_VAL = 
 __device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned long long *state, unsigned tile,
                                                                         unsigned long long total, int lane)
 {
+    // LB_WIDE predecessors per lane and round.  Measured on B200 (1024^2 pixels = 256 tiles, 100-step bench, same box):
+    // 4 per lane (2 rounds instead of 8 for the last tile) is 2 us per frame SLOWER than 1 -- the rounds overlap with the
+    // tiles' own loads, the extra loads and selects do not -- so 1 stays (scripts/r2/r2_sweep18.sh).
+#ifndef DP_LB_WIDE
+#define DP_LB_WIDE 1
+#endif
+    constexpr int LB_WIDE = DP_LB_WIDE;
     unsigned long long prefix = 0;
     if (tile == 0) {
         if (lane == 0) atomicExch(&state[0], LB_INC | total);
         return 0;
     }
     if (lane == 0) atomicExch(&state[tile], LB_AGG | total);
-    long long j0 = (long long)tile - 1;                      // lane l looks at tile j0 - l
+    long long j0 = (long long)tile - 1;                      // lane l looks at tiles j0 - LB_WIDE*l - k, k = 0 .. LB_WIDE-1
     for (;;) {
-        const long long j = j0 - lane;
-        unsigned long long sv = LB_INC;                      // "tiles" before the first one: inclusive prefix 0
-        if (j >= 0) {
-            do {
-                sv = *reinterpret_cast<volatile unsigned long long *>(&state[j]);
-            } while ((sv >> 62) == 0);
+        unsigned long long sv[LB_WIDE];
+#pragma unroll
+        for (int k = 0; k < LB_WIDE; ++k) {
+            const long long j = j0 - (long long)(LB_WIDE * lane + k);
+            sv[k] = LB_INC;                                  // "tiles" before the first one: inclusive prefix 0
+            if (j >= 0) sv[k] = *reinterpret_cast<volatile unsigned long long *>(&state[j]);
         }
-        const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv & LB_INC) != 0);
-        const int first_inc = __ffs(inc_mask) - 1;           // nearest predecessor with an inclusive prefix
-        unsigned long long v = (first_inc < 0 || lane <= first_inc) ? (sv & LB_VAL) : 0ull;
+#pragma unroll
+        for (int k = 0; k < LB_WIDE; ++k) {
+            const long long j = j0 - (long long)(LB_WIDE * lane + k);
+            while ((sv[k] >> 62) == 0) sv[k] = *reinterpret_cast<volatile unsigned long long *>(&state[j]);
+        }
+        // values up to and including the nearest predecessor that carries an inclusive prefix
+        unsigned long long v = 0;
+        bool closed = false;
+#pragma unroll
+        for (int k = 0; k < LB_WIDE; ++k) {
+            if (!closed) v += sv[k] & LB_VAL;
+            closed = closed || (sv[k] & LB_INC) != 0;
+        }
+        const unsigned inc_mask = __ballot_sync(0xffffffffu, closed);
+        const int first_inc = __ffs(inc_mask) - 1;           // first lane (nearest tiles) holding an inclusive prefix
+        if (first_inc >= 0 && lane > first_inc) v = 0ull;
 #pragma unroll
         for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         prefix += v;
         if (first_inc >= 0) break;
-        j0 -= 32;
+        j0 -= 32 * LB_WIDE;
     }
     if (lane == 0) atomicExch(&state[tile], LB_INC | (prefix + total));
     return prefix;
@@ -136,6 +156,13 @@ cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t
                            uint32_t *pixel, float *intensity, int64_t cap, unsigned long long *scratch,
                            long long *d_count, long long *d_frame_count, int64_t nframes, cudaStream_t s,
                            bool scratch_zeroed = false, long long *early_n = nullptr);
+// dp_project's compaction launch doing the call's resets and uploads itself (no prologue launch): block 0 writes the
+// per-frame constants (n_xf <= 8), the tile that finishes LAST zeroes counts[1..3] (hits, the traversal's two work
+// counters), resets `ord_next` and leaves the look-back scratch clean for the next call (the scratch must be zero on
+// entry: zero it once when it is allocated).  n_elems > 0.
+cudaError_t launch_compact_fused(const void *heat, int dtype, int64_t n_elems, double thr, uint32_t *pixel, float *intensity,
+                                 int64_t cap, unsigned long long *scratch, long long *counts, struct OrderState *ord_next,
+                                 struct FrameXf *d_xf, const struct FrameXf *h_xf, int n_xf, long long *early_n, cudaStream_t s);
 // dp_project's resets and uploads as kernel launches (no copy-engine work in the kernel stream): zeroes the
 // compaction scratch, counts[0..2] (rays, hits, traversal work counter), resets `ord_next`, writes the per-frame
 // constants.  launch_publish_counts stores counts[0..1] to a device or mapped pinned-host address.

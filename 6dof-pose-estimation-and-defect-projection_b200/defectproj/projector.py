@@ -565,6 +565,7 @@ class FrameStream:
         self.counts_h = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
         self._identity = None
         self.last_d2h_bytes = 0
+        self.speculate = True        # queue a frame's read-back behind its kernels, sized like the previous frame (see run)
 
     def run(self, heats, K, poses, thr=0.5, frame="object", accumulate=True, before_kernels=None):
         """heats: sequence of pinned host tensors [H,W]; K [3,3] or per frame; poses [B,4,4].
@@ -584,6 +585,8 @@ class FrameStream:
         ev_out = [torch.cuda.Event() for _ in range(self.ring)]
         done_k = [False, False]
         pending = []                                   # frames whose D2H has been queued, not yet yielded
+        next_d2h = 0
+        self._pred = None                              # (rays, dense) of the last frame handed out
         prof = [] if getattr(self, "profile", False) else None     # per frame: timing events around each stage
 
         def mark(stream):
@@ -591,31 +594,69 @@ class FrameStream:
             e.record(stream)
             return e
 
-        def queue_d2h(i):
+        def copy_out(i, m, dense, lo=0):
+            """D2H of rows [lo, m) of frame i's results on the output stream (the pixel list of a dense frame is not shipped)"""
+            b, r = i % 2, i % self.ring
+            for k in self.want:
+                if k == "pixel" and dense:
+                    continue                               # not copied: pop_result hands out the identity
+                self.out_h[r][k][lo:m].copy_(self.out_d[b][k][lo:m], non_blocking=True)
+
+        def queue_d2h(i, pred=None):
+            """pred=None: wait for frame i's counts on the host, then queue its exact-size read-back.  pred=(rays, dense)
+            of an earlier frame: queue the read-back NOW, behind frame i's kernels on the device (no host round trip between
+            the kernels and the copy), sized by the prediction; validate() checks the real count before the frame's device
+            buffers are reused and fetches what a larger frame still misses."""
             b = i % 2
-            ev_k[b].synchronize()                      # the 16-byte counts of frame i are on the host now
-            n, nh = int(self.counts_h[b][0]), int(self.counts_h[b][1])
-            m = min(n, self.cap)
             r = i % self.ring
-            dense = n == self.H * self.W and m == n        # every pixel selected: the pixel list is 0..n-1
+            e = {"i": i, "r": r, "n": None, "nh": None}
+            if pred is None:
+                ev_k[b].synchronize()                      # the 16-byte counts of frame i are on the host now
+                e["n"], e["nh"] = int(self.counts_h[b][0]), int(self.counts_h[b][1])
+                e["m"] = min(e["n"], self.cap)
+                e["dense"] = e["n"] == self.H * self.W and e["m"] == e["n"]    # every pixel selected: the pixel list is 0..n-1
+                self._pred = (e["n"], e["dense"])
+            else:
+                e["m"], e["dense"] = min(pred[0], self.cap), pred[1]
             with torch.cuda.stream(self.s_out):
+                if pred is not None:
+                    self.s_out.wait_event(ev_k[b])
                 if prof is not None:
                     prof[i]["out0"] = mark(self.s_out)
-                for k in self.want:
-                    if k == "pixel" and dense:
-                        continue                           # not copied: pop_result hands out the identity
-                    self.out_h[r][k][:m].copy_(self.out_d[b][k][:m], non_blocking=True)
+                copy_out(i, e["m"], e["dense"])
                 ev_out[r].record(self.s_out)
                 if prof is not None:
                     prof[i]["out1"] = mark(self.s_out)
-            self.last_d2h_bytes = 16 + sum(self.out_h[r][k][:m].numel() * self.out_h[r][k].element_size()
-                                           for k in self.want if not (k == "pixel" and dense))
-            pending.append((i, r, n, nh, m))
+            pending.append(e)
+
+        def validate(i):
+            """Frame i was read back on a prediction: its real counts (ev_k[i % 2] still stands for frame i) decide whether
+            rows are missing; they are fetched while the frame's device buffers are still intact."""
+            e = next((p for p in pending if p["i"] == i), None)
+            if e is None or e["n"] is not None:
+                return
+            b = i % 2
+            ev_k[b].synchronize()
+            e["n"], e["nh"] = int(self.counts_h[b][0]), int(self.counts_h[b][1])
+            m_true = min(e["n"], self.cap)
+            dense_true = e["n"] == self.H * self.W and m_true == e["n"]
+            if m_true > e["m"] or (e["dense"] and not dense_true):
+                with torch.cuda.stream(self.s_out):
+                    if e["dense"] and not dense_true:
+                        copy_out(i, m_true, False)                 # the pixel list after all
+                    else:
+                        copy_out(i, m_true, dense_true, lo=e["m"])
+                    ev_out[e["r"]].record(self.s_out)
+            e["m"], e["dense"] = m_true, dense_true
+            self._pred = (e["n"], dense_true)
 
         def pop_result():
-            i, r, n, nh, m = pending.pop(0)
+            validate(pending[0]["i"])
+            e = pending.pop(0)
+            i, r, n, nh, m, dense = e["i"], e["r"], e["n"], e["nh"], e["m"], e["dense"]
             ev_out[r].synchronize()
-            dense = n == self.H * self.W and m == n
+            self.last_d2h_bytes = 16 + sum(self.out_h[r][k][:m].numel() * self.out_h[r][k].element_size()
+                                           for k in self.want if not (k == "pixel" and dense))
             res = {k: self.out_h[r][k][:m].numpy() for k in self.want if not (k == "pixel" and dense)}
             if "pixel" in self.want:
                 if dense:
@@ -642,7 +683,9 @@ class FrameStream:
                 if prof is not None:
                     prof[i]["in1"] = mark(self.s_in)
             if i >= 2:
-                # the device result buffer b is free once frame i-2's D2H is done
+                # the device result buffer b is free once frame i-2's D2H is done (all of it: a read-back queued on a
+                # prediction is checked against the frame's real counts first)
+                validate(i - 2)
                 self.s_k.wait_event(ev_out[(i - 2) % self.ring])
             self.s_k.wait_event(ev_in[b])
             if before_kernels is not None:
@@ -658,12 +701,16 @@ class FrameStream:
             if prof is not None:
                 prof[i]["k1"] = mark(self.s_k)
             done_k[b] = True
-            if i >= 1:
-                queue_d2h(i - 1)
-            while len(pending) > 1:
+            # read-backs in frame order: speculative (no host wait) once an earlier frame's size is known, else exact
+            pred = self._pred if self.speculate else None
+            while next_d2h <= (i if pred is not None else i - 1):
+                queue_d2h(next_d2h, pred)
+                next_d2h += 1
+            while len(pending) > (2 if pred is not None else 1):
                 yield pop_result()
-        if B:
-            queue_d2h(B - 1)
+        while next_d2h < B:
+            queue_d2h(next_d2h, None)
+            next_d2h += 1
         t_end.record(self.s_out)
         while pending:
             yield pop_result()

@@ -752,6 +752,19 @@ def run_ours(args):
     modes = {"payload": ("pixel", "face", "point"), "full": ("pixel", "t_hit", "face", "point"),
              "lean": ("pixel", "t_hit", "face"), "accumulate_only": ()}
     e2e = {k: run_mode(w) for k, w in modes.items()}
+
+    # what the link gives: the payload's bytes as plain pinned D2H copies back to back (no kernels, nothing else on the bus)
+    pay_d = torch.empty(n_pix * 4, dtype=torch.float32, device=dev)
+    pay_h = torch.empty(n_pix * 4, dtype=torch.float32).pin_memory()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):
+        c0.record(stream)
+        for _ in range(8):
+            pay_h.copy_(pay_d, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize()
+    pcie_d2h_gbs = 8 * pay_h.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del pay_d, pay_h
     h2d = n_pix * 4 + 128                       # heatmap + per-frame constants
     # the same frame as one blocking call (no overlap), for reference
     h_out = {"pixel": torch.empty(n_pix, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
@@ -828,8 +841,12 @@ def run_ours(args):
             "e2e": {"value": head["value"], "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": head["d2h_bytes_per_step"],
                     "ms_per_frame": head["ms_per_frame"], "steps": e2e_steps, "wall_ms_per_frame": head["wall_ms_per_frame"],
                     "blocking_call_ms_per_frame": blocking_ms,
+                    "pcie_d2h_gbs": pcie_d2h_gbs,
+                    "pcie_bound_mrays_s": pcie_d2h_gbs * 1e9 / 16.0 / 1e6,
                     "api": "defectproj.FrameStream.run (3-stream pipeline over dp_project); blocking_call = Context.project",
                     "l2": "132 MiB (> 126 MB L2) memset on the kernel stream before every frame, inside the timed region",
+                    "pcie": "pcie_d2h_gbs: this rank's pinned device-to-host copy rate measured with the payload's bytes back to back; "
+                            "pcie_bound_mrays_s = that rate / 16 B per ray: the ceiling of the payload mode on this link",
                     "outputs": "the drop-in's payload: the float32 hit point and the face id of every ray (16 B/ray; the reference "
                                "returns the hit points, /root/reference/src/defect_projection.py:261-264, the face ids are the "
                                "extension north_star names) + ray/hit counts; t_hit (= |point|) travels in mode 'full' "

@@ -728,20 +728,26 @@ def test_stage_timings_are_opt_in(ctx):
         ctx.set_timing(False)
 
 
-def test_frame_stream_equals_blocking_calls(ctx, orc):
-    """The pipelined host-buffer API (H2D | kernels | D2H on three streams) returns what Context.project returns."""
+@pytest.mark.parametrize("speculate", [True, False])
+def test_frame_stream_equals_blocking_calls(ctx, orc, speculate):
+    """The pipelined host-buffer API (H2D | kernels | D2H on three streams) returns what Context.project returns -- with
+    the read-back queued behind the kernels on a prediction of the frame's size (sparse, empty and dense frames in turn:
+    every misprediction path) and with the exact-size read-back after a host wait."""
     import torch
     from defectproj import FrameStream
     V, F = synth.param_mesh(*synth.MESH_CONFIGS["c1_30k"], seed=0)
     K, H, W = synth.K_matrix(305.0, 305.0, 320.0, 180.0), 360, 640
-    B = 7
+    B = 11
     poses = synth.helix_poses(B, turns=1)
     heats = [torch.from_numpy(synth.blob_heatmap((H, W), seed=40 + i)).pin_memory() for i in range(B)]
     heats[3] = torch.zeros((H, W)).pin_memory()                                   # an empty frame in the middle
     heats[5] = torch.ones((H, W)).pin_memory()                                    # a dense one: its pixel list is the identity
+    heats[8] = torch.ones((H, W)).pin_memory()                                    # dense, dense, then sparse again
+    heats[9] = torch.ones((H, W)).pin_memory()
     ctx.set_mesh(V, F).build_bvh()
     ctx.accum_reset()
     fs = FrameStream(ctx, H, W, want=("pixel", "t_hit", "face", "point"))
+    fs.speculate = speculate
     got = {}
     for i, res in fs.run(heats, K, poses, 0.5, "object", True):
         got[i] = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in res.items()}
