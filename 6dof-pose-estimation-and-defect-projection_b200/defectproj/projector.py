@@ -532,17 +532,20 @@ class Projector:
 class FrameStream:
     """Host-buffer streaming of frames through one context with copies and kernels overlapped.
 
-    Three CUDA streams: H2D of frame i+1, kernels of frame i and D2H of frame i-1 run concurrently on
-    double-buffered device memory; the host only waits for the 16-byte ray/hit counts of a frame before it
-    queues that frame's (exact-size) result copy.  A dense frame (every pixel selected) does not ship its pixel
-    list: it is the identity, handed out as one shared read-only array.  Inputs and outputs are pinned host tensors, so
-    every copy is a real DMA.  Results are identical to Context.project on the same frame.
+    Three CUDA streams: H2D of frame i+1, kernels of frame i and D2H of frame i-1 run concurrently on `nbuf` sets of
+    device buffers (two; a third so that the kernels never wait for a read-back measured equal: on the bench frame the
+    kernel stream, not the read-back, is the longer chain -- scripts/stream_timeline2.py).  A frame's read-back is queued right behind its
+    kernels, sized like the last frame whose counts are known (`speculate`; its real counts are checked before its
+    device buffers are reused, and rows a larger frame still misses are fetched then); without a prediction the host
+    waits for the frame's 16-byte counts and queues the exact-size copy.  A dense frame (every pixel selected) does not
+    ship its pixel list: it is the identity, handed out as one shared read-only array.  Inputs and outputs are pinned host
+    tensors, so every copy is a real DMA.  Results are identical to Context.project on the same frame.
     """
 
     _DT = {"pixel": "int32", "intensity": "float32", "t_hit": "float32", "face": "int32", "point": "float32"}
 
     def __init__(self, ctx: Context, H: int, W: int, want=("pixel", "t_hit", "face"), cap=None, ring: int = 3,
-                 heat_dtype="float32"):
+                 heat_dtype="float32", nbuf: int = 2):
         import torch
         self.ctx, self.H, self.W, self.want = ctx, int(H), int(W), tuple(want)
         self.cap = int(cap) if cap is not None else self.H * self.W
@@ -551,7 +554,8 @@ class FrameStream:
         self.dev = dev
         hd = getattr(torch, heat_dtype)
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-        self.heat_d = [torch.empty((1, self.H, self.W), dtype=hd, device=dev) for _ in range(2)]
+        self.nbuf = max(2, int(nbuf))                  # device-side slots (heatmap, results, counts) a frame cycles through
+        self.heat_d = [torch.empty((1, self.H, self.W), dtype=hd, device=dev) for _ in range(self.nbuf)]
 
         def outs(device, pin):
             d = {}
@@ -560,9 +564,9 @@ class FrameStream:
                 t = torch.empty(shp, dtype=getattr(torch, self._DT[k]), device=device)
                 d[k] = t.pin_memory() if pin else t
             return d
-        self.out_d = [outs(dev, False) for _ in range(2)]
+        self.out_d = [outs(dev, False) for _ in range(self.nbuf)]
         self.out_h = [outs("cpu", True) for _ in range(self.ring)]
-        self.counts_h = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.counts_h = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(self.nbuf)]
         self._identity = None
         self.last_d2h_bytes = 0
         self.speculate = True        # queue a frame's read-back behind its kernels, sized like the previous frame (see run)
@@ -580,10 +584,11 @@ class FrameStream:
         B = len(heats)
         K = np.asarray(K, np.float64).reshape(-1, 9)
         poses = None if poses is None else np.asarray(poses, np.float64).reshape(-1, 4, 4)
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_k = [torch.cuda.Event() for _ in range(2)]
+        NB = self.nbuf
+        ev_in = [torch.cuda.Event() for _ in range(NB)]
+        ev_k = [torch.cuda.Event() for _ in range(NB)]
         ev_out = [torch.cuda.Event() for _ in range(self.ring)]
-        done_k = [False, False]
+        done_k = [False] * NB
         pending = []                                   # frames whose D2H has been queued, not yet yielded
         next_d2h = 0
         self._pred = None                              # (rays, dense) of the last frame handed out
@@ -596,7 +601,7 @@ class FrameStream:
 
         def copy_out(i, m, dense, lo=0):
             """D2H of rows [lo, m) of frame i's results on the output stream (the pixel list of a dense frame is not shipped)"""
-            b, r = i % 2, i % self.ring
+            b, r = i % NB, i % self.ring
             for k in self.want:
                 if k == "pixel" and dense:
                     continue                               # not copied: pop_result hands out the identity
@@ -607,7 +612,7 @@ class FrameStream:
             of an earlier frame: queue the read-back NOW, behind frame i's kernels on the device (no host round trip between
             the kernels and the copy), sized by the prediction; validate() checks the real count before the frame's device
             buffers are reused and fetches what a larger frame still misses."""
-            b = i % 2
+            b = i % NB
             r = i % self.ring
             e = {"i": i, "r": r, "n": None, "nh": None}
             if pred is None:
@@ -630,12 +635,12 @@ class FrameStream:
             pending.append(e)
 
         def validate(i):
-            """Frame i was read back on a prediction: its real counts (ev_k[i % 2] still stands for frame i) decide whether
+            """Frame i was read back on a prediction: its real counts (ev_k[i % NB] still stands for frame i) decide whether
             rows are missing; they are fetched while the frame's device buffers are still intact."""
             e = next((p for p in pending if p["i"] == i), None)
             if e is None or e["n"] is not None:
                 return
-            b = i % 2
+            b = i % NB
             ev_k[b].synchronize()
             e["n"], e["nh"] = int(self.counts_h[b][0]), int(self.counts_h[b][1])
             m_true = min(e["n"], self.cap)
@@ -672,21 +677,21 @@ class FrameStream:
             return i, res
 
         for i in range(B):
-            b = i % 2
+            b = i % NB
             with torch.cuda.stream(self.s_in):
                 if done_k[b]:
-                    self.s_in.wait_event(ev_k[b])      # kernels of frame i-2 have consumed this heat buffer
+                    self.s_in.wait_event(ev_k[b])      # kernels of frame i-nbuf have consumed this heat buffer
                 if prof is not None:
                     prof.append({"in0": mark(self.s_in)})
                 self.heat_d[b].copy_(heats[i].reshape(1, self.H, self.W), non_blocking=True)
                 ev_in[b].record(self.s_in)
                 if prof is not None:
                     prof[i]["in1"] = mark(self.s_in)
-            if i >= 2:
-                # the device result buffer b is free once frame i-2's D2H is done (all of it: a read-back queued on a
+            if i >= NB:
+                # the device result buffer b is free once frame i-NB's D2H is done (all of it: a read-back queued on a
                 # prediction is checked against the frame's real counts first)
-                validate(i - 2)
-                self.s_k.wait_event(ev_out[(i - 2) % self.ring])
+                validate(i - NB)
+                self.s_k.wait_event(ev_out[(i - NB) % self.ring])
             self.s_k.wait_event(ev_in[b])
             if before_kernels is not None:
                 with torch.cuda.stream(self.s_k):
