@@ -105,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.001)
 
     def start(self):
         if self.nv:
@@ -853,10 +853,12 @@ def run_ours(args):
                                "(20 B/ray); pixel u32 is the identity for a dense frame (synthesised on the host, not copied); "
                                "heatmap f32 in; pinned host memory",
                     "modes": {k: e2e_entry(k) for k in keys}},
-            # k_project_prologue, k_compact, k_trace per frame (rays and hit points are generated inside k_trace; with
-            # DP_FUSE_RAYS=0 also k_raygen and k_points); per batch k_pack_records, k_vertex_max, and k_peer_snapshot +
+            # k_compact_project (the compaction, which also does the call's resets and uploads) and k_trace per frame (rays
+            # and hit points are generated inside k_trace; DP_FUSE_RAYS=0: also k_raygen and k_points; DP_FUSED_PROLOGUE=0:
+            # also k_project_prologue); per batch k_pack_records, k_vertex_max, and k_peer_snapshot +
             # k_peer_combine (peer path) or a snapshot copy followed by NCCL's kernels
-            "gpu_launches": (3 if os.environ.get("DP_FUSE_RAYS", "1") != "0" else 5) * args.steps + (4 if peer else 3) * nb_batches,
+            "gpu_launches": ((2 if os.environ.get("DP_FUSED_PROLOGUE", "1") != "0" else 3)
+                             + (0 if os.environ.get("DP_FUSE_RAYS", "1") != "0" else 2)) * args.steps + (4 if peer else 3) * nb_batches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(args.mesh), "peak_source": peak_src,
                          "kernel": "k_trace<false,0,%d,%d>" % ((6, 1) if nb == B_NODE_FAT else (7, 0)), "kernel_ms": k_ms,

@@ -148,6 +148,36 @@ def test_sharded_frame_lands_in_every_window(built_lib, case, monkeypatch):
             c.close()
 
 
+def test_missing_rank_times_out_instead_of_hanging(built_lib, monkeypatch):
+    """A rank that never reaches the combine: the waiting kernel gives up after its 4 s budget, leaves the totals alone and
+    sets the window's error word (PeerCombiner.check raises); the GPU is not left spinning."""
+    import time
+    import torch
+    from defectproj import Context
+    from defectproj.projector import PeerCombiner
+    monkeypatch.setenv("DP_PEER_BLOCKS", "4")
+    V, F, H, W, K = _scene()
+    ctxs = [Context(0).set_mesh(V, F).build_bvh() for _ in range(2)]
+    try:
+        combs = [PeerCombiner(c, r, 2, local_contexts=ctxs) for r, c in enumerate(ctxs)]
+        for cb in combs:
+            cb.open_local()
+        heat = torch.rand((1, H, W), device="cuda")
+        ctxs[0].project_device(heat, K, _frame_pose(0)[None], 0.5, "object", True, sync=True)
+        t0 = time.perf_counter()
+        combs[0].submit()                                 # rank 1 never submits
+        torch.cuda.synchronize()
+        waited = time.perf_counter() - t0
+        assert 3.0 < waited < 8.0
+        assert ctxs[0].peer_status() == 1 and ctxs[1].peer_status() == 0
+        with pytest.raises(RuntimeError):
+            combs[0].check()
+        assert not combs[0].result()[0].any()             # nothing was folded
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_peer_ranks_under_torchrun(built_lib):
     """The same over CUDA IPC between real ranks (needs >= 2 GPUs; the 1-GPU box skips)."""
     import torch
