@@ -84,7 +84,7 @@ struct dp_ctx {
     bool peer_res_points = false;
 
     // per-call scratch
-    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, pscratch, counts, fcounts, xf, stats, jet;
+    DevBuf heat, pixel, inten, t_hit, face, point, point64, rays6, dir4, ray_nodes, order, cost, tmp[8], cscratch, pscratch, raytab, counts, fcounts, xf, stats, jet;
     long long *h_counts = nullptr;   // pinned: [0] rays, [1] hits
     const void *counts_alias_src = nullptr;   // last dp_rays_out.counts address and its device alias
     long long *counts_alias = nullptr;
@@ -211,7 +211,7 @@ void dp_destroy(dp_ctx *ctx)
     DevBuf *bufs[] = {&ctx->V, &ctx->F, &ctx->Vposed, &ctx->V64, &ctx->Vposed64, &ctx->obj_nodes, &ctx->obj_tris, &ctx->obj_wlo, &ctx->obj_whi,
                       &ctx->cam_nodes, &ctx->cam_tris, &ctx->cam_wlo, &ctx->cam_whi, &ctx->obj_fat, &ctx->cam_fat, &ctx->scales, &ctx->tri_face, &ctx->wparent, &ctx->arrived,
                       &ctx->accum, &ctx->heat, &ctx->pixel, &ctx->inten, &ctx->t_hit,
-                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->pscratch, &ctx->counts, &ctx->fcounts, &ctx->xf,
+                      &ctx->face, &ctx->point, &ctx->point64, &ctx->rays6, &ctx->dir4, &ctx->ray_nodes, &ctx->order, &ctx->cost, &ctx->cscratch, &ctx->pscratch, &ctx->raytab, &ctx->counts, &ctx->fcounts, &ctx->xf,
                       &ctx->stats, &ctx->jet};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : ctx->tmp) b.release();
@@ -684,9 +684,16 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
         }
         early_n = ctx->counts_alias;
     }
+    // one K for every frame: the compaction launch also tabulates the two per-pixel quotients of the ray generation
+    static const bool raytab_knob = [] { const char *e = getenv("DP_RAYTAB"); return e ? atoi(e) != 0 : true; }();
+    double *d_raytab = nullptr;
+    if (fused_prologue && nK == 1 && raytab_knob) {
+        CK(ctx->raytab.ensure((size_t)(W + H) * 8 + 16), "dp_project: ray table");
+        d_raytab = ctx->raytab.as<double>();
+    }
     if (fused_prologue)
         CK(launch_compact_fused(d_heat, dtype, n_elems, thr, d_pixel, d_int, cap, ctx->pscratch.as<unsigned long long>(), d_counts,
-                                ord_next, ctx->xf.as<FrameXf>(), hxf.data(), (int)nframes, early_n, s),
+                                ord_next, ctx->xf.as<FrameXf>(), hxf.data(), (int)nframes, early_n, s, d_raytab, H, W),
            "dp_project: compaction");
     else
         CK(launch_compact(d_heat, dtype, n_elems, frame_elems, thr, d_pixel, d_int, cap,
@@ -726,7 +733,7 @@ int dp_project(dp_ctx *ctx, int frame, const void *heat, int dtype, int64_t nfra
     CK(launch_trace_pixels(view_of(b), d_dir4, d_int, d_counts, cap, n_elems, H, W, ctx->xf.as<FrameXf>(),
                            d_t, d_face, accumulate ? &acc : nullptr, reinterpret_cast<unsigned long long *>(d_counts + 2),
                            d_counts + 1, st, ord_prev, ord_next, s, true, ctx->shard, d_pixel, nframes, fuse ? d_pt : nullptr,
-                           fuse ? d_p64 : nullptr, peer_out),
+                           fuse ? d_p64 : nullptr, peer_out, fuse ? d_raytab : nullptr),
        "dp_project: traversal");
     if (peer_mode) CK(launch_peer_frame_done(ctx->peer, ++ctx->peer_epoch[1], s), "dp_project: frame barrier");
     if (ctx->timing_on) CK(cudaEventRecord(ctx->ev[3], s), "dp_project");

@@ -162,10 +162,18 @@ template <typename T>
 __global__ void __launch_bounds__(CT_THREADS)
 k_compact_project(const T *__restrict__ heat, long long n, T thr, uint32_t *__restrict__ pixel,
                   float *__restrict__ intensity, long long cap, unsigned long long *scratch, long long *counts,
-                  long long *early_n, int aligned, OrderState *ord_next, FrameXf *xf, int n_xf, const __grid_constant__ XfPack pack)
+                  long long *early_n, int aligned, OrderState *ord_next, FrameXf *xf, int n_xf, const __grid_constant__ XfPack pack,
+                  double *raytab, int H, int W)
 {
     __shared__ int s_last;
     if (blockIdx.x == 0 && (int)threadIdx.x < 16 * n_xf) xf[threadIdx.x >> 4].v[threadIdx.x & 15] = pack.f[threadIdx.x >> 4].v[threadIdx.x & 15];
+    if (raytab) {
+        // the two per-pixel quotients of compute_rays (:216-217), once per column / row instead of once per ray
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W + H; i += gridDim.x * blockDim.x) {
+            const double *c = pack.f[0].v;
+            raytab[i] = i < W ? __ddiv_rn(__dsub_rn((double)i, c[2]), c[0]) : __ddiv_rn(__dsub_rn((double)(i - W), c[3]), c[1]);
+        }
+    }
     compact_tile<T>(heat, n, thr, pixel, intensity, cap, scratch, counts, early_n, aligned);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -268,7 +276,8 @@ cudaError_t launch_project_prologue(unsigned long long *scratch, int64_t n_elems
 
 cudaError_t launch_compact_fused(const void *heat, int dtype, int64_t n_elems, double thr, uint32_t *pixel, float *intensity,
                                  int64_t cap, unsigned long long *scratch, long long *counts, OrderState *ord_next,
-                                 FrameXf *d_xf, const FrameXf *h_xf, int n_xf, long long *early_n, cudaStream_t s)
+                                 FrameXf *d_xf, const FrameXf *h_xf, int n_xf, long long *early_n, cudaStream_t s, double *raytab,
+                                 int H, int W)
 {
     XfPack pack;
     memset(&pack, 0, sizeof(pack));
@@ -278,11 +287,11 @@ cudaError_t launch_compact_fused(const void *heat, int dtype, int64_t n_elems, d
     if (dtype == 1)
         k_compact_project<double><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const double *>(heat), n_elems, thr, pixel,
                                                                            intensity, cap, scratch, counts, early_n, aligned,
-                                                                           ord_next, d_xf, n_xf, pack);
+                                                                           ord_next, d_xf, n_xf, pack, raytab, H, W);
     else
         k_compact_project<float><<<(unsigned)ntiles, CT_THREADS, 0, s>>>(static_cast<const float *>(heat), n_elems, (float)thr,
                                                                           pixel, intensity, cap, scratch, counts, early_n,
-                                                                          aligned, ord_next, d_xf, n_xf, pack);
+                                                                          aligned, ord_next, d_xf, n_xf, pack, raytab, H, W);
     return cudaGetLastError();
 }
 

@@ -162,7 +162,10 @@ cudaError_t launch_compact(const void *heat, int dtype, int64_t n_elems, int64_t
 // entry: zero it once when it is allocated).  n_elems > 0.
 cudaError_t launch_compact_fused(const void *heat, int dtype, int64_t n_elems, double thr, uint32_t *pixel, float *intensity,
                                  int64_t cap, unsigned long long *scratch, long long *counts, struct OrderState *ord_next,
-                                 struct FrameXf *d_xf, const struct FrameXf *h_xf, int n_xf, long long *early_n, cudaStream_t s);
+                                 struct FrameXf *d_xf, const struct FrameXf *h_xf, int n_xf, long long *early_n, cudaStream_t s,
+                                 double *raytab = nullptr, int H = 0, int W = 0);
+// raytab [W + H] doubles (optional, all frames share h_xf[0]'s intrinsics): xn(x) = (x - cx) / fx for every column, then
+// yn(y) = (y - cy) / fy for every row, written by the first blocks of the compaction for the traversal's ray generation
 // dp_project's resets and uploads as kernel launches (no copy-engine work in the kernel stream): zeroes the
 // compaction scratch, counts[0..2] (rays, hits, traversal work counter), resets `ord_next`, writes the per-frame
 // constants.  launch_publish_counts stores counts[0..1] to a device or mapped pinned-host address.
@@ -190,7 +193,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
                                 bool counter_zeroed = false, RayShard shard = RayShard(), const uint32_t *pixel = nullptr,
                                 int64_t n_xf = 0, float *point = nullptr, double *point64 = nullptr,
-                                const struct PeerOut *peer_out = nullptr);
+                                const struct PeerOut *peer_out = nullptr, const double *raytab = nullptr);
 // dir4 == nullptr: the traversal generates the rays itself from pixel[] / xf[] and writes the hit points (point, point64)
 // per-vertex maxima from the per-face maxima (run when the accumulators are read, not per hit)
 cudaError_t launch_vertex_max(const uint32_t *fmax, const int32_t *F, int64_t nF, uint32_t *vmax, cudaStream_t s);

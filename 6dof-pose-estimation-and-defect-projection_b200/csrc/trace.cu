@@ -451,8 +451,11 @@ constexpr int NR_STACK = 64;                          // stack entries per ray (
                                                       // 16-23 % faster than packets at 35k-110k rays, 30-35 % at 9k-16k)
 #endif
 
+// raytab (optional): xn of every column followed by yn of every row, the same two float64 quotients computed once per
+// call by the compaction launch when all frames share one K (2 of the 5 float64 divisions of a ray; same bits)
 __device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
-                                              uint32_t &fr, double &dcx, double &dcy, double &dcz)
+                                              uint32_t &fr, double &dcx, double &dcy, double &dcz,
+                                              const double *__restrict__ raytab = nullptr)
 {
     const uint32_t hw = (uint32_t)H * (uint32_t)W;
     fr = pix / hw;
@@ -461,8 +464,8 @@ __device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const 
     const uint32_t x = rem - y * (uint32_t)W;
     if ((long long)fr >= n_xf) fr = 0;
     const double *c = xf[fr].v;
-    const double xn = __ddiv_rn(__dsub_rn((double)x, c[2]), c[0]);
-    const double yn = __ddiv_rn(__dsub_rn((double)y, c[3]), c[1]);
+    const double xn = raytab ? __ldg(raytab + x) : __ddiv_rn(__dsub_rn((double)x, c[2]), c[0]);
+    const double yn = raytab ? __ldg(raytab + W + y) : __ddiv_rn(__dsub_rn((double)y, c[3]), c[1]);
     const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xn, xn), __dmul_rn(yn, yn)), 1.0));
     dcx = __ddiv_rn(xn, nrm);
     dcy = __ddiv_rn(yn, nrm);
@@ -474,10 +477,10 @@ __device__ __forceinline__ void pixel_ray_f64(uint32_t pix, int H, int W, const 
 // same operations in the same order, bit-identical results, no 32-byte ray record through HBM.
 __device__ __forceinline__ void pixel_ray_object(uint32_t pix, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
                                                  float &ox, float &oy, float &oz, float &dx, float &dy, float &dz,
-                                                 double &dcx, double &dcy, double &dcz)
+                                                 double &dcx, double &dcy, double &dcz, const double *__restrict__ raytab = nullptr)
 {
     uint32_t fr;
-    pixel_ray_f64(pix, H, W, xf, n_xf, fr, dcx, dcy, dcz);
+    pixel_ray_f64(pix, H, W, xf, n_xf, fr, dcx, dcy, dcz, raytab);
     const double *Ri = xf[fr].v + 4;
     dx = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[0], dcx), __dmul_rn(Ri[1], dcy)), __dmul_rn(Ri[2], dcz));
     dy = (float)__dadd_rn(__dadd_rn(__dmul_rn(Ri[3], dcx), __dmul_rn(Ri[4], dcy)), __dmul_rn(Ri[5], dcz));
@@ -563,7 +566,8 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
              float *__restrict__ t_hit, int32_t *__restrict__ face, Accum acc, int has_acc,
              unsigned long long *work_counter, long long *d_hits, TraceStats *stats, uint2 *s_stack, long long s_lo,
              long long s_hi, const uint32_t *__restrict__ pixel, int H, int W, const FrameXf *__restrict__ xf, long long n_xf,
-             float *__restrict__ point, double *__restrict__ point64, const PeerOut *__restrict__ peer_out)
+             float *__restrict__ point, double *__restrict__ point64, const PeerOut *__restrict__ peer_out,
+             const double *__restrict__ raytab)
 {
     const int lane = threadIdx.x & 31, c = lane & 7, g = lane >> 3;
     const unsigned gmask = 0xffu << (8 * g);
@@ -591,7 +595,7 @@ trace_narrow(const WideNode *__restrict__ nodes, const TriRec *__restrict__ tris
                     ox = o4.x; oy = o4.y; oz = o4.z; dx = d.x; dy = d.y; dz = d.z;
                 } else {
                     // in-kernel ray generation: lane 0 of the ray's eight computes, the others receive
-                    if (c == 0) pixel_ray_object(pixel[i], H, W, xf, n_xf, ox, oy, oz, dx, dy, dz, dcx, dcy, dcz);
+                    if (c == 0) pixel_ray_object(pixel[i], H, W, xf, n_xf, ox, oy, oz, dx, dy, dz, dcx, dcy, dcz, raytab);
                 }
             }
             if (!dir4) {
@@ -746,7 +750,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         unsigned long long *work_counter, long long *d_hits, TraceStats *stats, int allow_tiled,
         const OrderState *__restrict__ ord_prev, OrderState *ord_next, int prefetch, int narrow_enabled, int shard_rank,
         int shard_world, const uint32_t *__restrict__ pixel, long long n_xf, float *__restrict__ point,
-        double *__restrict__ point64, const PeerOut *__restrict__ peer_out)
+        double *__restrict__ point64, const PeerOut *__restrict__ peer_out, const double *__restrict__ raytab)
 {
     // dir4 == nullptr (SRC 0): rays are generated here from pixel[] and xf[], hit points written here (no k_raygen / k_points)
     // (the learnt packet lists hold packets of the previous launch over the same shard: dp_set_ray_shard drops them)
@@ -769,7 +773,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
         // sparse frame: eight lanes per ray (work items come from the second counter)
         static_assert(STACK_SMEM * TR_THREADS >= (NR_THREADS / 8) * NR_STACK, "the narrow path borrows the packet stack");
         trace_narrow<STATS>(nodes, tris, d_scale, dir4, intensity, n, t_hit, face, acc, has_acc, work_counter + 1, d_hits, stats,
-                            s_stack, sh.s_lo, sh.s_hi, pixel, H, W, xf, n_xf, point, point64, peer_out);
+                            s_stack, sh.s_lo, sh.s_hi, pixel, H, W, xf, n_xf, point, point64, peer_out, raytab);
         return;
     }
     const bool tiled = sh.tiled;
@@ -821,7 +825,7 @@ k_trace(const WideNode *__restrict__ nodes, const uint4 *__restrict__ fat, const
                         dx = d.x; dy = d.y; dz = d.z;
                     } else {
                         double dcx, dcy, dcz;
-                        pixel_ray_object(pixel[slot], H, W, xf, n_xf, ox, oy, oz, dx, dy, dz, dcx, dcy, dcz);
+                        pixel_ray_object(pixel[slot], H, W, xf, n_xf, ox, oy, oz, dx, dy, dz, dcx, dcy, dcz, raytab);
                         if (want_pts) { s_dcam[threadIdx.x] = dcx; s_dcam[TR_THREADS + threadIdx.x] = dcy; s_dcam[2 * TR_THREADS + threadIdx.x] = dcz; }
                     }
                     if (has_acc && intensity) prefetch_l1(intensity + slot, true);   // read by the packet epilogue
@@ -1214,7 +1218,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
                                 int32_t *face, const Accum *acc, unsigned long long *work_counter, long long *d_hits,
                                 TraceStats *stats, const OrderState *ord_prev, OrderState *ord_next, cudaStream_t s,
                                 bool counter_zeroed, RayShard shard, const uint32_t *pixel, int64_t n_xf, float *point,
-                                double *point64, const PeerOut *peer_out)
+                                double *point64, const PeerOut *peer_out, const double *raytab)
 {
     if (n_max <= 0) return cudaSuccess;
     cudaError_t e;
@@ -1232,7 +1236,7 @@ cudaError_t launch_trace_pixels(const BvhView &bvh, const float4 *dir4, const fl
     k_trace<ST, 0, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, dir4, nullptr, intensity, d_n, \
                                                         n_max, total_px, H, W, xf, t_hit, face, a, acc != nullptr, work_counter, \
                                                         d_hits, stats, knob_tiled(), ord_prev, ord_next, pf, narrow, shard.rank, \
-                                                        shard.world, pixel, (long long)n_xf, point, point64, peer_out)
+                                                        shard.world, pixel, (long long)n_xf, point, point64, peer_out, raytab)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE0(true, DP_MIN_BLOCKS_BIG, 0);
@@ -1262,7 +1266,7 @@ cudaError_t launch_trace_rays6(const BvhView &bvh, const float *rays6, int64_t n
 #define DP_LAUNCH_TRACE1(ST, MB, FMT)                                                                                          \
     k_trace<ST, 1, MB, FMT><<<grid, TR_THREADS, 0, s>>>(bvh.nodes, bvh.fat, bvh.tris, bvh.d_scale, nullptr, rays6, nullptr, nullptr, \
                                                         n, 0, 0, 0, nullptr, t_hit, face, a, 0, work_counter, nullptr, stats, 0, \
-                                                        nullptr, nullptr, pf, 0, 0, 1, nullptr, 0, nullptr, nullptr, nullptr)
+                                                        nullptr, nullptr, pf, 0, 0, 1, nullptr, 0, nullptr, nullptr, nullptr, nullptr)
     if (stats) {
         if (variant == 2) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_FAT, 1);
         else if (variant == 1) DP_LAUNCH_TRACE1(true, DP_MIN_BLOCKS_BIG, 0);
