@@ -416,6 +416,20 @@ def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_thresh
     return project_debug_rays(rays, np.array([0, 0, 0])), mesh_copy
 
 
+def _to_host(tensors):
+    """CUDA tensors -> numpy arrays through pinned memory: all copies queued, one stream synchronisation (a .cpu() per
+    array is a synchronisation per array: 0.1 ms of the call for eight small arrays)."""
+    import torch
+    pinned = {}
+    for k, t in tensors.items():
+        t = t.contiguous()
+        hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        hbuf.copy_(t, non_blocking=True)
+        pinned[k] = hbuf
+    torch.cuda.current_stream().synchronize()
+    return {k: v.numpy() for k, v in pinned.items()}
+
+
 def _is_cuda_tensor(x):
     return type(x).__module__.startswith("torch") and bool(getattr(x, "is_cuda", False))
 
@@ -454,17 +468,20 @@ def _ray_tracing_device(T, V, F, K, heat_t, heatmap_threshold):
     n, h = ctx.project_device(heat_t[None], K, None, heatmap_threshold, "camera", True, out=o, sync=True)
     pix_d, face_d, t_d = o["pixel"][:n], o["face"][:n], o["t_hit"][:n]
     inten_d = heat_t.reshape(-1)[pix_d.long()]                          # exact values, in the heatmap's own dtype
-    pix = pix_d.cpu().numpy().view(np.uint32).astype(np.int64)
-    face = face_d.cpu().numpy()
-    t_hit = t_d.cpu().numpy()
-    _GEN[0] += 1
-    _LAST = _LazyResult(ctx, _GEN[0], pixel=pix, intensity=inten_d.cpu().numpy(), t_hit=t_hit, face=face, n_rays=n, n_hits=h)
+    back = dict(pixel=pix_d, face=face_d, t_hit=t_d, intensity=inten_d)
     if h > 0:
         pk = ctx.pack_hits_device(inten_d, face_d, pix_d, o["point64"][:n], want=("points", "colors", "face", "pixel"))
-        pcd = PointCloud(pk["points"].cpu().numpy(), pk["colors"].cpu().numpy())
-        pcd.face_ids = pk["face"].cpu().numpy()
+        back.update(pk_points=pk["points"], pk_colors=pk["colors"], pk_face=pk["face"], pk_pixel=pk["pixel"])
+    got = _to_host(back)                                                # eight copies, ONE synchronisation
+    pix = got["pixel"].view(np.uint32).astype(np.int64)
+    face, t_hit = got["face"], got["t_hit"]
+    _GEN[0] += 1
+    _LAST = _LazyResult(ctx, _GEN[0], pixel=pix, intensity=got["intensity"], t_hit=t_hit, face=face, n_rays=n, n_hits=h)
+    if h > 0:
+        pcd = PointCloud(got["pk_points"], got["pk_colors"])
+        pcd.face_ids = got["pk_face"]
         pcd.t_hit = t_hit[face >= 0]
-        pcd.pixels = pk["pixel"].cpu().numpy().view(np.uint32).astype(np.int64)
+        pcd.pixels = got["pk_pixel"].view(np.uint32).astype(np.int64)
         return pcd, mesh_copy
     ys, xs = np.divmod(pix, W)
     rays = ctx.compute_rays(xs, ys, K) if len(pix) else np.zeros((0, 3))
