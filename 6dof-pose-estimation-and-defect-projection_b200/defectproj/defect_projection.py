@@ -382,6 +382,10 @@ def ray_tracing(data_dir, target_mesh, heatmap, color_intrinsics, heatmap_thresh
         raise ValueError("heatmap must be 2-D")
     if heat.dtype not in (np.float32, np.float64):
         heat = heat.astype(np.float64)
+    if os.environ.get("DP_FACADE_UPLOAD", "1") != "0" and heat.size > 0:
+        # staged into pinned memory, uploaded asynchronously, then the call continues as for a heatmap that already lives
+        # on the device: no per-pixel array comes back, the results return behind one synchronisation
+        return _ray_tracing_device(T, V, F, K, _upload_heatmap(heat), heatmap_threshold)
     global _LAST
     ctx = _scene(V, F)
     ctx.pose_mesh(T)
@@ -435,6 +439,23 @@ def _is_cuda_tensor(x):
 
 
 _DEVOUT = {}
+_UPLOAD = {}                # (shape, dtype, device) -> (pinned tensor, its numpy view, device tensor)
+
+
+def _upload_heatmap(heat):
+    import torch
+    ctx = get_context()
+    key = (heat.shape, heat.dtype.str, ctx.device)
+    st = _UPLOAD.get(key)
+    if st is None:
+        dt = torch.float64 if heat.dtype == np.float64 else torch.float32
+        pin = torch.empty(heat.shape, dtype=dt, pin_memory=True)
+        st = _UPLOAD[key] = (pin, pin.numpy(), torch.empty(heat.shape, dtype=dt, device=f"cuda:{ctx.device}"))
+    pin, view, dev = st
+    np.copyto(view, heat)
+    with torch.cuda.device(ctx.device):
+        dev.copy_(pin, non_blocking=True)
+    return dev
 
 
 def _ray_tracing_device(T, V, F, K, heat_t, heatmap_threshold):
