@@ -204,12 +204,9 @@ cudaError_t launch_peer_combine(const PeerView &pv, int slot, unsigned long long
     // enough CTAs to keep a few MB of peer loads in flight; they share the SMs with whatever else runs.  Every CTA waits
     // in the barrier, so contexts that emulate several ranks on ONE device (the tests) must keep all their grids
     // co-resident: DP_PEER_BLOCKS bounds the grid there.
-    static int blocks = 0;
-    if (blocks == 0) {
-        const char *e = getenv("DP_PEER_BLOCKS");
-        blocks = e ? atoi(e) : 0;
-        if (blocks < 1 || blocks > 148 * 2) blocks = 148 * 2;
-    }
+    const char *e = getenv("DP_PEER_BLOCKS");             // read per launch: the tests set it per case
+    int blocks = e ? atoi(e) : 0;
+    if (blocks < 1 || blocks > 148 * 2) blocks = 148 * 2;
     k_peer_combine<<<blocks, 256, 0, s>>>(pv, slot, epoch, static_cast<uint4 *>(total), (long long)(bytes >> 4),
                                            (long long)(max_from >> 4), fold ? 1 : 0, gather_root, gathered, (long long)cap_rows,
                                            row_words, m_out, m_async);
