@@ -666,7 +666,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    clocks_value = dict(sampler.stop())             # the 20 timed steps last ~6 ms: one or two NVML samples
+    sampler = ClockSampler(local)                   # ... so the end-to-end runs (timed regions too) are sampled as well
+    sampler.start()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     tail_ms = ev[-1][1].elapsed_time(ev_tail)
     total_ms = float(sum(step_ms)) + tail_ms
@@ -752,6 +754,10 @@ def run_ours(args):
     modes = {"payload": ("pixel", "face", "point"), "full": ("pixel", "t_hit", "face", "point"),
              "lean": ("pixel", "t_hit", "face"), "accumulate_only": ()}
     e2e = {k: run_mode(w) for k, w in modes.items()}
+    clocks_e2e = sampler.stop()
+    clocks = {"sm_mhz": clocks_value["sm_mhz"] if clocks_value["sm_mhz"] is not None else clocks_e2e["sm_mhz"],
+              "sm_max_mhz": clocks_value["sm_max_mhz"], "reasons": sorted(set(clocks_value["reasons"]) | set(clocks_e2e["reasons"])),
+              "samples": clocks_value["samples"], "e2e_sm_mhz": clocks_e2e["sm_mhz"], "e2e_samples": clocks_e2e["samples"]}
 
     # what the link gives: the payload's bytes as plain pinned D2H copies back to back (no kernels, nothing else on the bus)
     pay_d = torch.empty(n_pix * 4, dtype=torch.float32, device=dev)
