@@ -362,6 +362,7 @@ class Projector:
         self.peer = None
         self._cnt = None
         self._res_slot = 0
+        self._records = self._gathered = self._rows = None
         import os
         if self.world > 1 and os.environ.get("DP_PEER", "1") != "0" and dist.get_backend(group) == "nccl":
             self.enable_peer()
@@ -422,14 +423,20 @@ class Projector:
         """(hist, fmax, vmax) over every batch submitted since the last reset and over all ranks."""
         return self.combiner.result()
 
-    def project_batch(self, heat, K, poses, thr=0.5, mode="object", out=None, reduce=True, reset=True):
+    def project_batch(self, heat, K, poses, thr=0.5, mode="object", out=None, reduce=True, reset=True, records_to=None):
         """heat: CUDA tensor [B_local,H,W] holding THIS rank's frames (see shard_range);
         poses: [B_local,4,4] model->camera.  mode 'object' = one launch for the whole batch,
         'camera' = per-frame dp_pose_mesh (refit) + launch, the reference-literal arithmetic.
         reduce: the batch's accumulators are snapshotted, zeroed and combined over the ranks into the running
         totals (`combined()`), asynchronously; reset: the totals start from zero with this batch (False: they keep
-        accumulating -- every hit is still counted once).  Returns (n_rays, n_hits) of this rank."""
+        accumulating -- every hit is still counted once).  records_to=r (mode 'object', `out` with 'pixel', 't_hit' and
+        'face'): the batch's hit records -- rows (pixel, t_hit bits, face) of the rays that hit, the rays the reference
+        keeps (/root/reference/src/defect_projection.py:259-264) -- of ALL ranks are gathered on rank r in rank order
+        (`hit_records()`): inside the combine kernel on the peer path (enable_peer(record_rows=...) sizes the windows),
+        by one count exchange + one all-gather on the NCCL path.  Returns (n_rays, n_hits) of this rank."""
         import torch
+        if records_to is not None and (mode != "object" or not reduce or out is None or any(k not in out for k in ("pixel", "t_hit", "face"))):
+            raise ValueError("records_to needs mode='object', reduce=True and out with 'pixel', 't_hit' and 'face'")
         if reset:
             self.ctx.accum_reset(torch.cuda.current_stream())
             self.combiner.reset_totals()
@@ -446,9 +453,46 @@ class Projector:
                 a, c = self.ctx.project_device(heat[b:b + 1], kb, None, thr, "camera", True, out=None, sync=True)
                 n += a
                 h += c
-        if reduce:
+        if records_to is not None:
+            self._records = self._gather_records(out, n, int(records_to))
+        elif reduce:
             self.combiner.submit(reset=True)
         return n, h
+
+    def _gather_records(self, out, n, root):
+        import torch
+        ctx = self.ctx
+        if self.peer is not None:
+            comb = self.peer
+            k = comb.acquire()
+            rec, cnt = comb.records(k)
+            if rec is None or rec.shape[0] < n:
+                raise MemoryError(f"the exchange windows hold {0 if rec is None else rec.shape[0]} records per rank, the batch has "
+                                  f"{n} rays: enable_peer(record_rows=...) on every rank")
+            ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n, out=rec, count_async=cnt, sync=False)
+            rows_cap = self.world * rec.shape[0]
+            if self.rank == root and (self._gathered is None or self._gathered.shape[0] < rows_cap):
+                self._gathered = torch.empty((rows_cap, rec.shape[1]), dtype=torch.int32, device=rec.device)
+            if self._rows is None:
+                self._rows = torch.zeros(1, dtype=torch.int64).pin_memory()
+            comb.submit(reset=True, gather_root=root, gathered=self._gathered, count_async=self._rows)
+            return ("peer", root)
+        rec = ctx.pack_records_device(out["t_hit"], out["face"], pixel=out["pixel"], n=n)
+        self.combiner.submit(reset=True)
+        return ("nccl", root, gather_hits(rec, group=self.group, dst=root))
+
+    def hit_records(self):
+        """The records gathered by the last project_batch(records_to=r): int32 CUDA tensor [m, 3] (pixel, t_hit bits, face)
+        on rank r, None elsewhere.  Waits for the combine."""
+        import torch
+        if self._records is None:
+            return None
+        if self._records[0] == "nccl":
+            return self._records[2]
+        torch.cuda.current_stream().wait_stream(self.peer.side)
+        torch.cuda.current_stream().synchronize()               # the row count is in pinned memory now
+        self.peer.check()
+        return self._gathered[:int(self._rows[0])] if self.rank == self._records[1] else None
 
     def project_frame_sharded(self, heat, K, pose, thr=0.5, out=None, gather="all", reduce=True, reset=True,
                               gather_stream=None):

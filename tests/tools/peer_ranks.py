@@ -88,6 +88,43 @@ def main():
             check(int(total_rows[0]) == want.shape[0], f"batch {batch}: gathered row count {int(total_rows[0])} vs {want.shape[0]}")
             check(torch.equal(gathered[:want.shape[0]], want), f"batch {batch}: gathered records")
 
+    # ---- A2: the same through the public call: Projector.project_batch(records_to=0) / hit_records()
+    for use_peer in (True, False):
+        if not use_peer:
+            proj.peer.ctx.peer_close()                       # collective (every rank is here): back to the NCCL combiner
+            dist.barrier()
+            proj.peer = None
+            proj.combiner = BatchCombiner(ctx, None)
+        B = 2
+        heats = torch.rand((B, H, W), device=dev) * (0.6 + 0.1 * rank)
+        poses_b = np.stack([frame_pose(50 + 2 * rank + j) for j in range(B)])
+        ob = dict(pixel=torch.empty(B * n_px, dtype=torch.int32, device=dev), t_hit=torch.empty(B * n_px, device=dev),
+                  face=torch.empty(B * n_px, dtype=torch.int32, device=dev))
+        if use_peer:
+            check(proj.enable_peer(record_rows=B * n_px, result_rays=n_px), "enable_peer for a batch of two frames")
+        nb, hb = proj.project_batch(heats, K, poses_b, 0.5, out=ob, records_to=0)
+        mine = ctx.pack_records_device(ob["t_hit"], ob["face"], pixel=ob["pixel"], n=nb)
+        check(mine.shape[0] == hb, "records of this rank == its hit count")
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = mine.shape[0]
+        dist.all_reduce(sizes)
+        allrec = torch.zeros((int(sizes.sum()), 3), dtype=torch.int32, device=dev)
+        lo = int(sizes[:rank].sum())
+        allrec[lo:lo + mine.shape[0]] = mine
+        dist.all_reduce(allrec)                              # disjoint rows: the sum is the concatenation in rank order
+        got = proj.hit_records()
+        hist_b = proj.combined()[0]
+        torch.cuda.synchronize()
+        if rank == 0:
+            check(got is not None and got.shape == allrec.shape and torch.equal(got, allrec), f"hit_records() (peer={use_peer})")
+        else:
+            check(got is None, "hit_records() is None off the root")
+        tot = torch.tensor([hb], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        check(int(hist_b.sum()) == int(tot[0]), f"combined histogram counts every rank's hits (peer={use_peer})")
+    check(proj.enable_peer(record_rows=n_px, result_rays=n_px), "peer path back on")
+    ctx, comb = proj.ctx, proj.combiner
+
     # ---- B: ONE frame's rays sharded, results stored into every rank's window by the traversal
     for case in ("dense", "sparse"):
         hm = torch.ones((H, W), device=dev) if case == "dense" else torch.from_numpy(synth.blob_heatmap((H, W), seed=5)).to(dev)
