@@ -1307,14 +1307,23 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     int L = 0;
     if (knob_collapse_launches() == 0) {
         // one cooperative launch walks all levels (grid barriers instead of host round trips), one read-back at the end
-        static int coop_grid = 0;
-        if (coop_grid == 0) {
+        static int coop_sms = 0, coop_per_sm = 0, coop_want = 0;
+        if (coop_sms == 0) {
             int dev = 0, sms = 0, per_sm = 0;
             if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
             if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
             if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_all, 256, 0)) != cudaSuccess) return e;
-            coop_grid = sms * (per_sm > 0 ? per_sm : 1);
+            const char *cp = getenv("DP_COOP_PER_SM");             // A/B: blocks per SM of the cooperative launch
+            coop_want = cp ? atoi(cp) : 0;
+            coop_per_sm = per_sm > 0 ? per_sm : 1;
+            coop_sms = sms;
         }
+        // Every level ends in one or two grid barriers, whose cost grows with the number of blocks: up to ~2M triangles
+        // the levels are short and three blocks per SM are enough (500k: 0.645 -> 0.617 ms, 1M: 0.893 -> 0.863 ms); the
+        // long levels of larger meshes want every resident block (5M: 2.70 ms with five, 2.74 with three)
+        int per_sm_now = coop_want > 0 ? coop_want : (n <= 2000000 ? 3 : coop_per_sm);
+        if (per_sm_now > coop_per_sm) per_sm_now = coop_per_sm;
+        const int coop_grid = coop_sms * per_sm_now;
         if ((e = cudaMemsetAsync(cres, 0, sizeof(CollapseResult), s)) != cudaSuccess) return e;
         void *kargs[] = {&ca, &cres};
         if ((e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_collapse_all), dim3(coop_grid), dim3(256), kargs, 0, s)) !=
