@@ -122,33 +122,41 @@ __global__ void k_morton(const float *__restrict__ V, const int32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// LSD radix sort, 8 bits per pass, stable.  Tile = 256 threads x 16 keys; every warp owns a
-// contiguous 512-key slice of the tile so that warp-local ranks (match_any) are stable.
+// LSD radix sort, RS_BITS = 10 bits per pass, stable: 30-bit Morton codes take three passes (8-bit digits took four),
+// the cell keys of the point-cloud grids two.  Tile = 256 threads x 16 keys; every warp owns a contiguous 512-key slice
+// of the tile so that warp-local ranks (match_any) are stable.
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
+#ifndef DP_RS_BITS
+#define DP_RS_BITS 10
+#endif
+constexpr int RS_BITS = DP_RS_BITS;
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_DPT = RS_BINS / RS_THREADS;     // digits per thread where a thread owns digits
+static_assert(RS_BINS % RS_THREADS == 0 && RS_DPT >= 1, "digits are dealt out to the threads of a block");
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(const uint32_t *__restrict__ keys, long long n, int shift, uint32_t *__restrict__ table, int nblocks)
 {
-    __shared__ unsigned h[256];
-    h[threadIdx.x] = 0;
+    __shared__ unsigned h[RS_BINS];
+    for (int k = threadIdx.x; k < RS_BINS; k += RS_THREADS) h[k] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * RS_TILE;
 #pragma unroll 4
     for (int r = 0; r < RS_ITEMS; ++r) {
         const long long i = base + r * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xffu], 1u);
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & (RS_BINS - 1)], 1u);
     }
     __syncthreads();
-    table[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+    for (int k = threadIdx.x; k < RS_BINS; k += RS_THREADS) table[(long long)k * nblocks + blockIdx.x] = h[k];
 }
 
 // Digit table: table[d * nb + b] = count of digit d in tile b.  One block per digit scans its row in place
 // (exclusive, over the tiles) and leaves the row total in totals[d]; the scatter kernel adds the exclusive scan of
-// the 256 totals itself.
+// the digit totals itself.
 __global__ void __launch_bounds__(256) k_rs_scan_rows(uint32_t *table, int nb, uint32_t *totals)
 {
     __shared__ unsigned s_warp[8];
@@ -189,10 +197,10 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
              uint32_t *__restrict__ vals_out, long long n, int shift, const uint32_t *__restrict__ table, int nblocks,
              const uint32_t *__restrict__ totals)
 {
-    __shared__ unsigned cnt[RS_WARPS][256];
+    __shared__ unsigned cnt[RS_WARPS][RS_BINS];
     __shared__ unsigned s_wsum[RS_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < RS_WARPS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+    for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * RS_TILE + (long long)warp * (32 * RS_ITEMS);
     uint32_t key[RS_ITEMS], val[RS_ITEMS];
@@ -204,7 +212,7 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
         const bool ok = i < n;
         key[r] = ok ? keys[i] : 0u;
         val[r] = ok ? vals[i] : 0u;
-        const unsigned digit = ok ? ((key[r] >> shift) & 0xffu) : (0x100u | (unsigned)lane);
+        const unsigned digit = ok ? ((key[r] >> shift) & (RS_BINS - 1)) : ((unsigned)RS_BINS | (unsigned)lane);
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         unsigned pre = 0;
         if (ok) pre = cnt[warp][digit];
@@ -215,9 +223,11 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
     }
     __syncthreads();
     {
-        // exclusive scan of the 256 digit totals (thread d owns digit d)
-        const unsigned tot = totals[tid];
-        unsigned inc = tot;
+        // exclusive scan of the digit totals: thread t owns the RS_DPT consecutive digits t * RS_DPT ...
+        unsigned tot[RS_DPT], mine = 0;
+#pragma unroll
+        for (int q = 0; q < RS_DPT; ++q) { tot[q] = totals[tid * RS_DPT + q]; mine += tot[q]; }
+        unsigned inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
@@ -225,17 +235,22 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
         }
         if (lane == 31) s_wsum[warp] = inc;
         __syncthreads();
-        unsigned dbase = inc - tot;
+        unsigned dbase = inc - mine;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w)
             if (w < warp) dbase += s_wsum[w];
-        // thread d turns the per-warp counts of digit d into starting offsets
-        unsigned run = dbase + table[(long long)tid * nblocks + blockIdx.x];
+        // ... and turns the per-warp counts of each of them into starting offsets
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const unsigned c = cnt[w][tid];
-            cnt[w][tid] = run;
-            run += c;
+        for (int q = 0; q < RS_DPT; ++q) {
+            const int d = tid * RS_DPT + q;
+            unsigned run = dbase + table[(long long)d * nblocks + blockIdx.x];
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) {
+                const unsigned c = cnt[w][d];
+                cnt[w][d] = run;
+                run += c;
+            }
+            dbase += tot[q];
         }
     }
     __syncthreads();
@@ -243,7 +258,7 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
     for (int r = 0; r < RS_ITEMS; ++r) {
         const long long i = base + r * 32 + lane;
         if (i < n) {
-            const unsigned digit = (key[r] >> shift) & 0xffu;
+            const unsigned digit = (key[r] >> shift) & (RS_BINS - 1);
             const unsigned pos = cnt[warp][digit] + rank[r];
             keys_out[pos] = key[r];
             vals_out[pos] = val[r];
@@ -1136,25 +1151,30 @@ cudaError_t ensure_scratch(void **scratch, size_t *have, size_t need)
 size_t radix_table_entries(int64_t n)
 {
     const int64_t nb = (n + RS_TILE - 1) / RS_TILE;
-    return (size_t)(256 * (nb > 0 ? nb : 1) + 256);      // counts per (digit, tile) + the 256 digit totals
+    return (size_t)((size_t)RS_BINS * (nb > 0 ? nb : 1) + RS_BINS);      // counts per (digit, tile) + the digit totals
 }
 
+// key_bits: the keys are below 2^key_bits (32 = anything).  An odd number of passes leaves the result in the _tmp
+// arrays: *result_in_tmp tells.
 cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
-                             uint32_t *table, cudaStream_t s, bool *result_in_tmp)
+                             uint32_t *table, cudaStream_t s, bool *result_in_tmp, int key_bits)
 {
     *result_in_tmp = false;
     if (n <= 1) return cudaSuccess;
+    if (key_bits < 1 || key_bits > 32) key_bits = 32;
+    const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
     const int nb = (int)((n + RS_TILE - 1) / RS_TILE);
     uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 8 * pass;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = RS_BITS * pass;
         k_rs_hist<<<nb, RS_THREADS, 0, s>>>(ki, n, shift, table, nb);
-        k_rs_scan_rows<<<256, 256, 0, s>>>(table, nb, table + 256ll * nb);
-        k_rs_scatter<<<nb, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, table, nb, table + 256ll * nb);
+        k_rs_scan_rows<<<RS_BINS, 256, 0, s>>>(table, nb, table + (long long)RS_BINS * nb);
+        k_rs_scatter<<<nb, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, table, nb, table + (long long)RS_BINS * nb);
         uint32_t *t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
     }
-    return cudaGetLastError();   // 4 passes: the result is back in keys / vals
+    *result_in_tmp = (passes & 1) != 0;
+    return cudaGetLastError();
 }
 
 // DP_COLLAPSE=0 selects the greedy largest-area expansion everywhere (kept for A/B measurements); DP_CPRIM overrides
@@ -1280,7 +1300,8 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     }
     bool in_tmp = false;
-    if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, n, table, s, &in_tmp)) != cudaSuccess) return e;
+    if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, n, table, s, &in_tmp, 30)) != cudaSuccess) return e;   // 30-bit Morton codes
+    if (in_tmp) { uint32_t *t = keys; keys = keys_t; keys_t = t; t = vals; vals = vals_t; vals_t = t; }
 
     if ((e = cudaMemsetAsync(parent, 0xff, 2 * N * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;

@@ -338,7 +338,7 @@ cudaError_t pose_and_refit(const void *V, int vdtype, int64_t nV, const int32_t 
 cudaError_t convert_f64_to_f32(const double *src, float *dst, int64_t n, cudaStream_t s);
 cudaError_t check_faces(const int32_t *F, int64_t nF, int64_t nV, int *d_flag, cudaStream_t s);
 cudaError_t radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
-                             uint32_t *table, cudaStream_t s, bool *result_in_tmp);
+                             uint32_t *table, cudaStream_t s, bool *result_in_tmp, int key_bits = 32);
 size_t radix_table_entries(int64_t n);
 
 }  // namespace dp

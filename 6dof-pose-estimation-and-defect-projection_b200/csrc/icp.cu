@@ -325,7 +325,10 @@ cudaError_t icp_grid_build(const double *tp, const double *tn, int64_t m, double
     if (cells < min_cells) return cudaSuccess;
     k_icp_grid_keys<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(tp, m, g, keys, vals);
     bool in_tmp = false;
-    if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, m, table, s, &in_tmp)) != cudaSuccess) return e;
+    int key_bits = 1;
+    while (key_bits < 32 && ((size_t)1 << key_bits) < cells) ++key_bits;              // cell keys are below `cells`
+    if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, m, table, s, &in_tmp, key_bits)) != cudaSuccess) return e;
+    if (in_tmp) { uint32_t *t = keys; keys = keys_t; keys_t = t; t = vals; vals = vals_t; vals_t = t; }
     if ((e = cudaMemsetAsync(cell_start, 0, cells * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(cell_end, 0, cells * 4, s)) != cudaSuccess) return e;
     k_icp_grid_gather<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(tp, tn, keys, vals, m, tps, tns, cell_start, cell_end);
