@@ -100,11 +100,15 @@ __device__ __forceinline__ unsigned expand10(unsigned v)
 }
 
 // code = interleave(x,y,z), x most significant; cell = min(1023, (c - lo) * (1024/ext))
+// (also clears the binary tree's parent links and completion flags for the passes that follow: two memsets less in
+// the build's stream)
 __global__ void k_morton(const float *__restrict__ V, const int32_t *__restrict__ F, long long n,
-                         const float *__restrict__ sbounds, uint32_t *keys, uint32_t *vals)
+                         const float *__restrict__ sbounds, uint32_t *keys, uint32_t *vals, int32_t *parent, int *flags)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (parent) { parent[2 * i] = -1; parent[2 * i + 1] = -1; }
+    if (flags) flags[i] = 0;
     float lo[3], hi[3];
     tri_box(V, F, i, lo, hi);
     unsigned q[3];
@@ -522,9 +526,14 @@ __device__ __forceinline__ void try_rotate(long long cur, long long n, int32_t *
 __global__ void k_binfit(const float *__restrict__ V, const int32_t *__restrict__ F, const uint32_t *__restrict__ sorted_tri,
                          long long n, int32_t *parent, int32_t *left, int32_t *right, const int32_t *first, int32_t *last,
                          float *bbox, int *flags, float *ctab, float c_prim, int rot_min, int rot_max, int rot_gg,
-                         BinRec *rec)
+                         BinRec *rec, unsigned *counters, int32_t *wroot, unsigned *cres_words, int n_cres_words)
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // the collapse's start state (node 0 = the root, its counters, the cooperative launch's result / barrier block):
+    // written here instead of by three small copies in the stream
+    if (counters && j < 4) counters[j] = j == 0 ? 1u : 0u;
+    if (wroot && j == 0) wroot[0] = 0;
+    if (cres_words && j < n_cres_words) cres_words[j] = 0u;
     if (j >= n) return;
     float lo[3], hi[3];
     tri_box(V, F, sorted_tri[j], lo, hi);
@@ -592,6 +601,7 @@ struct CollapseArgs {
     int32_t *sel;
     long long cap_nodes;
     const BinRec *rec;                 // per internal binary node: children, count, area, cut decisions
+    unsigned *arrived;                 // [cap_nodes] arrival counters of the bottom-up fit, cleared as the nodes are emitted
 };
 
 // one wide node `w` of the level that starts at `begin`; MODE 1: called by ONE thread (gl = 0), else by the eight lanes
@@ -836,6 +846,7 @@ __device__ __forceinline__ void collapse_node(const CollapseArgs &A, long long w
     if (gl == 0 && active) {
         nodes[w].w[0] = make_uint4(0u, 0u, 0u, ibit << 24);
         nodes[w].w[1] = make_uint4(cbase, tbase, meta_lo, meta_hi);
+        if (A.arrived) A.arrived[w] = 0u;                   // the fit's arrival counter of this node starts at zero
     }
 }
 
@@ -1294,7 +1305,7 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         topo.level_begin[1] = 1;
         return cudaSuccess;
     }
-    k_morton<<<blocks_for(n, 256), 256, 0, s>>>(V, F, n, sbounds, keys, vals);
+    k_morton<<<blocks_for(n, 256), 256, 0, s>>>(V, F, n, sbounds, keys, vals, parent, flags);
     if (morton_out_host) {
         if ((e = cudaMemcpyAsync(morton_out_host, keys, n * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -1303,27 +1314,24 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     if ((e = radix_sort_pairs(keys, vals, keys_t, vals_t, n, table, s, &in_tmp, 30)) != cudaSuccess) return e;   // 30-bit Morton codes
     if (in_tmp) { uint32_t *t = keys; keys = keys_t; keys_t = t; t = vals; vals = vals_t; vals_t = t; }
 
-    if ((e = cudaMemsetAsync(parent, 0xff, 2 * N * 4, s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
     if (n > 1) k_karras<<<blocks_for(n - 1, 256), 256, 0, s>>>(keys, n, left, right, parent, first, last);
-    k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, bbox, flags, ctab, c_prim,
-                                                knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec);
+    static_assert(sizeof(CollapseResult) % 4 == 0, "the result block is cleared word by word");
+    const int n_cres_words = (int)(sizeof(CollapseResult) / 4);
+    k_binfit<<<blocks_for(n > n_cres_words ? n : n_cres_words, 256), 256, 0, s>>>(
+        V, F, vals, n, parent, left, right, first, last, bbox, flags, ctab, c_prim, knob_rotate_min(), knob_rotate_max(),
+        knob_rotate_gg(), rec, counters, wroot, reinterpret_cast<unsigned *>(cres), n_cres_words);
     // further rotation passes over the rotated tree (each node looks at its new grandchildren once more)
     for (int pass = 1; pass < knob_rotate_passes() && knob_rotate_max() > 0; ++pass) {
         if ((e = cudaMemsetAsync(flags, 0, N * 4, s)) != cudaSuccess) return e;
         k_binfit<<<blocks_for(n, 256), 256, 0, s>>>(V, F, vals, n, parent, left, right, first, last, bbox, flags, ctab,
-                                                    c_prim, knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec);
+                                                    c_prim, knob_rotate_min(), knob_rotate_max(), knob_rotate_gg(), rec,
+                                                    nullptr, nullptr, nullptr, 0);
     }
 
     // top-down collapse, one launch per level of the wide tree
-    {
-        const unsigned init[4] = {1u, 0u, 0u, 0u};    // node 0 is the root
-        const int32_t root_id = 0;
-        if ((e = cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(wroot, &root_id, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
-    }
+    // (counters = {1, 0, 0, 0}: node 0 is the root; wroot[0] = 0; the result block zeroed: all written by k_binfit)
     CollapseArgs ca{n, left, right, first, last, bbox, vals, wroot, out.nodes, topo.tri_face, counters, ctab, c_prim,
-                    knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes, rec};
+                    knob_sah_collapse(), topo.wparent, knob_dp_max_count(), selbuf, out.cap_nodes, rec, topo.arrived};
     long long begin = 0, end = 1;
     int L = 0;
     if (knob_collapse_launches() == 0) {
@@ -1345,7 +1353,6 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
         int per_sm_now = coop_want > 0 ? coop_want : (n <= 2000000 ? 3 : coop_per_sm);
         if (per_sm_now > coop_per_sm) per_sm_now = coop_per_sm;
         const int coop_grid = coop_sms * per_sm_now;
-        if ((e = cudaMemsetAsync(cres, 0, sizeof(CollapseResult), s)) != cudaSuccess) return e;
         void *kargs[] = {&ca, &cres};
         if ((e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_collapse_all), dim3(coop_grid), dim3(256), kargs, 0, s)) !=
             cudaSuccess)
@@ -1380,7 +1387,6 @@ cudaError_t build_lbvh(const float *V, int64_t nV, const int32_t *F, int64_t nF,
     }
     topo.n_levels = L;
     out.n_nodes = end;
-    if ((e = cudaMemsetAsync(topo.arrived, 0, (size_t)out.n_nodes * 4, s)) != cudaSuccess) return e;
     k_fit_all<<<blocks_for(out.n_nodes * 8, 256), 256, 0, s>>>(out.n_nodes, out.nodes, out.nodes, out.tris, out.wlo, out.whi,
                                                            out.d_scale, V, F, topo.tri_face, topo.wparent, topo.arrived, out.fat);
     return cudaGetLastError();
